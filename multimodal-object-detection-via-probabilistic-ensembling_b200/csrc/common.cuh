@@ -1,0 +1,36 @@
+// Shared helpers for libprobenb200 (sm_100a).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "../../include/probenb200.h"
+
+namespace pe {
+
+void set_last_error(cudaError_t e, const char* where);
+
+#define PE_CUDA_CHECK(expr)                                    \
+  do {                                                         \
+    cudaError_t _e = (expr);                                   \
+    if (_e != cudaSuccess) {                                   \
+      ::pe::set_last_error(_e, #expr);                         \
+      return PE_ERR_CUDA;                                      \
+    }                                                          \
+  } while (0)
+
+#define PE_LAUNCH_CHECK()                                      \
+  do {                                                         \
+    cudaError_t _e = cudaGetLastError();                       \
+    if (_e != cudaSuccess) {                                   \
+      ::pe::set_last_error(_e, "kernel launch");               \
+      return PE_ERR_CUDA;                                      \
+    }                                                          \
+  } while (0)
+
+constexpr unsigned kFullMask = 0xffffffffu;
+
+int sm_count();
+
+template <typename T>
+__host__ __device__ constexpr T ceil_div(T a, T b) { return (a + b - 1) / b; }
+
+}  // namespace pe

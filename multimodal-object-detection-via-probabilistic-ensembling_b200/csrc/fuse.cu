@@ -1,0 +1,571 @@
+// ProbEn late fusion on sm_100a: cross-model IoU match + score fusion + box fusion + per-class NMS,
+// one launch for a whole batch of images.
+//
+// Replaces the Python loop of the reference's demo/FLIR/demo_probEn.py (:189-196 fusion, :92-187
+// nms_bayesian, :32-42 bayesian_fusion_multiclass, :73-77 weighted_box_fusion, :44-71 nms_1, :236-267
+// per-image dispatch).  See include/probenb200.h for the data layout.
+//
+// Mapping: one WARP per image when the image has <= 32 detections over all models (the realistic
+// regime: score>0.5 leaves tens), lane j <-> detection j; each lane loads its record with coalesced
+// loads (float4 box), the sort is rank-by-counting over warp shuffles, the greedy clustering walks
+// cluster heads with redux.sync min + ballot, members are folded into their head with shuffles.
+// Images with 33..1024 detections are appended to a work list and handled by a block-per-image kernel
+// that stages the records in shared memory and materialises the suppression bitmask there.
+//
+// Numerics: the reference works in float64 on float32-exact inputs.  Membership (iou > thr) is decided
+// in float32 and re-evaluated with the reference's exact float64 expression whenever the float32 margin
+// is within 1e-5 of the threshold, so cluster membership is decision-exact; box fusion accumulates in
+// float64; probEn log/exp run in float32 with the background mass 1-sum(p) formed in float64 (its sign
+// drives the reference's NaN behaviour).
+#include <math.h>
+#include "common.cuh"
+
+namespace pe {
+namespace {
+
+constexpr int kMaxBlockDets = 1024;  // cap for the block-per-image path
+constexpr int kBlockThreads = 256;
+
+struct FuseArgs {
+  const float4* boxes;
+  const float* scores;
+  const int* classes;
+  const float* probs;
+  const float* vars;
+  const int* offs;
+  int B, M;
+  float thr;
+  int score_mode, box_mode;
+  float img_w, img_h;
+  float4* out_boxes;
+  float* out_scores;
+  int* out_classes;
+  int* out_counts;
+  int* big_count;  // workspace[0]
+  int* big_list;   // workspace[1..B]
+};
+
+// ---- IoU decisions ---------------------------------------------------------------------------------
+
+// Reference expression, float64, legacy +1 areas and class offsets (demo_probEn.py:100-105,115-123).
+__device__ __noinline__ bool match_exact_f64(float4 a, int ca, float4 b, int cb, float img_w, float img_h,
+                                             float thr) {
+  const double W = (double)img_w, H = (double)img_h;
+  const double ax1 = __dadd_rn((double)a.x, __dmul_rn((double)ca, W));
+  const double ay1 = __dadd_rn((double)a.y, __dmul_rn((double)ca, H));
+  const double ax2 = __dadd_rn((double)a.z, __dmul_rn((double)ca, W));
+  const double ay2 = __dadd_rn((double)a.w, __dmul_rn((double)ca, H));
+  const double bx1 = __dadd_rn((double)b.x, __dmul_rn((double)cb, W));
+  const double by1 = __dadd_rn((double)b.y, __dmul_rn((double)cb, H));
+  const double bx2 = __dadd_rn((double)b.z, __dmul_rn((double)cb, W));
+  const double by2 = __dadd_rn((double)b.w, __dmul_rn((double)cb, H));
+  const double aa = __dmul_rn(__dadd_rn(__dsub_rn(ax2, ax1), 1.0), __dadd_rn(__dsub_rn(ay2, ay1), 1.0));
+  const double ab = __dmul_rn(__dadd_rn(__dsub_rn(bx2, bx1), 1.0), __dadd_rn(__dsub_rn(by2, by1), 1.0));
+  const double w = fmax(0.0, __dadd_rn(__dsub_rn(fmin(ax2, bx2), fmax(ax1, bx1)), 1.0));
+  const double h = fmax(0.0, __dadd_rn(__dsub_rn(fmin(ay2, by2), fmax(ay1, by1)), 1.0));
+  const double inter = __dmul_rn(w, h);
+  const double ovr = __ddiv_rn(inter, __dsub_rn(__dadd_rn(aa, ab), inter));
+  return ovr > (double)thr;
+}
+
+// Decision-exact "iou(head, cand) > thr" for the bayesian path.  area_* are float32 (+1) areas.
+__device__ __forceinline__ bool match_bayes(float4 h, int hc, float harea, float4 c, int cc, float carea,
+                                            float img_w, float img_h, float thr) {
+  if (hc == cc) {
+    const float w = fmaxf(0.f, fminf(h.z, c.z) - fmaxf(h.x, c.x) + 1.f);
+    const float hh = fmaxf(0.f, fminf(h.w, c.w) - fmaxf(h.y, c.y) + 1.f);
+    const float inter = w * hh;
+    const float uni = harea + carea - inter;
+    const float d = inter - thr * uni;
+    if (fabsf(d) <= 1e-5f * fabsf(uni)) return match_exact_f64(h, hc, c, cc, img_w, img_h, thr);
+    return d > 0.f && uni > 0.f ? true : (uni > 0.f ? false : match_exact_f64(h, hc, c, cc, img_w, img_h, thr));
+  }
+  // different classes live in different offset tiles; they can only touch through the +1 border.
+  const float dx = (float)(cc - hc) * img_w, dy = (float)(cc - hc) * img_h;
+  const float w = fminf(h.z, c.z + dx) - fmaxf(h.x, c.x + dx) + 1.f;
+  const float hh = fminf(h.w, c.w + dy) - fmaxf(h.y, c.y + dy) + 1.f;
+  if (w > -0.01f && hh > -0.01f) return match_exact_f64(h, hc, c, cc, img_w, img_h, thr);
+  return false;
+}
+
+// torchvision nms float32 expression on coordinate-offset boxes (no FMA contraction).
+__device__ __forceinline__ float nms_area(float4 b) {
+  return __fmul_rn(__fsub_rn(b.z, b.x), __fsub_rn(b.w, b.y));
+}
+__device__ __forceinline__ bool match_nms(float4 h, float harea, float4 c, float carea, float thr) {
+  const float w = fmaxf(0.f, __fsub_rn(fminf(h.z, c.z), fmaxf(h.x, c.x)));
+  const float hh = fmaxf(0.f, __fsub_rn(fminf(h.w, c.w), fmaxf(h.y, c.y)));
+  const float inter = __fmul_rn(w, hh);
+  const float ovr = __fdiv_rn(inter, __fsub_rn(__fadd_rn(harea, carea), inter));
+  return ovr > thr;
+}
+__device__ __forceinline__ float4 offset_box(float4 b, float off) {
+  return make_float4(__fadd_rn(b.x, off), __fadd_rn(b.y, off), __fadd_rn(b.z, off), __fadd_rn(b.w, off));
+}
+
+// ---- per-detection precomputation for the fusion stage -------------------------------------------------
+
+template <int K>
+struct DetAux {
+  float lg[K + 1];  // log p_k, log(1 - sum p)
+  bool bad;         // reference would take log of a negative number -> NaN posterior
+  float pmax;       // max_k p_k  (score_mode max reads probs, not scores)
+  double wgt;       // box-fusion weight
+};
+
+template <int K>
+__device__ __forceinline__ DetAux<K> make_aux(const float* p, float score, float var, int box_mode) {
+  DetAux<K> a;
+  double s = 0.0;
+  a.bad = false;
+  a.pmax = -INFINITY;
+#pragma unroll
+  for (int k = 0; k < K; ++k) {
+    s = __dadd_rn(s, (double)p[k]);
+    a.lg[k] = logf(p[k]);
+    a.bad |= (p[k] < 0.f);
+    a.pmax = fmaxf(a.pmax, p[k]);
+  }
+  const double bg = __dsub_rn(1.0, s);
+  a.bad |= (bg < 0.0);
+  a.lg[K] = logf((float)bg);
+  a.wgt = box_mode == PE_BOX_VAVG ? __ddiv_rn(1.0, (double)var) : (box_mode == PE_BOX_SAVG ? (double)score : 1.0);
+  return a;
+}
+
+// Posterior of the product model (demo_probEn.py:32-42) from summed logs; max-subtracted softmax.
+template <int K>
+__device__ __forceinline__ void probEn_finish(const float* S, bool bad, float* score, int* cls) {
+  if (bad) { *score = __int_as_float(0x7fc00000); *cls = 0; return; }
+  float mx = S[0];
+  int am = 0;
+#pragma unroll
+  for (int k = 1; k <= K; ++k)
+    if (S[k] > mx) { mx = S[k]; am = k; }
+  float den = 0.f;
+#pragma unroll
+  for (int k = 0; k <= K; ++k) den += expf(S[k] - mx);
+  const float r = 1.f / den;  // exp(mx - mx) == 1
+  if (r != r) { *score = r; *cls = 0; return; }
+  *score = r;
+  *cls = am;
+}
+
+// ---- warp-per-image kernel ---------------------------------------------------------------------------
+
+__device__ __forceinline__ float4 shfl4(float4 v, int src) {
+  return make_float4(__shfl_sync(kFullMask, v.x, src), __shfl_sync(kFullMask, v.y, src),
+                     __shfl_sync(kFullMask, v.z, src), __shfl_sync(kFullMask, v.w, src));
+}
+
+template <int K>
+__global__ void __launch_bounds__(kBlockThreads) fuse_warp_kernel(const FuseArgs a) {
+  const int lane = threadIdx.x & 31;
+  const int warps_total = (gridDim.x * blockDim.x) >> 5;
+  const bool nms_path = a.score_mode == PE_SCORE_MAX && a.box_mode == PE_BOX_ARGMAX;
+
+  for (int img = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; img < a.B; img += warps_total) {
+    const int o = lane <= a.M ? __ldg(a.offs + (size_t)img * a.M + lane) : 0;
+    const int base = __shfl_sync(kFullMask, o, 0);
+    const int n = __shfl_sync(kFullMask, o, a.M) - base;
+    const int len = __shfl_down_sync(kFullMask, o, 1) - o;
+    const int live = __popc(__ballot_sync(kFullMask, lane < a.M && len > 0));
+    if (n <= 0) {
+      if (lane == 0) a.out_counts[img] = 0;
+      continue;
+    }
+    if (n > 32) {
+      if (lane == 0) {
+        if (n > kMaxBlockDets) a.out_counts[img] = -1;
+        else a.big_list[atomicAdd(a.big_count, 1)] = img;
+      }
+      continue;
+    }
+    const bool act = lane < n;
+    const int row = base + (act ? lane : 0);
+    const float4 box = __ldg(a.boxes + row);
+    const float score = __ldg(a.scores + row);
+    const int cls = __ldg(a.classes + row);
+    if (live == 1) {  // single contributing model: pass-through in input order (demo_probEn.py:240-252)
+      if (act) {
+        a.out_boxes[row] = box;
+        a.out_scores[row] = score;
+        a.out_classes[row] = cls;
+      }
+      if (lane == 0) a.out_counts[img] = n;
+      continue;
+    }
+
+    // ---- order: rank by counting.  bayes: ties -> higher index first; nms: stable (lower index first)
+    int rank = 0;
+    for (int k = 0; k < n; ++k) {
+      const float sk = __shfl_sync(kFullMask, score, k);
+      rank += (sk > score) || (sk == score && (nms_path ? k < lane : k > lane));
+    }
+
+    float4 mbox = box;  // box used for matching
+    float area;
+    if (nms_path) {
+      float mc = act ? fmaxf(fmaxf(box.x, box.y), fmaxf(box.z, box.w)) : -INFINITY;
+#pragma unroll
+      for (int s = 16; s > 0; s >>= 1) mc = fmaxf(mc, __shfl_xor_sync(kFullMask, mc, s));
+      mbox = offset_box(box, __fmul_rn((float)cls, __fadd_rn(mc, 1.f)));
+      area = nms_area(mbox);
+    } else {
+      area = (box.z - box.x + 1.f) * (box.w - box.y + 1.f);
+    }
+
+    // ---- greedy clustering over heads in rank order
+    unsigned removed = n == 32 ? 0u : ~((1u << n) - 1u);
+    unsigned my_cluster = 0;
+    int my_pos = -1, nheads = 0;
+    while (true) {
+      const unsigned key = ((removed >> lane) & 1u) ? 0xffffffffu : ((unsigned)rank << 5 | (unsigned)lane);
+      const unsigned mn = __reduce_min_sync(kFullMask, key);
+      if (mn == 0xffffffffu) break;
+      const int hl = mn & 31;
+      const float4 hb = shfl4(mbox, hl);
+      const int hc = __shfl_sync(kFullMask, cls, hl);
+      const float ha = __shfl_sync(kFullMask, area, hl);
+      bool m = false;
+      if (!((removed >> lane) & 1u) && lane != hl)
+        m = nms_path ? match_nms(hb, ha, mbox, area, a.thr)
+                     : match_bayes(hb, hc, ha, mbox, cls, area, a.img_w, a.img_h, a.thr);
+      const unsigned mm = __ballot_sync(kFullMask, m);
+      if (lane == hl) { my_cluster = mm; my_pos = nheads; }
+      removed |= mm | (1u << hl);
+      ++nheads;
+    }
+    if (lane == 0) a.out_counts[img] = nheads;
+
+    if (nms_path) {  // survivors keep their own record (demo_probEn.py:66-69)
+      if (my_pos >= 0) {
+        a.out_boxes[base + my_pos] = box;
+        a.out_scores[base + my_pos] = score;
+        a.out_classes[base + my_pos] = cls;
+      }
+      continue;
+    }
+
+    // ---- fold members into heads
+    float pr[K];
+#pragma unroll
+    for (int k = 0; k < K; ++k) pr[k] = act ? __ldg(a.probs + (size_t)row * K + k) : 0.5f / K;
+    const float var = act ? __ldg(a.vars + row) : 1.f;
+    const DetAux<K> me = make_aux<K>(pr, score, var, a.box_mode);
+
+    float S[K + 1];
+#pragma unroll
+    for (int k = 0; k <= K; ++k) S[k] = me.lg[k];
+    bool bad = me.bad;
+    float pmax = me.pmax;
+    double ssum = (double)score, wsum = me.wgt;
+    double bx = me.wgt * (double)box.x, by = me.wgt * (double)box.y, bz = me.wgt * (double)box.z,
+           bw = me.wgt * (double)box.w;
+    int cnt = 1;
+    int best_rank = 0x7fffffff;  // argmax box: earliest member whose score ties the head's
+    float4 best_box = box;
+    unsigned rem = my_cluster;
+    while (__any_sync(kFullMask, rem != 0u)) {
+      const bool has = rem != 0u;
+      const int src = has ? __ffs(rem) - 1 : lane;
+      rem &= rem - 1u;
+      const float4 ob = shfl4(box, src);
+      const float os = __shfl_sync(kFullMask, score, src);
+      const int orank = __shfl_sync(kFullMask, rank, src);
+      const double ow = __shfl_sync(kFullMask, me.wgt, src);
+      const float opmax = __shfl_sync(kFullMask, me.pmax, src);
+      const bool obad = __shfl_sync(kFullMask, (int)me.bad, src);
+      float ol[K + 1];
+#pragma unroll
+      for (int k = 0; k <= K; ++k) ol[k] = __shfl_sync(kFullMask, me.lg[k], src);
+      if (has) {
+#pragma unroll
+        for (int k = 0; k <= K; ++k) S[k] += ol[k];
+        bad |= obad;
+        pmax = fmaxf(pmax, opmax);
+        ssum += (double)os;
+        wsum += ow;
+        bx += ow * (double)ob.x; by += ow * (double)ob.y; bz += ow * (double)ob.z; bw += ow * (double)ob.w;
+        ++cnt;
+        if (os == score && orank < best_rank) { best_rank = orank; best_box = ob; }
+      }
+    }
+    if (my_pos >= 0) {
+      float fs = score;
+      int fc = cls;
+      float4 fb = box;
+      if (cnt > 1) {
+        if (a.score_mode == PE_SCORE_PROBEN) probEn_finish<K>(S, bad, &fs, &fc);
+        else if (a.score_mode == PE_SCORE_AVG) fs = (float)(ssum / (double)cnt);
+        else fs = pmax;
+        if (a.box_mode == PE_BOX_ARGMAX) fb = best_box;
+        else {
+          const double inv = 1.0 / wsum;
+          fb = make_float4((float)(bx * inv), (float)(by * inv), (float)(bz * inv), (float)(bw * inv));
+        }
+      }
+      a.out_boxes[base + my_pos] = fb;
+      a.out_scores[base + my_pos] = fs;
+      a.out_classes[base + my_pos] = fc;
+    }
+  }
+}
+
+// ---- block-per-image kernel for 33..1024 detections ------------------------------------------------------
+
+template <int K>
+__global__ void __launch_bounds__(kBlockThreads) fuse_block_kernel(const FuseArgs a) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  float4* s_box = reinterpret_cast<float4*>(smem_raw);                 // original boxes, rank order
+  float4* s_mbox = s_box + kMaxBlockDets;                              // matching boxes (nms: offset)
+  float* s_score = reinterpret_cast<float*>(s_mbox + kMaxBlockDets);
+  float* s_area = s_score + kMaxBlockDets;
+  int* s_cls = reinterpret_cast<int*>(s_area + kMaxBlockDets);
+  int* s_src = s_cls + kMaxBlockDets;                                  // rank -> row offset in the image
+  int* s_pos = s_src + kMaxBlockDets;                                  // rank -> output position or -1
+  unsigned* s_mask = reinterpret_cast<unsigned*>(s_pos + kMaxBlockDets);  // [n][W]
+  __shared__ float s_red[kBlockThreads / 32];
+  __shared__ int s_nheads;
+
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const bool nms_path = a.score_mode == PE_SCORE_MAX && a.box_mode == PE_BOX_ARGMAX;
+  const int nbig = *a.big_count;
+
+  for (int bi = blockIdx.x; bi < nbig; bi += gridDim.x) {
+    const int img = a.big_list[bi];
+    const int base = a.offs[(size_t)img * a.M];
+    const int n = a.offs[(size_t)img * a.M + a.M] - base;
+    const int W = (n + 31) >> 5;
+    int live = 0;
+    for (int m = 0; m < a.M; ++m) live += a.offs[(size_t)img * a.M + m + 1] > a.offs[(size_t)img * a.M + m];
+    __syncthreads();  // previous iteration done with smem
+    if (live == 1) {
+      for (int j = tid; j < n; j += blockDim.x) {
+        a.out_boxes[base + j] = a.boxes[base + j];
+        a.out_scores[base + j] = a.scores[base + j];
+        a.out_classes[base + j] = a.classes[base + j];
+      }
+      if (tid == 0) a.out_counts[img] = n;
+      continue;
+    }
+    // stage scores (input order) in s_area, compute ranks, scatter records to rank order
+    for (int j = tid; j < n; j += blockDim.x) s_area[j] = a.scores[base + j];
+    float mc = -INFINITY;
+    __syncthreads();
+    for (int j = tid; j < n; j += blockDim.x) {
+      const float sj = s_area[j];
+      int rank = 0;
+      for (int k = 0; k < n; ++k) {
+        const float sk = s_area[k];
+        rank += (sk > sj) || (sk == sj && (nms_path ? k < j : k > j));
+      }
+      const float4 b = a.boxes[base + j];
+      s_box[rank] = b;
+      s_score[rank] = sj;
+      s_cls[rank] = a.classes[base + j];
+      s_src[rank] = j;
+      s_pos[rank] = -1;
+      mc = fmaxf(mc, fmaxf(fmaxf(b.x, b.y), fmaxf(b.z, b.w)));
+    }
+    if (nms_path) {  // block max of all coordinates
+#pragma unroll
+      for (int s = 16; s > 0; s >>= 1) mc = fmaxf(mc, __shfl_xor_sync(kFullMask, mc, s));
+      if (lane == 0) s_red[wid] = mc;
+    }
+    __syncthreads();
+    if (nms_path) {
+      mc = s_red[0];
+      for (int w = 1; w < kBlockThreads / 32; ++w) mc = fmaxf(mc, s_red[w]);
+    }
+    for (int r = tid; r < n; r += blockDim.x) {
+      const float4 b = s_box[r];
+      if (nms_path) {
+        const float4 ob = offset_box(b, __fmul_rn((float)s_cls[r], __fadd_rn(mc, 1.f)));
+        s_mbox[r] = ob;
+        s_area[r] = nms_area(ob);
+      } else {
+        s_mbox[r] = b;
+        s_area[r] = (b.z - b.x + 1.f) * (b.w - b.y + 1.f);
+      }
+    }
+    __syncthreads();
+    // suppression bitmask: word (i, w) holds bits j = 32w.. with j > i and iou(i, j) > thr
+    for (int item = tid; item < n * W; item += blockDim.x) {
+      const int i = item / W, w = item - i * W;
+      unsigned bits = 0;
+      if (w >= (i >> 5)) {
+        const float4 hb = s_mbox[i];
+        const float ha = s_area[i];
+        const int hc = s_cls[i];
+        const int j0 = w << 5;
+        for (int t = 0; t < 32; ++t) {
+          const int j = j0 + t;
+          if (j > i && j < n) {
+            const bool m = nms_path ? match_nms(hb, ha, s_mbox[j], s_area[j], a.thr)
+                                    : match_bayes(hb, hc, ha, s_mbox[j], s_cls[j], s_area[j], a.img_w, a.img_h, a.thr);
+            bits |= (unsigned)m << t;
+          }
+        }
+      }
+      s_mask[item] = bits;
+    }
+    __syncthreads();
+    // serial head scan by warp 0: lane w owns word w of the removed set (W <= 32)
+    if (wid == 0) {
+      unsigned removed = 0;
+      int nheads = 0;
+      for (int i = 0; i < n; ++i) {
+        const unsigned rw = __shfl_sync(kFullMask, removed, i >> 5);
+        if ((rw >> (i & 31)) & 1u) continue;
+        unsigned rowbits = 0;
+        if (lane < W) {
+          rowbits = s_mask[i * W + lane] & ~removed;
+          s_mask[i * W + lane] = rowbits;  // now: members of cluster i
+          removed |= rowbits;
+          if (lane == (i >> 5)) removed |= 1u << (i & 31);
+        }
+        if (lane == 0) s_pos[i] = nheads;
+        ++nheads;
+      }
+      if (lane == 0) { s_nheads = nheads; a.out_counts[img] = nheads; }
+    }
+    __syncthreads();
+    // one thread per head folds its members in rank order, head last (the reference's order)
+    for (int i = tid; i < n; i += blockDim.x) {
+      const int pos = s_pos[i];
+      if (pos < 0) continue;
+      const float4 hbox = s_box[i];
+      const float hscore = s_score[i];
+      float fs = hscore;
+      int fc = s_cls[i];
+      float4 fb = hbox;
+      if (!nms_path) {
+        float S[K + 1];
+#pragma unroll
+        for (int k = 0; k <= K; ++k) S[k] = 0.f;
+        bool bad = false;
+        float pmax = -INFINITY;
+        double ssum = 0.0, wsum = 0.0, bx = 0.0, by = 0.0, bz = 0.0, bw = 0.0;
+        int cnt = 0;
+        bool have_best = false;
+        float4 best_box = hbox;
+        auto fold = [&](int r) {
+          const int rowm = base + s_src[r];
+          float pr[K];
+#pragma unroll
+          for (int k = 0; k < K; ++k) pr[k] = a.probs[(size_t)rowm * K + k];
+          const DetAux<K> d = make_aux<K>(pr, s_score[r], a.vars[rowm], a.box_mode);
+          const float4 ob = s_box[r];
+#pragma unroll
+          for (int k = 0; k <= K; ++k) S[k] += d.lg[k];
+          bad |= d.bad;
+          pmax = fmaxf(pmax, d.pmax);
+          ssum += (double)s_score[r];
+          wsum += d.wgt;
+          bx += d.wgt * (double)ob.x; by += d.wgt * (double)ob.y; bz += d.wgt * (double)ob.z; bw += d.wgt * (double)ob.w;
+          ++cnt;
+          if (!have_best && s_score[r] == hscore) { have_best = true; best_box = ob; }
+        };
+        for (int w = i >> 5; w < W; ++w) {
+          unsigned bits = s_mask[i * W + w];
+          while (bits) {
+            const int t = __ffs(bits) - 1;
+            bits &= bits - 1u;
+            fold((w << 5) + t);
+          }
+        }
+        if (cnt > 0) {
+          fold(i);
+          if (a.score_mode == PE_SCORE_PROBEN) probEn_finish<K>(S, bad, &fs, &fc);
+          else if (a.score_mode == PE_SCORE_AVG) fs = (float)(ssum / (double)cnt);
+          else fs = pmax;
+          if (a.box_mode == PE_BOX_ARGMAX) fb = best_box;
+          else {
+            const double inv = 1.0 / wsum;
+            fb = make_float4((float)(bx * inv), (float)(by * inv), (float)(bz * inv), (float)(bw * inv));
+          }
+        }
+      }
+      a.out_boxes[base + pos] = fb;
+      a.out_scores[base + pos] = fs;
+      a.out_classes[base + pos] = fc;
+    }
+  }
+}
+
+constexpr size_t block_smem_bytes() {
+  return (size_t)kMaxBlockDets * (2 * sizeof(float4) + 2 * sizeof(float) + 3 * sizeof(int)) +
+         (size_t)kMaxBlockDets * (kMaxBlockDets / 32) * sizeof(unsigned);
+}
+
+template <int K>
+int launch_fuse(const FuseArgs& a, cudaStream_t st) {
+  PE_CUDA_CHECK(cudaMemsetAsync(a.big_count, 0, sizeof(int), st));
+  const int warps_per_block = kBlockThreads / 32;
+  const int sms = sm_count();
+  // persistent-style grid: a multiple of the SM count, at most 8 resident blocks per SM worth of warps
+  long long want = ceil_div<long long>(a.B, warps_per_block);
+  long long cap = (long long)sms * 8;
+  int grid = (int)(want < cap ? (want > 0 ? want : 1) : cap);
+  fuse_warp_kernel<K><<<grid, kBlockThreads, 0, st>>>(a);
+  PE_LAUNCH_CHECK();
+  static bool attr_set[8] = {false};
+  if (!attr_set[K]) {
+    PE_CUDA_CHECK(cudaFuncSetAttribute(fuse_block_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)block_smem_bytes()));
+    attr_set[K] = true;
+  }
+  const int grid_b = a.B < sms ? a.B : sms;
+  fuse_block_kernel<K><<<grid_b, kBlockThreads, block_smem_bytes(), st>>>(a);
+  PE_LAUNCH_CHECK();
+  return PE_OK;
+}
+
+}  // namespace
+}  // namespace pe
+
+extern "C" PE_API size_t pe_fuse_workspace_bytes(int B) { return sizeof(int) * ((size_t)(B > 0 ? B : 0) + 4); }
+
+extern "C" PE_API int pe_fuse_max_dets_per_image(void) { return pe::kMaxBlockDets; }
+
+extern "C" PE_API int pe_fuse_batch(const float* boxes, const float* scores, const int32_t* classes, const float* probs,
+                             const float* vars, const int32_t* det_offsets, int B, int M, int K, float iou_thr,
+                             int score_mode, int box_mode, float img_w, float img_h, float* out_boxes,
+                             float* out_scores, int32_t* out_classes, int32_t* out_counts, void* workspace,
+                             size_t workspace_bytes, void* stream) {
+  if (B < 0 || M < 1 || M > 31) return PE_ERR_INVALID_ARGUMENT;
+  if (score_mode < PE_SCORE_PROBEN || score_mode > PE_SCORE_MAX) return PE_ERR_INVALID_ARGUMENT;
+  if (box_mode < PE_BOX_VAVG || box_mode > PE_BOX_ARGMAX) return PE_ERR_INVALID_ARGUMENT;
+  if (B == 0) return PE_OK;
+  if (!det_offsets || !out_counts || !workspace) return PE_ERR_INVALID_ARGUMENT;
+  if (!boxes || !scores || !classes || !probs || !vars || !out_boxes || !out_scores || !out_classes)
+    return PE_ERR_INVALID_ARGUMENT;
+  if ((reinterpret_cast<uintptr_t>(boxes) & 15) || (reinterpret_cast<uintptr_t>(out_boxes) & 15))
+    return PE_ERR_INVALID_ARGUMENT;
+  if (workspace_bytes < pe_fuse_workspace_bytes(B)) return PE_ERR_WORKSPACE_TOO_SMALL;
+  pe::FuseArgs a;
+  a.boxes = reinterpret_cast<const float4*>(boxes);
+  a.scores = scores;
+  a.classes = classes;
+  a.probs = probs;
+  a.vars = vars;
+  a.offs = det_offsets;
+  a.B = B;
+  a.M = M;
+  a.thr = iou_thr;
+  a.score_mode = score_mode;
+  a.box_mode = box_mode;
+  a.img_w = img_w;
+  a.img_h = img_h;
+  a.out_boxes = reinterpret_cast<float4*>(out_boxes);
+  a.out_scores = out_scores;
+  a.out_classes = out_classes;
+  a.out_counts = out_counts;
+  a.big_count = reinterpret_cast<int*>(workspace);
+  a.big_list = a.big_count + 4;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (K == 1) return pe::launch_fuse<1>(a, st);
+  if (K == 3) return pe::launch_fuse<3>(a, st);
+  return PE_ERR_UNSUPPORTED;
+}
