@@ -71,6 +71,28 @@ PE_API int pe_fuse_batch(const float* boxes, const float* scores, const int32_t*
                   float* out_scores, int32_t* out_classes, int32_t* out_counts, void* workspace,
                   size_t workspace_bytes, void* stream);
 
+
+/* ------------------------------------------------------------------------------------------------
+ * Convolution / linear layer on tcgen05 tensor cores (implicit GEMM, TMA-fed, fp32 accumulate in TMEM).
+ * Replaces the cuDNN/cuBLAS calls behind detectron2.layers.Conv2d + FrozenBatchNorm2d (folded into w/bias,
+ * detectron2/layers/batch_norm.py:45-64) on the detector path: modeling/backbone/resnet.py:160-221,
+ * modeling/backbone/fpn.py:127-137, modeling/proposal_generator/rpn.py:74-85, and nn.Linear in
+ * modeling/roi_heads/box_head.py:73-81 / fast_rcnn.py:531-545 (H = 1, W = rows).
+ *   x        [N, H, W, Cin]  bf16 NHWC, Cin % 64 == 0
+ *   w        [Cout, KH, KW, Cin] bf16 (K-major), KH = KW in {1, 3}, zero padding KH/2
+ *   bias     [Cout] fp32 or NULL;  Cout % 8 == 0
+ *   stride   1, or 2 for 1x1 convs (stride_in_1x1, resnet.py:158)
+ *   residual_mode 0: none; 1: += residual[N,Ho,Wo,Cout] (bottleneck shortcut, resnet.py:216-219);
+ *                 2: += residual[N,ceil(Ho/2),ceil(Wo/2),Cout] nearest-2x upsampled (FPN top-down, fpn.py:131-133)
+ *   relu     fused ReLU after the adds;  out_fp32: y is fp32 instead of bf16
+ *   y        [N, Ho, Wo, Cout]
+ */
+typedef struct pe_conv_desc {
+  int N, H, W, Cin, Cout, KH, KW, stride, relu, residual_mode, out_fp32;
+} pe_conv_desc;
+PE_API int pe_conv2d_fwd(const pe_conv_desc* desc, const void* x, const void* w, const float* bias,
+                         const void* residual, void* y, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

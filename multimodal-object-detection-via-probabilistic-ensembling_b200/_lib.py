@@ -23,6 +23,15 @@ SIGNATURES = {
                       [c_void_p] * 5 + [c_size_t, c_void_p]),
 }
 
+
+
+class ConvDesc(ctypes.Structure):
+    """struct pe_conv_desc (include/probenb200.h)."""
+    _fields_ = [(n, c_int) for n in ("N", "H", "W", "Cin", "Cout", "KH", "KW", "stride", "relu", "residual_mode", "out_fp32")]
+
+
+SIGNATURES["pe_conv2d_fwd"] = (c_int, [ctypes.POINTER(ConvDesc)] + [c_void_p] * 6)
+
 _lib = None
 
 

@@ -33,4 +33,8 @@ int sm_count();
 template <typename T>
 __host__ __device__ constexpr T ceil_div(T a, T b) { return (a + b - 1) / b; }
 
+// conv_gemm.cu
+int conv2d_launch(const pe_conv_desc& d, const void* x, const void* w, const float* bias, const void* residual, void* y,
+                  cudaStream_t st);
+
 }  // namespace pe

@@ -1,0 +1,453 @@
+// Implicit-GEMM convolution / linear layer on the 5th-gen tensor cores (tcgen05 + TMEM + TMA), sm_100a.
+//
+// Replaces the cuDNN / cuBLAS calls behind the reference's detectron2.layers.Conv2d (+FrozenBatchNorm2d,
+// folded offline) and nn.Linear on the detector path: ResNet bottlenecks (modeling/backbone/resnet.py:160-221),
+// FPN lateral/output convs (modeling/backbone/fpn.py:127-137), the RPN head (proposal_generator/rpn.py:74-85)
+// and the box head FCs (roi_heads/box_head.py:73-81, fast_rcnn.py:531-545).
+//
+// D[pixels, Cout] = sum_{taps, Cin} A[pixels(+tap), Cin] * W[Cout, tap, Cin]; activations NHWC bf16,
+// weights [Cout][KH][KW][Cin] bf16, fp32 accumulation in TMEM.
+//   * M tile = a TH x TW spatial patch of 128 output pixels of one image; for every filter tap the
+//     producer warp issues ONE 4-D TMA box load (64 ch, TW, TH, 1) at the shifted coordinate, so zero
+//     padding, image borders and ragged tiles all come from TMA out-of-bounds zero fill.  Stride-2 1x1
+//     convs read through a strided tensor map.  Linear layers are the H=1 case.
+//   * B tile = (64 k, BLOCK_N) box of the K-major weight matrix.  Both land in 128B-swizzled K-major smem
+//     tiles that tcgen05.mma consumes directly through shared-memory descriptors.
+//   * warp 0: TMA producer, warp 1: MMA issuer (one elected lane), warp 2: TMEM allocator,
+//     warps 4-7: epilogue (tcgen05.ld -> +bias, +residual / nearest-2x-upsampled residual, ReLU -> bf16/fp32
+//     NHWC stores).  Two TMEM accumulator stages overlap the epilogue of tile i with the mainloop of i+1.
+//   * persistent grid: min(#tiles, #SMs) CTAs, static round-robin tile schedule.
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include "common.cuh"
+
+namespace pe {
+namespace {
+
+constexpr int kBlockM = 128;
+constexpr int kBlockK = 64;  // one 128-byte swizzle atom of bf16
+constexpr int kUmmaK = 16;
+constexpr int kThreads = 256;
+constexpr int kEpilogueWarp0 = 4;
+constexpr uint32_t kWatchdogPolls = 1u << 27;  // mbarrier polls before trapping (debug safety net)
+
+struct ConvArgs {
+  int N, Ho, Wo, Cin, Cout;
+  int KH, KW, pad;
+  int TH, TW, tiles_h, tiles_w, tiles_n;
+  int k_chunks;  // Cin / 64
+  int relu, residual_mode, out_fp32;
+  int res_H, res_W;  // residual spatial size (mode 2: the coarser map)
+  const float* bias;
+  const __nv_bfloat16* residual;
+  void* out;
+};
+
+// ---------------------------------------------------------------------------------------------- PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t polls = 0;
+  while (!mbar_try_wait(bar, parity)) {
+    if (++polls > kWatchdogPolls) __trap();  // a lost arrive would otherwise hang the GPU box
+  }
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tma_load_4d(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, int c1, int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
+}
+
+// K-major, 128B-swizzled smem tile: rows of 128 B, 8-row groups 1024 B apart (cute UMMA::SmemDescriptor).
+__device__ __forceinline__ uint64_t umma_smem_desc(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);  // start address, bits [0,14)
+  d |= (uint64_t)1 << 16;                       // leading byte offset (unused for swizzled K-major) = 1
+  d |= (uint64_t)(1024 >> 4) << 32;             // stride byte offset = 1024 B
+  d |= (uint64_t)1 << 46;                       // descriptor version (Blackwell)
+  d |= (uint64_t)2 << 61;                       // SWIZZLE_128B
+  return d;
+}
+// kind::f16 instruction descriptor: bf16 x bf16 -> fp32, both operands K-major, M x N tile.
+__host__ __device__ constexpr uint32_t umma_instr_desc(int M, int N) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tmem_ld_32x32b_x16(uint32_t taddr, uint32_t* v) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+template <int kCols>
+__device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "n"(kCols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+template <int kCols>
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "n"(kCols) : "memory");
+}
+
+// ---------------------------------------------------------------------------------------------- configuration
+template <int BLOCK_N>
+struct TileCfg {
+  static constexpr int kABytes = kBlockM * kBlockK * 2;   // 16 KB
+  static constexpr int kBBytes = BLOCK_N * kBlockK * 2;
+  static constexpr int kStageBytes = kABytes + kBBytes;
+  static constexpr int kStages = BLOCK_N >= 256 ? 4 : (BLOCK_N >= 128 ? 6 : 8);
+  static constexpr int kTmemCols = 2 * BLOCK_N < 32 ? 32 : 2 * BLOCK_N;
+  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*alignment slack*/ + 256 /*barriers*/;
+};
+
+// ---------------------------------------------------------------------------------------------- epilogue helpers
+__device__ __forceinline__ float bf16_lo(uint32_t u) { return __uint_as_float(u << 16); }
+__device__ __forceinline__ float bf16_hi(uint32_t u) { return __uint_as_float(u & 0xffff0000u); }
+__device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
+  __nv_bfloat162 t = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&t);
+}
+
+// ---------------------------------------------------------------------------------------------- kernel
+template <int BLOCK_N>
+__global__ void __launch_bounds__(kThreads, 1)
+conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, const ConvArgs a) {
+  using Cfg = TileCfg<BLOCK_N>;
+  extern __shared__ unsigned char smem_dyn[];
+  unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~(uintptr_t)1023);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::kStages * Cfg::kStageBytes);
+  uint64_t* full_bar = bars;
+  uint64_t* empty_bar = bars + Cfg::kStages;
+  uint64_t* tmem_full = bars + 2 * Cfg::kStages;
+  uint64_t* tmem_empty = tmem_full + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int tiles_m = a.N * a.tiles_h * a.tiles_w;
+  const int num_tiles = tiles_m * a.tiles_n;
+  const int k_iters = a.KH * a.KW * a.k_chunks;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&map_a);
+    tma_prefetch_desc(&map_b);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < Cfg::kStages; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&tmem_full[s], 1);
+      mbar_init(&tmem_empty[s], 4);  // one arrive per epilogue warp
+    }
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc<Cfg::kTmemCols>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ================================ TMA producer ================================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int nt = tile % a.tiles_n, mt = tile / a.tiles_n;
+        const int tw = mt % a.tiles_w, th = (mt / a.tiles_w) % a.tiles_h, img = mt / (a.tiles_w * a.tiles_h);
+        const int h0 = th * a.TH - a.pad, w0 = tw * a.TW - a.pad, n0 = nt * BLOCK_N;
+        for (int kh = 0; kh < a.KH; ++kh)
+          for (int kw = 0; kw < a.KW; ++kw)
+            for (int kc = 0; kc < a.k_chunks; ++kc) {
+              mbar_wait(&empty_bar[stage], phase ^ 1);
+              unsigned char* sa = smem + stage * Cfg::kStageBytes;
+              unsigned char* sb = sa + Cfg::kABytes;
+              mbar_expect_tx(&full_bar[stage], Cfg::kStageBytes);
+              tma_load_4d(&map_a, &full_bar[stage], sa, kc * kBlockK, w0 + kw, h0 + kh, img);
+              tma_load_2d(&map_b, &full_bar[stage], sb, ((kh * a.KW + kw) * a.k_chunks + kc) * kBlockK, n0);
+              if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
+            }
+      }
+    }
+  } else if (warp == 1) {
+    // ================================ MMA issuer ================================
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_instr_desc(kBlockM, BLOCK_N);
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * BLOCK_N;
+        for (int it = 0; it < k_iters; ++it) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + stage * Cfg::kStageBytes);
+          const uint32_t sb = sa + Cfg::kABytes;
+          const uint64_t da = umma_smem_desc(sa), db = umma_smem_desc(sb);
+#pragma unroll
+          for (int k = 0; k < kBlockK / kUmmaK; ++k) {
+            // advance 32 B (= 2 x 16 B) along K inside the swizzle atom
+            umma_bf16(d_tmem, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (it | k) != 0);
+          }
+          umma_commit(&empty_bar[stage]);  // frees the smem stage once these MMAs retire
+          if (it == k_iters - 1) umma_commit(&tmem_full[acc]);
+          if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
+        }
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      }
+    }
+  } else if (warp >= kEpilogueWarp0) {
+    // ================================ epilogue ================================
+    const int q = warp - kEpilogueWarp0;  // TMEM lane quarter owned by this warp
+    const int row = q * 32 + lane;
+    const int ph = row / a.TW, pw = row - ph * a.TW;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      const int nt = tile % a.tiles_n, mt = tile / a.tiles_n;
+      const int tw = mt % a.tiles_w, th = (mt / a.tiles_w) % a.tiles_h, img = mt / (a.tiles_w * a.tiles_h);
+      const int h = th * a.TH + ph, w = tw * a.TW + pw, n0 = nt * BLOCK_N;
+      const bool pix_ok = h < a.Ho && w < a.Wo;
+      const size_t opix = ((size_t)img * a.Ho + h) * a.Wo + w;
+      size_t rpix = opix;
+      if (a.residual_mode == 2) rpix = ((size_t)img * a.res_H + (h >> 1)) * a.res_W + (w >> 1);
+      mbar_wait(&tmem_full[acc], acc_phase);
+      tc_fence_after();
+#pragma unroll 1
+      for (int c0 = 0; c0 < BLOCK_N; c0 += 16) {
+        uint32_t v[16];
+        tmem_ld_32x32b_x16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BLOCK_N + c0), v);
+        tmem_ld_wait();
+        const int ch = n0 + c0;
+        if (pix_ok && ch < a.Cout) {  // Cout is a multiple of 8; a 16-wide chunk may be half valid
+          const int nvalid = a.Cout - ch >= 16 ? 16 : 8;
+          float f[16];
+#pragma unroll
+          for (int i = 0; i < 16; ++i) f[i] = __uint_as_float(v[i]);
+          if (a.bias) {
+#pragma unroll
+            for (int i = 0; i < 16; i += 4) {
+              if (i < nvalid) {
+                const float4 b4 = __ldg(reinterpret_cast<const float4*>(a.bias + ch + i));
+                f[i] += b4.x; f[i + 1] += b4.y; f[i + 2] += b4.z; f[i + 3] += b4.w;
+              }
+            }
+          }
+          if (a.residual_mode) {
+            const uint4* rp = reinterpret_cast<const uint4*>(a.residual + rpix * a.Cout + ch);
+#pragma unroll
+            for (int i = 0; i < 16; i += 8) {
+              if (i < nvalid) {
+                const uint4 r = __ldg(rp + i / 8);
+                f[i] += bf16_lo(r.x); f[i + 1] += bf16_hi(r.x); f[i + 2] += bf16_lo(r.y); f[i + 3] += bf16_hi(r.y);
+                f[i + 4] += bf16_lo(r.z); f[i + 5] += bf16_hi(r.z); f[i + 6] += bf16_lo(r.w); f[i + 7] += bf16_hi(r.w);
+              }
+            }
+          }
+          if (a.relu) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) f[i] = fmaxf(f[i], 0.f);
+          }
+          if (a.out_fp32) {
+            float4* op = reinterpret_cast<float4*>(reinterpret_cast<float*>(a.out) + opix * a.Cout + ch);
+#pragma unroll
+            for (int i = 0; i < 16; i += 4)
+              if (i < nvalid) op[i / 4] = make_float4(f[i], f[i + 1], f[i + 2], f[i + 3]);
+          } else {
+            uint4* op = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(a.out) + opix * a.Cout + ch);
+#pragma unroll
+            for (int i = 0; i < 16; i += 8)
+              if (i < nvalid)
+                op[i / 8] = make_uint4(pack_bf16(f[i], f[i + 1]), pack_bf16(f[i + 2], f[i + 3]),
+                                       pack_bf16(f[i + 4], f[i + 5]), pack_bf16(f[i + 6], f[i + 7]));
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc<Cfg::kTmemCols>(tmem_base);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------- host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+
+// bf16 tensor map with 128B swizzle; dims/strides innermost first, strides[i] = byte stride of dim i+1.
+bool make_map(CUtensorMap* m, const void* base, int rank, const cuuint64_t* dims, const cuuint64_t* strides,
+              const cuuint32_t* box) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (!fn) return false;
+  cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(base), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS;
+}
+
+void pick_patch(int Ho, int Wo, int* TH, int* TW) {
+  long best = -1;
+  int bh = 8, bw = 16;
+  for (int tw = 8; tw <= 128; tw <<= 1) {
+    const int th = kBlockM / tw;
+    const long cover = (long)ceil_div(Ho, th) * th * ceil_div(Wo, tw) * tw;
+    // prefer least padded work, then the squarer patch
+    const long score = cover * 1024 + (th > tw ? th / tw : tw / th);
+    if (best < 0 || score < best) { best = score; bh = th; bw = tw; }
+  }
+  *TH = bh;
+  *TW = bw;
+}
+
+template <int BLOCK_N>
+int launch_conv(const CUtensorMap& ma, const CUtensorMap& mb, const ConvArgs& a, cudaStream_t st) {
+  using Cfg = TileCfg<BLOCK_N>;
+  static bool attr_done = false;
+  if (!attr_done) {
+    PE_CUDA_CHECK(cudaFuncSetAttribute(conv_gemm_kernel<BLOCK_N>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
+    attr_done = true;
+  }
+  const int tiles = a.N * a.tiles_h * a.tiles_w * a.tiles_n;
+  const int grid = tiles < sm_count() ? tiles : sm_count();
+  conv_gemm_kernel<BLOCK_N><<<grid, kThreads, Cfg::kSmemBytes, st>>>(ma, mb, a);
+  PE_LAUNCH_CHECK();
+  return PE_OK;
+}
+
+}  // namespace
+
+int conv2d_launch(const pe_conv_desc& d, const void* x, const void* w, const float* bias, const void* residual, void* y,
+                  cudaStream_t st) {
+  if (d.N < 1 || d.H < 1 || d.W < 1 || d.Cin < 64 || d.Cin % 64 || d.Cout < 8 || d.Cout % 8) return PE_ERR_INVALID_ARGUMENT;
+  if (!((d.KH == 1 && d.KW == 1) || (d.KH == 3 && d.KW == 3))) return PE_ERR_UNSUPPORTED;
+  if (d.stride != 1 && !(d.stride == 2 && d.KH == 1)) return PE_ERR_UNSUPPORTED;
+  if (d.residual_mode < 0 || d.residual_mode > 2 || (d.residual_mode && !residual)) return PE_ERR_INVALID_ARGUMENT;
+  if (!x || !w || !y) return PE_ERR_INVALID_ARGUMENT;
+  ConvArgs a;
+  a.N = d.N;
+  a.Ho = d.stride == 2 ? (d.H - 1) / 2 + 1 : d.H;
+  a.Wo = d.stride == 2 ? (d.W - 1) / 2 + 1 : d.W;
+  a.Cin = d.Cin;
+  a.Cout = d.Cout;
+  a.KH = d.KH;
+  a.KW = d.KW;
+  a.pad = d.KH / 2;
+  pick_patch(a.Ho, a.Wo, &a.TH, &a.TW);
+  a.tiles_h = ceil_div(a.Ho, a.TH);
+  a.tiles_w = ceil_div(a.Wo, a.TW);
+  const int bn = d.Cout >= 256 ? 256 : (d.Cout >= 128 ? 128 : (d.Cout >= 64 ? 64 : (d.Cout > 16 ? 32 : 16)));
+  a.tiles_n = ceil_div(d.Cout, bn);
+  a.k_chunks = d.Cin / kBlockK;
+  a.relu = d.relu;
+  a.residual_mode = d.residual_mode;
+  a.out_fp32 = d.out_fp32;
+  a.res_H = (a.Ho + 1) / 2;
+  a.res_W = (a.Wo + 1) / 2;
+  a.bias = bias;
+  a.residual = reinterpret_cast<const __nv_bfloat16*>(residual);
+  a.out = y;
+
+  CUtensorMap ma, mb;
+  {
+    const cuuint64_t s = (cuuint64_t)d.stride;
+    cuuint64_t dims[4] = {(cuuint64_t)d.Cin, (cuuint64_t)a.Wo, (cuuint64_t)a.Ho, (cuuint64_t)d.N};
+    cuuint64_t strides[3] = {s * d.Cin * 2, s * (cuuint64_t)d.W * d.Cin * 2, (cuuint64_t)d.H * d.W * d.Cin * 2};
+    cuuint32_t box[4] = {(cuuint32_t)kBlockK, (cuuint32_t)a.TW, (cuuint32_t)a.TH, 1};
+    if (!make_map(&ma, x, 4, dims, strides, box)) return PE_ERR_CUDA;
+  }
+  {
+    cuuint64_t dims[2] = {(cuuint64_t)d.KH * d.KW * d.Cin, (cuuint64_t)d.Cout};
+    cuuint64_t strides[1] = {(cuuint64_t)d.KH * d.KW * d.Cin * 2};
+    cuuint32_t box[2] = {(cuuint32_t)kBlockK, (cuuint32_t)bn};
+    if (!make_map(&mb, w, 2, dims, strides, box)) return PE_ERR_CUDA;
+  }
+  switch (bn) {
+    case 256: return launch_conv<256>(ma, mb, a, st);
+    case 128: return launch_conv<128>(ma, mb, a, st);
+    case 64: return launch_conv<64>(ma, mb, a, st);
+    case 32: return launch_conv<32>(ma, mb, a, st);
+    default: return launch_conv<16>(ma, mb, a, st);
+  }
+}
+
+}  // namespace pe
+
+extern "C" PE_API int pe_conv2d_fwd(const pe_conv_desc* desc, const void* x, const void* w, const float* bias,
+                                    const void* residual, void* y, void* stream) {
+  if (!desc) return PE_ERR_INVALID_ARGUMENT;
+  return pe::conv2d_launch(*desc, x, w, bias, residual, y, reinterpret_cast<cudaStream_t>(stream));
+}

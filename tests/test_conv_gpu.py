@@ -1,0 +1,74 @@
+"""tcgen05 implicit-GEMM conv / linear (pe_conv2d_fwd) against a plain PyTorch fp32 reference of the same
+op evaluated on the same bf16-rounded operands (floating-point kernel: tolerance = bf16 output rounding +
+fp32 accumulation-order noise, stated per test)."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+from probenb200 import ops
+
+pytestmark = pytest.mark.gpu
+
+
+def ref_conv(x, w, bias, residual, stride, relu, residual_mode):
+    xf = x.float().permute(0, 3, 1, 2)
+    wf = w.float().permute(0, 3, 1, 2)
+    y = F.conv2d(xf, wf, bias, stride=stride, padding=w.shape[1] // 2)
+    if residual_mode == 1:
+        y = y + residual.float().permute(0, 3, 1, 2)
+    elif residual_mode == 2:
+        y = y + F.interpolate(residual.float().permute(0, 3, 1, 2), scale_factor=2, mode="nearest")[:, :, :y.shape[2], :y.shape[3]]
+    if relu:
+        y = F.relu(y)
+    return y.permute(0, 2, 3, 1).contiguous()
+
+
+CASES = [
+    # N, H, W, Cin, Cout, k, stride, relu, residual_mode, out_fp32
+    (1, 8, 16, 64, 64, 1, 1, False, 0, False),      # single tile, single k-chunk
+    (1, 8, 16, 128, 128, 1, 1, True, 0, False),     # two k-chunks
+    (2, 20, 24, 64, 256, 1, 1, True, 1, False),     # ragged tiles, residual add
+    (2, 13, 16, 256, 16, 1, 1, False, 0, True),     # RPN-like narrow fp32 output
+    (1, 25, 32, 128, 64, 3, 1, True, 0, False),     # 3x3, borders
+    (2, 50, 64, 64, 64, 3, 1, True, 0, False),
+    (1, 26, 32, 256, 512, 1, 2, False, 0, False),   # stride-2 1x1 (shortcut)
+    (1, 25, 31, 128, 128, 1, 2, True, 0, False),    # odd sizes, stride 2
+    (2, 26, 32, 256, 256, 1, 1, False, 2, False),   # FPN lateral + upsampled top-down
+    (1, 100, 128, 256, 256, 3, 1, False, 0, False), # many tiles per CTA (persistent loop, both acc stages)
+    (4, 7, 9, 512, 1024, 1, 1, True, 1, False),     # tiny maps, 4 n-tiles
+    (1, 1, 300, 1024, 32, 1, 1, False, 0, True),    # predictor-like linear, N tile 32
+]
+
+
+@pytest.mark.parametrize("case", CASES)
+def test_conv_matches_fp32_reference(case):
+    N, H, W, Cin, Cout, k, stride, relu, rmode, out_fp32 = case
+    g = torch.Generator(device="cuda").manual_seed(sum(int(v) * (i + 1) for i, v in enumerate(case)))
+    x = torch.randn(N, H, W, Cin, device="cuda", generator=g).bfloat16()
+    w = (torch.randn(Cout, k, k, Cin, device="cuda", generator=g) / (k * k * Cin) ** 0.5).bfloat16()
+    bias = torch.randn(Cout, device="cuda", generator=g)
+    Ho, Wo = ((H - 1) // 2 + 1, (W - 1) // 2 + 1) if stride == 2 else (H, W)
+    res = None
+    if rmode == 1:
+        res = torch.randn(N, Ho, Wo, Cout, device="cuda", generator=g).bfloat16()
+    elif rmode == 2:
+        res = torch.randn(N, (Ho + 1) // 2, (Wo + 1) // 2, Cout, device="cuda", generator=g).bfloat16()
+    y = ops.conv2d_nhwc(x, w, bias, res, stride, relu, rmode, out_fp32)
+    torch.cuda.synchronize()
+    want = ref_conv(x, w, bias, res, stride, relu, rmode)
+    assert y.shape == want.shape
+    err = (y.float() - want).abs()
+    # outputs are O(1..4); bf16 rounding of the result is <= 2^-8 relative, fp32 accumulation noise ~1e-4
+    tol = 1e-3 + (0.0 if out_fp32 else 1.0) * want.abs() * 2 ** -8
+    assert bool((err <= tol).all()), "max err %g" % float(err.max())
+
+
+def test_linear_large_k():
+    g = torch.Generator(device="cuda").manual_seed(7)
+    x = torch.randn(1000, 12544, device="cuda", generator=g).bfloat16()
+    w = (torch.randn(1024, 12544, device="cuda", generator=g) / 112).bfloat16()
+    b = torch.randn(1024, device="cuda", generator=g)
+    y = ops.linear(x, w, b, relu=True)
+    want = F.relu(x.float() @ w.float().t() + b)
+    err = (y.float() - want).abs()
+    assert bool((err <= 2e-3 + want.abs() * 2 ** -8).all()), float(err.max())
