@@ -89,9 +89,93 @@ PE_API int pe_fuse_batch(const float* boxes, const float* scores, const int32_t*
  */
 typedef struct pe_conv_desc {
   int N, H, W, Cin, Cout, KH, KW, stride, relu, residual_mode, out_fp32;
+  int in_fp16; /* x and w are IEEE fp16 instead of bf16 (stem: raw pixel range needs the 11-bit mantissa) */
 } pe_conv_desc;
 PE_API int pe_conv2d_fwd(const pe_conv_desc* desc, const void* x, const void* w, const float* bias,
                          const void* residual, void* y, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Detector engine: the inference path of detectron2/modeling/meta_arch/rcnn.py:219-267 (GeneralizedRCNN with
+ * ResNet-50/101-FPN, RPN, StandardROIHeads + the fork's variance head, fast_rcnn.py:531-545) as a native
+ * kernel sequence.  The engine owns no device memory:
+ *   weights    one blob laid out per the manifest pe_detector_param_info() publishes (the host folds
+ *              FrozenBatchNorm2d into conv weights/biases and repacks to [Cout][KH][KW][Cin] bf16; kinds:
+ *              0 conv+BN, 1 conv+bias, 2 stem 7x7 as [64][Kpad] fp16, 3 RPN objectness|deltas rows,
+ *              4 fc1 with (c,ph,pw)->(ph,pw,c) column permutation, 5 linear, 6 cls|bbox|var predictor rows);
+ *   workspace  pe_detector_workspace_bytes() of scratch; pe_detector_buffer_info() exposes named
+ *              intermediates (p2..p6, rpn_out2..6, proposals, roi_feats, head_out, ...) for stage-wise parity tests;
+ *   images     [B, in_channels, img_h, img_w] float32 (what GeneralizedRCNN.forward receives in
+ *              batched_inputs[i]["image"], i.e. after ResizeShortestEdge), normalised + zero padded to the
+ *              canvas on the fly (rcnn.py:269-286);
+ *   out        fixed-stride records, PE_MAX_DETECTIONS per image, already rescaled to (out_h, out_w) by
+ *              detector_postprocess (postprocessing.py:8-52); field names follow the fork's Instances fields.
+ */
+#define PE_MAX_DETECTIONS 100
+typedef struct pe_detector pe_detector;
+typedef struct pe_detector_config {
+  int depth;           /* 50 | 101 (MODEL.RESNETS.DEPTH) */
+  int in_channels;     /* 3 | 4 (early fusion BGRT) | 6 with middle_fusion (BGRTTT) */
+  int middle_fusion;   /* rcnn.py:240-248: shared backbone on both 3-channel halves, features concatenated */
+  int num_classes;     /* K: 3 (FLIR) | 1 (KAIST) */
+  int max_batch;
+  int canvas_h, canvas_w;            /* padded network input, multiples of 32 (fpn.py:102) */
+  float pixel_mean[8], pixel_std[8];
+  float score_thresh, nms_thresh, rpn_nms_thresh;
+  int pre_nms_topk, post_nms_topk, detections_per_image;
+} pe_detector_config;
+typedef struct pe_param_info {
+  char name[96];
+  int kind, cout, kh, kw, cin;
+  size_t weight_offset, bias_offset;
+} pe_param_info;
+typedef struct pe_detections {
+  float* boxes;          /* [B, 100, 4] xyxy in the (out_h, out_w) frame */
+  float* scores;         /* [B, 100] */
+  int32_t* classes;      /* [B, 100] */
+  float* class_logits;   /* [B, 100, K+1] */
+  float* probs;          /* [B, 100, K]   (prob_score) */
+  float* vars;           /* [B, 100]      (vars, with the reference's candidate-index quirk) */
+  int32_t* roi_index;    /* [B, 100] proposal row each detection came from */
+  int32_t* counts;       /* [B] */
+} pe_detections;
+PE_API int pe_detector_create(const pe_detector_config* cfg, pe_detector** out);
+PE_API void pe_detector_destroy(pe_detector* d);
+PE_API int pe_detector_num_params(const pe_detector* d);
+PE_API int pe_detector_param_info(const pe_detector* d, int i, pe_param_info* info);
+PE_API size_t pe_detector_weight_bytes(const pe_detector* d);
+PE_API size_t pe_detector_workspace_bytes(const pe_detector* d);
+PE_API int pe_detector_buffer_info(const pe_detector* d, const char* name, size_t* offset, int* dims4, int* elem_bytes);
+PE_API int pe_detector_forward(pe_detector* d, const void* weights, const float* images, int B, int img_h, int img_w,
+                               float out_h, float out_w, const pe_detections* out, void* workspace, size_t workspace_bytes,
+                               void* stream);
+/* Gathers M models' detections into pe_fuse_batch's packed layout (det_offsets [B*M+1] + SoA rows). */
+PE_API int pe_pack_detections(const pe_detections* models, int M, int B, int K, int32_t* det_offsets, float* boxes,
+                              float* scores, int32_t* classes, float* probs, float* vars, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Op-level entry points of the detector's non-GEMM stages (the engine launches the same kernels).
+ *
+ * pe_rpn_proposals: find_top_rpn_proposals (modeling/proposal_generator/rpn_outputs.py:52-162) + anchors
+ *   (anchor_generator.py:130-199, sizes 32..512 x ratios .5/1/2, strides 4..64) + apply_deltas
+ *   (box_regression.py:78-115).  rpn_out[l]: [B, H[l], W[l], 16] fp32 channels-last = 3 objectness logits,
+ *   12 anchor deltas (a*4+j), 1 pad.  proposals [B, 1000, 4], proposal_counts [B].
+ * pe_roi_align_fwd: ROIPooler + ROIAlign(7x7, sampling_ratio 0, aligned) (modeling/poolers.py:180-235,
+ *   layers/csrc/ROIAlign/ROIAlign_cuda.cu:65-139; pybind seam detectron2._C.roi_align_forward, csrc/vision.cpp:89).
+ *   features[l]: p2..p5 [B, H[l], W[l], C] bf16; out [B*max_props, 49, C] bf16 (rows past the count are zero).
+ * pe_head_postprocess: FastRCNNOutputs.inference + fast_rcnn_inference_single_image (fast_rcnn.py:86-147,
+ *   345-360,417-452) + detector_postprocess (postprocessing.py:8-52).  head_out [B*max_props, npad] fp32 rows =
+ *   K+1 class logits | 4K box deltas | 1 log-variance | pad.
+ */
+PE_API size_t pe_rpn_proposals_workspace_bytes(int B);
+PE_API int pe_rpn_proposals(const float* const* rpn_out, const int* H, const int* W, int B, int pre_nms_topk,
+                            int post_nms_topk, float nms_thresh, float img_h, float img_w, float* proposals,
+                            int32_t* proposal_counts, void* workspace, size_t workspace_bytes, void* stream);
+PE_API int pe_roi_align_fwd(const void* const* features, const int* H, const int* W, int C, const float* proposals,
+                            const int32_t* proposal_counts, int B, int max_props, void* out, void* stream);
+PE_API int pe_head_postprocess(const float* head_out, int npad, const float* proposals, const int32_t* proposal_counts,
+                               int B, int max_props, int K, float img_h, float img_w, float out_h, float out_w,
+                               float score_thresh, float nms_thresh, int detections_per_image,
+                               const pe_detections* out, void* stream);
 
 #ifdef __cplusplus
 }

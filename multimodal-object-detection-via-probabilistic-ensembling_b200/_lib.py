@@ -27,10 +27,50 @@ SIGNATURES = {
 
 class ConvDesc(ctypes.Structure):
     """struct pe_conv_desc (include/probenb200.h)."""
-    _fields_ = [(n, c_int) for n in ("N", "H", "W", "Cin", "Cout", "KH", "KW", "stride", "relu", "residual_mode", "out_fp32")]
+    _fields_ = [(n, c_int) for n in ("N", "H", "W", "Cin", "Cout", "KH", "KW", "stride", "relu", "residual_mode", "out_fp32", "in_fp16")]
 
 
 SIGNATURES["pe_conv2d_fwd"] = (c_int, [ctypes.POINTER(ConvDesc)] + [c_void_p] * 6)
+
+
+class DetectorConfig(ctypes.Structure):
+    """struct pe_detector_config."""
+    _fields_ = ([(n, c_int) for n in ("depth", "in_channels", "middle_fusion", "num_classes", "max_batch", "canvas_h", "canvas_w")] +
+                [("pixel_mean", c_float * 8), ("pixel_std", c_float * 8)] +
+                [(n, c_float) for n in ("score_thresh", "nms_thresh", "rpn_nms_thresh")] +
+                [(n, c_int) for n in ("pre_nms_topk", "post_nms_topk", "detections_per_image")])
+
+
+class ParamInfo(ctypes.Structure):
+    """struct pe_param_info."""
+    _fields_ = [("name", ctypes.c_char * 96)] + [(n, c_int) for n in ("kind", "cout", "kh", "kw", "cin")] + \
+               [("weight_offset", c_size_t), ("bias_offset", c_size_t)]
+
+
+class Detections(ctypes.Structure):
+    """struct pe_detections (device pointers)."""
+    _fields_ = [(n, c_void_p) for n in ("boxes", "scores", "classes", "class_logits", "probs", "vars", "roi_index", "counts")]
+
+
+SIGNATURES.update({
+    "pe_detector_create": (c_int, [ctypes.POINTER(DetectorConfig), ctypes.POINTER(c_void_p)]),
+    "pe_detector_destroy": (None, [c_void_p]),
+    "pe_detector_num_params": (c_int, [c_void_p]),
+    "pe_detector_param_info": (c_int, [c_void_p, c_int, ctypes.POINTER(ParamInfo)]),
+    "pe_detector_weight_bytes": (c_size_t, [c_void_p]),
+    "pe_detector_workspace_bytes": (c_size_t, [c_void_p]),
+    "pe_detector_buffer_info": (c_int, [c_void_p, c_char_p, ctypes.POINTER(c_size_t), ctypes.POINTER(c_int * 4), ctypes.POINTER(c_int)]),
+    "pe_detector_forward": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_float, c_float,
+                                    ctypes.POINTER(Detections), c_void_p, c_size_t, c_void_p]),
+    "pe_pack_detections": (c_int, [ctypes.POINTER(Detections), c_int, c_int, c_int] + [c_void_p] * 7),
+    "pe_rpn_proposals_workspace_bytes": (c_size_t, [c_int]),
+    "pe_rpn_proposals": (c_int, [ctypes.POINTER(c_void_p), ctypes.POINTER(c_int), ctypes.POINTER(c_int), c_int, c_int, c_int,
+                                 c_float, c_float, c_float, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
+    "pe_roi_align_fwd": (c_int, [ctypes.POINTER(c_void_p), ctypes.POINTER(c_int), ctypes.POINTER(c_int), c_int, c_void_p, c_void_p,
+                                 c_int, c_int, c_void_p, c_void_p]),
+    "pe_head_postprocess": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_int, c_int, c_int] + [c_float] * 6 + [c_int] +
+                            [ctypes.POINTER(Detections), c_void_p]),
+})
 
 _lib = None
 

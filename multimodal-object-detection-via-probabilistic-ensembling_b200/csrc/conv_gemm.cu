@@ -36,7 +36,7 @@ struct ConvArgs {
   int KH, KW, pad;
   int TH, TW, tiles_h, tiles_w, tiles_n;
   int k_chunks;  // Cin / 64
-  int relu, residual_mode, out_fp32;
+  int relu, residual_mode, out_fp32, in_fp16;
   int res_H, res_W;  // residual spatial size (mode 2: the coarser map)
   const float* bias;
   const __nv_bfloat16* residual;
@@ -103,9 +103,10 @@ __device__ __forceinline__ uint64_t umma_smem_desc(uint32_t smem_addr) {
   d |= (uint64_t)2 << 61;                       // SWIZZLE_128B
   return d;
 }
-// kind::f16 instruction descriptor: bf16 x bf16 -> fp32, both operands K-major, M x N tile.
-__host__ __device__ constexpr uint32_t umma_instr_desc(int M, int N) {
-  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+// kind::f16 instruction descriptor: (bf16 | fp16) x same -> fp32, both operands K-major, M x N tile.
+__host__ __device__ constexpr uint32_t umma_instr_desc(int M, int N, bool fp16) {
+  return (1u << 4) | ((fp16 ? 0u : 1u) << 7) | ((fp16 ? 0u : 1u) << 10) | ((uint32_t)(N >> 3) << 17) |
+         ((uint32_t)(M >> 4) << 24);
 }
 __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
   asm volatile(
@@ -222,7 +223,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
   } else if (warp == 1) {
     // ================================ MMA issuer ================================
     if (lane == 0) {
-      constexpr uint32_t idesc = umma_instr_desc(kBlockM, BLOCK_N);
+      const uint32_t idesc = umma_instr_desc(kBlockM, BLOCK_N, a.in_fp16 != 0);
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
@@ -415,6 +416,7 @@ int conv2d_launch(const pe_conv_desc& d, const void* x, const void* w, const flo
   a.relu = d.relu;
   a.residual_mode = d.residual_mode;
   a.out_fp32 = d.out_fp32;
+  a.in_fp16 = d.in_fp16;
   a.res_H = (a.Ho + 1) / 2;
   a.res_W = (a.Wo + 1) / 2;
   a.bias = bias;

@@ -1,0 +1,747 @@
+// Non-GEMM kernels of the detector path (sm_100a): pre-processing + stem im2col, max-pool, RPN top-k /
+// decode / NMS / merge, multi-level ROIAlign, Fast R-CNN head post-processing, and the packer that turns the
+// per-model detections into pe_fuse_batch's layout.  All batched, no host synchronisation.
+//
+// Reference semantics restated (paths relative to the reference checkout):
+//   stem_im2col      detectron2/modeling/meta_arch/rcnn.py:269-286 (normalise, zero pad to /32) feeding
+//                    modeling/backbone/resnet.py:369-384 (7x7/2 conv as a GEMM over K = 49*C)
+//   maxpool3x3s2     resnet.py:383 (F.max_pool2d(k=3, s=2, p=1))
+//   subsample2       modeling/backbone/fpn.py:166-178 (LastLevelMaxPool = max_pool2d(k=1, s=2))
+//   rpn_topk         modeling/proposal_generator/rpn_outputs.py:95-124,409-451 + anchor_generator.py:130-199 +
+//                    box_regression.py:78-115 + clip / non-empty test of rpn_outputs.py:131-146
+//   rpn_nms/merge    rpn_outputs.py:147-160 via detectron2/layers/nms.py:9-26 (per-level NMS, IoU 0.7, top-1000)
+//   roi_align        modeling/poolers.py:13-81,180-235 + layers/csrc/ROIAlign/ROIAlign_cuda.cu:65-139
+//                    (aligned=True, sampling_ratio=0)
+//   head_post        modeling/roi_heads/fast_rcnn.py:86-147,345-360,417-452 + modeling/postprocessing.py:8-52
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+#include <math.h>
+#include "common.cuh"
+#include "detector_kernels.cuh"
+
+namespace pe {
+namespace {
+
+__device__ __forceinline__ float bflo(uint32_t u) { return __uint_as_float(u << 16); }
+__device__ __forceinline__ float bfhi(uint32_t u) { return __uint_as_float(u & 0xffff0000u); }
+__device__ __forceinline__ uint32_t packbf(float a, float b) {
+  __nv_bfloat162 t = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&t);
+}
+__device__ __forceinline__ bool finite4(float4 b) { return isfinite(b.x) && isfinite(b.y) && isfinite(b.z) && isfinite(b.w); }
+
+// ---------------------------------------------------------------------------------------------- stem im2col
+__global__ void stem_im2col_kernel(const float* __restrict__ img, __half* __restrict__ A, int B, int Ctot, int c0, int C,
+                                   int Hi, int Wi, int Ho, int Wo, int Kp, StemNorm nrm) {
+  const int groups = Kp >> 3;
+  const long long total = (long long)B * Ho * Wo * groups;
+  for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
+    const int g = (int)(t % groups);
+    long long pix = t / groups;
+    const int wo = (int)(pix % Wo);
+    pix /= Wo;
+    const int ho = (int)(pix % Ho), b = (int)(pix / Ho);
+    __align__(16) __half v[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int k = g * 8 + j;
+      float val = 0.f;
+      if (k < 49 * C) {
+        const int tap = k / C, c = k - tap * C;
+        const int kh = tap / 7, kw = tap - kh * 7;
+        const int y = 2 * ho - 3 + kh, x = 2 * wo - 3 + kw;
+        if (y >= 0 && y < Hi && x >= 0 && x < Wi) {
+          const float p = __ldg(img + (((size_t)b * Ctot + c0 + c) * Hi + y) * Wi + x);
+          val = __fdiv_rn(p - nrm.mean[c], nrm.std[c]);
+        }
+      }
+      v[j] = __float2half_rn(val);
+    }
+    *reinterpret_cast<uint4*>(A + (size_t)t * 8) = *reinterpret_cast<const uint4*>(v);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------- pooling
+__global__ void maxpool3x3s2_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ y, int B, int H, int W,
+                                    int C, int Ho, int Wo) {
+  const int cg = C >> 3;
+  const long long total = (long long)B * Ho * Wo * cg;
+  for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
+    const int g = (int)(t % cg);
+    long long pix = t / cg;
+    const int wo = (int)(pix % Wo);
+    pix /= Wo;
+    const int ho = (int)(pix % Ho), b = (int)(pix / Ho);
+    float m[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) m[j] = -INFINITY;
+    for (int dy = 0; dy < 3; ++dy) {
+      const int yy = 2 * ho - 1 + dy;
+      if (yy < 0 || yy >= H) continue;
+      for (int dx = 0; dx < 3; ++dx) {
+        const int xx = 2 * wo - 1 + dx;
+        if (xx < 0 || xx >= W) continue;
+        const uint4 r = __ldg(reinterpret_cast<const uint4*>(x + (((size_t)b * H + yy) * W + xx) * C) + g);
+        m[0] = fmaxf(m[0], bflo(r.x)); m[1] = fmaxf(m[1], bfhi(r.x)); m[2] = fmaxf(m[2], bflo(r.y)); m[3] = fmaxf(m[3], bfhi(r.y));
+        m[4] = fmaxf(m[4], bflo(r.z)); m[5] = fmaxf(m[5], bfhi(r.z)); m[6] = fmaxf(m[6], bflo(r.w)); m[7] = fmaxf(m[7], bfhi(r.w));
+      }
+    }
+    reinterpret_cast<uint4*>(y)[t] = make_uint4(packbf(m[0], m[1]), packbf(m[2], m[3]), packbf(m[4], m[5]), packbf(m[6], m[7]));
+  }
+}
+
+__global__ void subsample2_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ y, int B, int H, int W, int C,
+                                  int Ho, int Wo) {
+  const int cg = C >> 3;
+  const long long total = (long long)B * Ho * Wo * cg;
+  for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
+    const int g = (int)(t % cg);
+    long long pix = t / cg;
+    const int wo = (int)(pix % Wo);
+    pix /= Wo;
+    const int ho = (int)(pix % Ho), b = (int)(pix / Ho);
+    reinterpret_cast<uint4*>(y)[t] = __ldg(reinterpret_cast<const uint4*>(x + (((size_t)b * H + 2 * ho) * W + 2 * wo) * C) + g);
+  }
+}
+
+// concat two NHWC tensors along channels (middle fusion, rcnn.py:245-247)
+__global__ void concat_channels_kernel(const __nv_bfloat16* __restrict__ a, const __nv_bfloat16* __restrict__ b,
+                                       __nv_bfloat16* __restrict__ y, long long pixels, int C) {
+  const int cg = C >> 3;
+  const long long total = pixels * cg * 2;
+  for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
+    const int g = (int)(t % (2 * cg));
+    const long long pix = t / (2 * cg);
+    const uint4* src = g < cg ? reinterpret_cast<const uint4*>(a + pix * C) + g : reinterpret_cast<const uint4*>(b + pix * C) + (g - cg);
+    reinterpret_cast<uint4*>(y)[t] = __ldg(src);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------- RPN top-k + decode
+__device__ __forceinline__ uint32_t sort_key(float f) {
+  const uint32_t u = __float_as_uint(f);
+  return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__device__ __forceinline__ float key_to_float(uint32_t k) {
+  return __uint_as_float((k & 0x80000000u) ? (k & 0x7fffffffu) : ~k);
+}
+
+constexpr int kTopkThreads = 1024;
+constexpr int kTopkCap = kTopkSlots;  // pre_nms_topk <= 1024
+
+// Finds, scanning bins from the highest down, the bin holding the kth largest element.
+// hist has nbins (<= 2048) entries; returns through smem result[0]=bin, result[1]=count in higher bins.
+__device__ void find_kth_bin(const unsigned* hist, int nbins, unsigned kth, unsigned* result, unsigned* warp_tot) {
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  // each thread owns 2 descending-ordered bins
+  const int i0 = nbins - 1 - 2 * tid, i1 = i0 - 1;
+  const unsigned h0 = i0 >= 0 ? hist[i0] : 0u, h1 = i1 >= 0 ? hist[i1] : 0u;
+  unsigned s = h0 + h1;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    const unsigned o = __shfl_up_sync(kFullMask, s, d);
+    if (lane >= d) s += o;
+  }
+  if (lane == 31) warp_tot[wid] = s;
+  __syncthreads();
+  if (wid == 0) {
+    unsigned w = warp_tot[lane];
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const unsigned o = __shfl_up_sync(kFullMask, w, d);
+      if (lane >= d) w += o;
+    }
+    warp_tot[lane] = w;  // inclusive over warps
+  }
+  __syncthreads();
+  const unsigned before = (wid ? warp_tot[wid - 1] : 0u) + s - (h0 + h1);  // count in bins above i0
+  if (before < kth && kth <= before + h0) { result[0] = (unsigned)i0; result[1] = before; }
+  else if (before + h0 < kth && kth <= before + h0 + h1) { result[0] = (unsigned)i1; result[1] = before + h0; }
+  __syncthreads();
+}
+
+__global__ void __launch_bounds__(kTopkThreads) rpn_topk_kernel(const RpnLevels lv, int pre_topk, float img_h, float img_w,
+                                                                float4* __restrict__ cand_box, float* __restrict__ cand_score,
+                                                                unsigned char* __restrict__ cand_valid, int* __restrict__ cand_count) {
+  __shared__ unsigned hist[2048];
+  __shared__ unsigned long long sel[kTopkCap];
+  __shared__ unsigned warp_tot[32];
+  __shared__ unsigned res[2];
+  __shared__ unsigned sel_n, eq_run;
+  const int level = blockIdx.x, b = blockIdx.y, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const int H = lv.H[level], W = lv.W[level], A = 3;
+  const int n = H * W * A;
+  const int k = pre_topk < n ? pre_topk : n;
+  const float* base = lv.out[level] + (size_t)b * H * W * kRpnOutC;
+  auto logit = [&](int e) { return __ldg(base + (size_t)(e / A) * kRpnOutC + (e % A)); };
+
+  uint32_t prefix = 0, prefix_mask = 0;
+  unsigned kth = (unsigned)k;
+  const int shifts[3] = {21, 10, 0};
+  const int widths[3] = {11, 11, 10};
+  for (int pass = 0; pass < 3; ++pass) {
+    for (int i = tid; i < 2048; i += blockDim.x) hist[i] = 0;
+    __syncthreads();
+    const int sh = shifts[pass], nb = 1 << widths[pass];
+    for (int e = tid; e < n; e += blockDim.x) {
+      const uint32_t key = sort_key(logit(e));
+      if ((key & prefix_mask) == prefix) atomicAdd(&hist[(key >> sh) & (nb - 1)], 1u);
+    }
+    __syncthreads();
+    find_kth_bin(hist, nb, kth, res, warp_tot);
+    prefix |= res[0] << sh;
+    prefix_mask |= (uint32_t)(nb - 1) << sh;
+    kth -= res[1];
+    __syncthreads();
+  }
+  const uint32_t T = prefix;       // key of the kth largest element
+  const unsigned need_eq = kth;    // how many elements equal to T are selected (lowest index first)
+  const unsigned eq_total = hist[T & 1023u];
+  if (tid == 0) { sel_n = 0; eq_run = 0; }
+  __syncthreads();
+  if (eq_total == need_eq) {
+    for (int e = tid; e < n; e += blockDim.x) {
+      const uint32_t key = sort_key(logit(e));
+      if (key >= T) sel[atomicAdd(&sel_n, 1u)] = ((unsigned long long)key << 32) | (unsigned)(0xffffffffu - (unsigned)e);
+    }
+  } else {
+    // ties at the threshold: take them in index order with a block-wide running count
+    for (int e0 = 0; e0 < n; e0 += blockDim.x) {
+      const int e = e0 + tid;
+      uint32_t key = 0;
+      bool gt = false, eq = false;
+      if (e < n) { key = sort_key(logit(e)); gt = key > T; eq = key == T; }
+      const unsigned bal = __ballot_sync(kFullMask, eq);
+      const unsigned before_lane = __popc(bal & ((1u << lane) - 1u));
+      if (lane == 0) warp_tot[wid] = __popc(bal);
+      __syncthreads();
+      unsigned before = eq_run;
+      for (int w2 = 0; w2 < wid; ++w2) before += warp_tot[w2];
+      if (gt || (eq && before + before_lane < need_eq))
+        sel[atomicAdd(&sel_n, 1u)] = ((unsigned long long)key << 32) | (unsigned)(0xffffffffu - (unsigned)e);
+      __syncthreads();
+      if (tid == 0) { unsigned tot = 0; for (int w2 = 0; w2 < 32; ++w2) tot += warp_tot[w2]; eq_run += tot; }
+      __syncthreads();
+    }
+  }
+  __syncthreads();
+  for (int i = k + tid; i < kTopkCap; i += blockDim.x) sel[i] = 0ull;
+  __syncthreads();
+  // bitonic sort, descending
+  for (int size = 2; size <= kTopkCap; size <<= 1) {
+    for (int stride = size >> 1; stride > 0; stride >>= 1) {
+      const int i = tid;
+      const int j = i ^ stride;
+      if (j > i) {
+        const unsigned long long a = sel[i], c = sel[j];
+        const bool desc = (i & size) == 0;
+        if (desc ? a < c : a > c) { sel[i] = c; sel[j] = a; }
+      }
+      __syncthreads();
+    }
+  }
+  // decode the selected anchors
+  const size_t obase = ((size_t)b * kRpnLevels + level) * kTopkCap;
+  if (tid < k) {
+    const unsigned long long s = sel[tid];
+    const int e = (int)(0xffffffffu - (unsigned)(s & 0xffffffffu));
+    const float score = key_to_float((uint32_t)(s >> 32));
+    const int pix = e / A, an = e - pix * A;
+    const int y = pix / W, x = pix - y * W;
+    const float sx = (float)(x * lv.stride[level]), sy = (float)(y * lv.stride[level]);
+    const float ax1 = __fadd_rn(sx, lv.anchor[level][an][0]), ay1 = __fadd_rn(sy, lv.anchor[level][an][1]);
+    const float ax2 = __fadd_rn(sx, lv.anchor[level][an][2]), ay2 = __fadd_rn(sy, lv.anchor[level][an][3]);
+    const float4 d = __ldg(reinterpret_cast<const float4*>(base + (size_t)pix * kRpnOutC + 4 + an * 4));
+    const float wdt = __fsub_rn(ax2, ax1), hgt = __fsub_rn(ay2, ay1);
+    const float cx = __fadd_rn(ax1, __fmul_rn(0.5f, wdt)), cy = __fadd_rn(ay1, __fmul_rn(0.5f, hgt));
+    const float dw = fminf(d.z, kScaleClamp), dh = fminf(d.w, kScaleClamp);
+    const float pcx = __fadd_rn(__fmul_rn(d.x, wdt), cx), pcy = __fadd_rn(__fmul_rn(d.y, hgt), cy);
+    const float pw = __fmul_rn(expf(dw), wdt), ph = __fmul_rn(expf(dh), hgt);
+    float4 bx = make_float4(__fsub_rn(pcx, __fmul_rn(0.5f, pw)), __fsub_rn(pcy, __fmul_rn(0.5f, ph)),
+                            __fadd_rn(pcx, __fmul_rn(0.5f, pw)), __fadd_rn(pcy, __fmul_rn(0.5f, ph)));
+    const bool fin = finite4(bx) && isfinite(score);
+    bx.x = fminf(fmaxf(bx.x, 0.f), img_w); bx.z = fminf(fmaxf(bx.z, 0.f), img_w);
+    bx.y = fminf(fmaxf(bx.y, 0.f), img_h); bx.w = fminf(fmaxf(bx.w, 0.f), img_h);
+    const bool ok = fin && (bx.z - bx.x > 0.f) && (bx.w - bx.y > 0.f);
+    cand_box[obase + tid] = bx;
+    cand_score[obase + tid] = score;
+    cand_valid[obase + tid] = ok ? 1 : 0;
+  }
+  if (tid == 0) cand_count[b * kRpnLevels + level] = k;
+}
+
+// ---------------------------------------------------------------------------------------------- NMS (bitmask)
+__device__ __forceinline__ bool iou_gt(float4 a, float aa, float4 b, float ab, float thr) {
+  const float w = fmaxf(0.f, __fsub_rn(fminf(a.z, b.z), fmaxf(a.x, b.x)));
+  const float h = fmaxf(0.f, __fsub_rn(fminf(a.w, b.w), fmaxf(a.y, b.y)));
+  const float inter = __fmul_rn(w, h);
+  return __fdiv_rn(inter, __fsub_rn(__fadd_rn(aa, ab), inter)) > thr;
+}
+
+constexpr int kNmsThreads = 1024;
+
+// One block per score-sorted segment of <= 1024 boxes.  keep_idx gets the surviving positions in order.
+__global__ void __launch_bounds__(kNmsThreads) segment_nms_kernel(const float4* __restrict__ boxes, const unsigned char* __restrict__ valid,
+                                                                  const int* __restrict__ counts, int seg_stride, float thr,
+                                                                  int* __restrict__ keep_idx, int* __restrict__ keep_count) {
+  extern __shared__ __align__(16) unsigned char nms_smem[];
+  float4* sb = reinterpret_cast<float4*>(nms_smem);
+  float* sa = reinterpret_cast<float*>(sb + 1024);
+  unsigned* mask = reinterpret_cast<unsigned*>(sa + 1024);  // [n][32]
+  const int seg = blockIdx.x, tid = threadIdx.x, lane = tid & 31;
+  const int n = counts[seg];
+  const size_t base = (size_t)seg * seg_stride;
+  for (int i = tid; i < n; i += blockDim.x) {
+    const float4 b = boxes[base + i];
+    sb[i] = b;
+    sa[i] = __fmul_rn(__fsub_rn(b.z, b.x), __fsub_rn(b.w, b.y));
+  }
+  __syncthreads();
+  const int Wn = (n + 31) >> 5;
+  for (int item = tid; item < n * Wn; item += blockDim.x) {
+    const int i = item / Wn, w = item - i * Wn;
+    unsigned bits = 0;
+    if (w >= (i >> 5)) {
+      const float4 bi = sb[i];
+      const float ai = sa[i];
+      const int j0 = w << 5;
+#pragma unroll 4
+      for (int t = 0; t < 32; ++t) {
+        const int j = j0 + t;
+        if (j > i && j < n && iou_gt(bi, ai, sb[j], sa[j], thr)) bits |= 1u << t;
+      }
+    }
+    mask[i * 32 + w] = bits;
+  }
+  __syncthreads();
+  if (tid < 32) {
+    unsigned removed = 0;  // lane w owns word w; invalid boxes start out removed
+    for (int w = 0; w < Wn; ++w) {
+      const int j = (w << 5) + lane;
+      const unsigned inv = __ballot_sync(kFullMask, j < n ? valid[base + j] == 0 : true);
+      if (lane == w) removed = inv;
+    }
+    int kept = 0;
+    for (int i = 0; i < n; ++i) {
+      const unsigned rw = __shfl_sync(kFullMask, removed, i >> 5);
+      if ((rw >> (i & 31)) & 1u) continue;
+      if (lane < Wn) removed |= mask[i * 32 + lane];
+      if (lane == 0) keep_idx[base + kept] = i;
+      ++kept;
+    }
+    if (lane == 0) keep_count[seg] = kept;
+  }
+}
+
+// Merge the per-level survivors of one image by descending score (ties: lower level, lower position) and keep
+// the first post_topk: rpn_outputs.py:147-156.
+__global__ void __launch_bounds__(1024) rpn_merge_kernel(const float4* __restrict__ cand_box, const float* __restrict__ cand_score,
+                                                         const int* __restrict__ keep_idx, const int* __restrict__ keep_count,
+                                                         int post_topk, int max_props, float4* __restrict__ props,
+                                                         int* __restrict__ prop_count) {
+  __shared__ float s_score[kRpnLevels][kTopkCap];
+  __shared__ int s_n[kRpnLevels];
+  const int b = blockIdx.x, tid = threadIdx.x;
+  if (tid < kRpnLevels) s_n[tid] = keep_count[b * kRpnLevels + tid];
+  __syncthreads();
+  for (int l = 0; l < kRpnLevels; ++l) {
+    const size_t base = ((size_t)b * kRpnLevels + l) * kTopkCap;
+    for (int i = tid; i < s_n[l]; i += blockDim.x) s_score[l][i] = cand_score[base + keep_idx[base + i]];
+  }
+  __syncthreads();
+  int total = 0;
+  for (int l = 0; l < kRpnLevels; ++l) total += s_n[l];
+  for (int l = 0; l < kRpnLevels; ++l) {
+    const size_t base = ((size_t)b * kRpnLevels + l) * kTopkCap;
+    for (int i = tid; i < s_n[l]; i += blockDim.x) {
+      const float s = s_score[l][i];
+      int rank = i;
+      for (int m = 0; m < kRpnLevels; ++m) {
+        if (m == l) continue;
+        // scores in level m are descending: count entries > s (and == s when m < l)
+        int lo = 0, hi = s_n[m];
+        while (lo < hi) {
+          const int mid = (lo + hi) >> 1;
+          const float v = s_score[m][mid];
+          if (v > s || (m < l && v == s)) lo = mid + 1; else hi = mid;
+        }
+        rank += lo;
+      }
+      if (rank < post_topk && rank < max_props) props[(size_t)b * max_props + rank] = cand_box[base + keep_idx[base + i]];
+    }
+  }
+  if (tid == 0) prop_count[b] = total < post_topk ? (total < max_props ? total : max_props) : (post_topk < max_props ? post_topk : max_props);
+}
+
+// ---------------------------------------------------------------------------------------------- ROIAlign
+__global__ void __launch_bounds__(256) roi_align_kernel(const RoiLevels fl, const float4* __restrict__ props, const int* __restrict__ prop_count,
+                                                        int B, int max_props, int C, __nv_bfloat16* __restrict__ out) {
+  const int lane = threadIdx.x & 31;
+  const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const long long total = (long long)B * max_props * 49;
+  if (warp >= total) return;
+  const int bin = (int)(warp % 49);
+  const long long roi = warp / 49;
+  const int b = (int)(roi / max_props), r = (int)(roi % max_props);
+  uint4* dst = reinterpret_cast<uint4*>(out + ((size_t)roi * 49 + bin) * C);
+  const int cgroups = C >> 3;
+  if (r >= prop_count[b]) {
+    for (int g = lane; g < cgroups; g += 32) dst[g] = make_uint4(0, 0, 0, 0);
+    return;
+  }
+  const float4 box = __ldg(props + roi);
+  // poolers.py:13-44: level = clamp(floor(4 + log2(sqrt(area)/224 + eps)), 2, 5) - 2
+  const float area = __fmul_rn(__fsub_rn(box.z, box.x), __fsub_rn(box.w, box.y));
+  float lvf = floorf(__fadd_rn(4.f, log2f(__fadd_rn(__fdiv_rn(sqrtf(area), 224.f), 2.220446049250313e-16f))));
+  lvf = fminf(fmaxf(lvf, 2.f), 5.f);
+  int lvl = (int)lvf - 2;
+  if (!(lvf == lvf)) lvl = 0;
+  const int H = fl.H[lvl], W = fl.W[lvl];
+  const float scale = fl.scale[lvl];
+  const __nv_bfloat16* feat = fl.feat[lvl] + (size_t)b * H * W * C;
+  const int ph = bin / 7, pw = bin - ph * 7;
+  const float rsw = __fsub_rn(__fmul_rn(box.x, scale), 0.5f), rsh = __fsub_rn(__fmul_rn(box.y, scale), 0.5f);
+  const float rew = __fsub_rn(__fmul_rn(box.z, scale), 0.5f), reh = __fsub_rn(__fmul_rn(box.w, scale), 0.5f);
+  const float roi_w = __fsub_rn(rew, rsw), roi_h = __fsub_rn(reh, rsh);
+  const float bin_h = __fdiv_rn(roi_h, 7.f), bin_w = __fdiv_rn(roi_w, 7.f);
+  const int gh = (int)ceilf(__fdiv_rn(roi_h, 7.f)), gw = (int)ceilf(__fdiv_rn(roi_w, 7.f));
+  const float count = (float)max(gh * gw, 1);
+  for (int g = lane; g < cgroups; g += 32) {
+    float acc[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+    for (int iy = 0; iy < gh; ++iy) {
+      const float yy = rsh + ph * bin_h + (iy + 0.5f) * bin_h / (float)gh;
+      for (int ix = 0; ix < gw; ++ix) {
+        const float xx = rsw + pw * bin_w + (ix + 0.5f) * bin_w / (float)gw;
+        if (yy < -1.f || yy > (float)H || xx < -1.f || xx > (float)W) continue;
+        float y = fmaxf(yy, 0.f), x = fmaxf(xx, 0.f);
+        int yl = (int)y, xl = (int)x, yh, xh;
+        if (yl >= H - 1) { yh = yl = H - 1; y = (float)yl; } else yh = yl + 1;
+        if (xl >= W - 1) { xh = xl = W - 1; x = (float)xl; } else xh = xl + 1;
+        const float ly = y - yl, lx = x - xl, hy = 1.f - ly, hx = 1.f - lx;
+        const float w1 = hy * hx, w2 = hy * lx, w3 = ly * hx, w4 = ly * lx;
+        const uint4 v1 = __ldg(reinterpret_cast<const uint4*>(feat + ((size_t)yl * W + xl) * C) + g);
+        const uint4 v2 = __ldg(reinterpret_cast<const uint4*>(feat + ((size_t)yl * W + xh) * C) + g);
+        const uint4 v3 = __ldg(reinterpret_cast<const uint4*>(feat + ((size_t)yh * W + xl) * C) + g);
+        const uint4 v4 = __ldg(reinterpret_cast<const uint4*>(feat + ((size_t)yh * W + xh) * C) + g);
+        acc[0] += w1 * bflo(v1.x) + w2 * bflo(v2.x) + w3 * bflo(v3.x) + w4 * bflo(v4.x);
+        acc[1] += w1 * bfhi(v1.x) + w2 * bfhi(v2.x) + w3 * bfhi(v3.x) + w4 * bfhi(v4.x);
+        acc[2] += w1 * bflo(v1.y) + w2 * bflo(v2.y) + w3 * bflo(v3.y) + w4 * bflo(v4.y);
+        acc[3] += w1 * bfhi(v1.y) + w2 * bfhi(v2.y) + w3 * bfhi(v3.y) + w4 * bfhi(v4.y);
+        acc[4] += w1 * bflo(v1.z) + w2 * bflo(v2.z) + w3 * bflo(v3.z) + w4 * bflo(v4.z);
+        acc[5] += w1 * bfhi(v1.z) + w2 * bfhi(v2.z) + w3 * bfhi(v3.z) + w4 * bfhi(v4.z);
+        acc[6] += w1 * bflo(v1.w) + w2 * bflo(v2.w) + w3 * bflo(v3.w) + w4 * bflo(v4.w);
+        acc[7] += w1 * bfhi(v1.w) + w2 * bfhi(v2.w) + w3 * bfhi(v3.w) + w4 * bfhi(v4.w);
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] /= count;
+    dst[g] = make_uint4(packbf(acc[0], acc[1]), packbf(acc[2], acc[3]), packbf(acc[4], acc[5]), packbf(acc[6], acc[7]));
+  }
+}
+
+// ---------------------------------------------------------------------------------------------- head post-processing
+constexpr int kHeadThreads = 256;
+constexpr int kMaxCand = 1024;  // score_thresh >= 0.5 admits at most one class per ROI, so <= 1000 candidates
+
+template <int K>
+__global__ void __launch_bounds__(kHeadThreads) head_post_kernel(const float* __restrict__ head /*[B*max_props][npad]*/, int npad,
+                                                                 const float4* __restrict__ props, const int* __restrict__ prop_count,
+                                                                 int max_props, HeadParams hp, DetOut out) {
+  __shared__ float4 c_box[kMaxCand];
+  __shared__ float c_score[kMaxCand];
+  __shared__ unsigned short c_row[kMaxCand], c_cls[kMaxCand], c_order[kMaxCand];
+  __shared__ unsigned char c_dead[kMaxCand];
+  __shared__ int warp_cnt[kHeadThreads / 32];
+  __shared__ int s_ncand, s_run, s_keep[kMaxDet], s_nkeep;
+  __shared__ float s_red[kHeadThreads / 32];
+  const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const int R = prop_count[b];
+  const float* hb = head + (size_t)b * max_props * npad;
+  if (tid == 0) { s_ncand = 0; s_run = 0; s_nkeep = 0; }
+  __syncthreads();
+  // 1. candidates (row-major over (roi, class)) with score > thresh, ordered compaction
+  for (int r0 = 0; r0 < R; r0 += blockDim.x) {
+    const int r = r0 + tid;
+    float pr[K + 1];
+    float4 bx[K];
+    int nc = 0;
+    bool above[K];
+#pragma unroll
+    for (int k2 = 0; k2 < K; ++k2) above[k2] = false;
+    if (r < R) {
+      const float* row = hb + (size_t)r * npad;
+      float mx = -INFINITY;
+#pragma unroll
+      for (int k2 = 0; k2 <= K; ++k2) { pr[k2] = row[k2]; mx = fmaxf(mx, pr[k2]); }
+      float den = 0.f;
+#pragma unroll
+      for (int k2 = 0; k2 <= K; ++k2) { pr[k2] = expf(pr[k2] - mx); den += pr[k2]; }
+      bool fin = true;
+#pragma unroll
+      for (int k2 = 0; k2 <= K; ++k2) { pr[k2] = __fdiv_rn(pr[k2], den); fin &= isfinite(pr[k2]); }
+      const float4 p = props[(size_t)b * max_props + r];
+      const float wdt = __fsub_rn(p.z, p.x), hgt = __fsub_rn(p.w, p.y);
+      const float cx = __fadd_rn(p.x, __fmul_rn(0.5f, wdt)), cy = __fadd_rn(p.y, __fmul_rn(0.5f, hgt));
+#pragma unroll
+      for (int k2 = 0; k2 < K; ++k2) {
+        const float* d = row + (K + 1) + 4 * k2;
+        const float dx = __fdiv_rn(d[0], 10.f), dy = __fdiv_rn(d[1], 10.f);
+        const float dw = fminf(__fdiv_rn(d[2], 5.f), kScaleClamp), dh = fminf(__fdiv_rn(d[3], 5.f), kScaleClamp);
+        const float pcx = __fadd_rn(__fmul_rn(dx, wdt), cx), pcy = __fadd_rn(__fmul_rn(dy, hgt), cy);
+        const float pw = __fmul_rn(expf(dw), wdt), ph = __fmul_rn(expf(dh), hgt);
+        float4 q = make_float4(__fsub_rn(pcx, __fmul_rn(0.5f, pw)), __fsub_rn(pcy, __fmul_rn(0.5f, ph)),
+                               __fadd_rn(pcx, __fmul_rn(0.5f, pw)), __fadd_rn(pcy, __fmul_rn(0.5f, ph)));
+        fin &= finite4(q);
+        q.x = fminf(fmaxf(q.x, 0.f), hp.img_w); q.z = fminf(fmaxf(q.z, 0.f), hp.img_w);
+        q.y = fminf(fmaxf(q.y, 0.f), hp.img_h); q.w = fminf(fmaxf(q.w, 0.f), hp.img_h);
+        bx[k2] = q;
+      }
+      if (fin) {
+#pragma unroll
+        for (int k2 = 0; k2 < K; ++k2) { above[k2] = pr[k2] > hp.score_thresh; nc += above[k2]; }
+      }
+    }
+    // exclusive scan of nc over the block
+    int inc = nc;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) { const int o = __shfl_up_sync(kFullMask, inc, d); if (lane >= d) inc += o; }
+    if (lane == 31) warp_cnt[wid] = inc;
+    __syncthreads();
+    int pos = s_run + inc - nc;
+    for (int w2 = 0; w2 < wid; ++w2) pos += warp_cnt[w2];
+    if (nc) {
+#pragma unroll
+      for (int k2 = 0; k2 < K; ++k2)
+        if (above[k2]) {
+          if (pos < kMaxCand) { c_box[pos] = bx[k2]; c_score[pos] = pr[k2]; c_row[pos] = (unsigned short)r; c_cls[pos] = (unsigned short)k2; }
+          ++pos;
+        }
+    }
+    __syncthreads();
+    if (tid == 0) { int tot = 0; for (int w2 = 0; w2 < kHeadThreads / 32; ++w2) tot += warp_cnt[w2]; s_run += tot; }
+    __syncthreads();
+  }
+  const int n = s_run < kMaxCand ? s_run : kMaxCand;
+  // 2. order by score (descending, ties lower candidate index first) and max coordinate for the offset trick
+  float mc = -INFINITY;
+  for (int i = tid; i < n; i += blockDim.x) {
+    const float s = c_score[i];
+    int rank = 0;
+    for (int j = 0; j < n; ++j) { const float t = c_score[j]; rank += (t > s) || (t == s && j < i); }
+    c_order[rank] = (unsigned short)i;
+    c_dead[i] = 0;
+    const float4 q = c_box[i];
+    mc = fmaxf(mc, fmaxf(fmaxf(q.x, q.y), fmaxf(q.z, q.w)));
+  }
+#pragma unroll
+  for (int s = 16; s > 0; s >>= 1) mc = fmaxf(mc, __shfl_xor_sync(kFullMask, mc, s));
+  if (lane == 0) s_red[wid] = mc;
+  __syncthreads();
+  mc = s_red[0];
+  for (int w2 = 1; w2 < kHeadThreads / 32; ++w2) mc = fmaxf(mc, s_red[w2]);
+  const float off1 = __fadd_rn(mc, 1.f);
+  // 3. greedy per-class NMS in score order, stop after detections_per_image survivors
+  for (int a = 0; a < n; ++a) {
+    const int i = c_order[a];
+    if (c_dead[i]) continue;        // uniform: shared memory, synchronised below
+    if (s_nkeep >= hp.max_det) break;
+    __syncthreads();
+    if (tid == 0) { s_keep[s_nkeep] = i; }
+    const float oi = __fmul_rn((float)c_cls[i], off1);
+    const float4 q = c_box[i];
+    const float4 bi = make_float4(__fadd_rn(q.x, oi), __fadd_rn(q.y, oi), __fadd_rn(q.z, oi), __fadd_rn(q.w, oi));
+    const float ai = __fmul_rn(__fsub_rn(bi.z, bi.x), __fsub_rn(bi.w, bi.y));
+    for (int c = a + 1 + tid; c < n; c += blockDim.x) {
+      const int j = c_order[c];
+      if (c_dead[j]) continue;
+      const float oj = __fmul_rn((float)c_cls[j], off1);
+      const float4 p = c_box[j];
+      const float4 bj = make_float4(__fadd_rn(p.x, oj), __fadd_rn(p.y, oj), __fadd_rn(p.z, oj), __fadd_rn(p.w, oj));
+      const float aj = __fmul_rn(__fsub_rn(bj.z, bj.x), __fsub_rn(bj.w, bj.y));
+      if (iou_gt(bi, ai, bj, aj, hp.nms_thresh)) c_dead[j] = 1;
+    }
+    __syncthreads();
+    if (tid == 0) s_nkeep = s_nkeep + 1;
+    __syncthreads();
+  }
+  __syncthreads();
+  // 4. emit: postprocess scale/clip/non-empty (postprocessing.py:8-52), fork fields
+  const int nk = s_nkeep;
+  if (wid == 0) {
+    int emitted = 0;
+    for (int i0 = 0; i0 < nk; i0 += 32) {
+      const int i = i0 + lane;
+      bool ok = false;
+      float4 q = make_float4(0, 0, 0, 0);
+      int ci = 0;
+      if (i < nk) {
+        ci = s_keep[i];
+        q = c_box[ci];
+        q.x = __fmul_rn(q.x, hp.scale_x); q.z = __fmul_rn(q.z, hp.scale_x);
+        q.y = __fmul_rn(q.y, hp.scale_y); q.w = __fmul_rn(q.w, hp.scale_y);
+        q.x = fminf(fmaxf(q.x, 0.f), hp.out_w); q.z = fminf(fmaxf(q.z, 0.f), hp.out_w);
+        q.y = fminf(fmaxf(q.y, 0.f), hp.out_h); q.w = fminf(fmaxf(q.w, 0.f), hp.out_h);
+        ok = (q.z - q.x > 0.f) && (q.w - q.y > 0.f);
+      }
+      const unsigned bal = __ballot_sync(kFullMask, ok);
+      if (ok) {
+        const int o = emitted + __popc(bal & ((1u << lane) - 1u));
+        const size_t ob = (size_t)b * kMaxDet + o;
+        const int r = c_row[ci];
+        const float* row = hb + (size_t)r * npad;
+        out.boxes[ob] = q;
+        out.scores[ob] = c_score[ci];
+        out.classes[ob] = (int)c_cls[ci];
+        float mx = -INFINITY;
+        for (int k2 = 0; k2 <= K; ++k2) { out.logits[ob * (K + 1) + k2] = row[k2]; mx = fmaxf(mx, row[k2]); }
+        float den = 0.f, e[K + 1];
+        for (int k2 = 0; k2 <= K; ++k2) { e[k2] = expf(row[k2] - mx); den += e[k2]; }
+        for (int k2 = 0; k2 < K; ++k2) out.probs[ob * K + k2] = __fdiv_rn(e[k2], den);
+        // sic: the reference indexes the per-ROI variance with the candidate-list index (quirk 1)
+        const int vrow = ci < R ? ci : R - 1;
+        out.vars[ob] = expf(hb[(size_t)vrow * npad + (K + 1) + 4 * K]);
+        out.roi_index[ob] = r;
+      }
+      emitted += __popc(bal);
+    }
+    if (lane == 0) out.count[b] = emitted;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------- pack for ProbEn
+__global__ void pack_offsets_kernel(PackIn in, int B, int M, int* __restrict__ offsets) {
+  // single block: exclusive scan of counts[b*M + m]
+  __shared__ int carry;
+  __shared__ int wsum[32];
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  if (tid == 0) carry = 0;
+  __syncthreads();
+  const int n = B * M;
+  for (int i0 = 0; i0 < n; i0 += blockDim.x) {
+    const int i = i0 + tid;
+    int c = 0;
+    if (i < n) { const int b = i / M, m = i - b * M; c = in.count[m][b]; }
+    int inc = c;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) { const int o = __shfl_up_sync(kFullMask, inc, d); if (lane >= d) inc += o; }
+    if (lane == 31) wsum[wid] = inc;
+    __syncthreads();
+    int pre = carry;
+    for (int w = 0; w < wid; ++w) pre += wsum[w];
+    if (i < n) offsets[i] = pre + inc - c;
+    __syncthreads();
+    if (tid == blockDim.x - 1) carry = pre + inc;
+    __syncthreads();
+  }
+  if (tid == 0) offsets[n] = carry;
+}
+
+__global__ void pack_copy_kernel(PackIn in, int B, int M, int K, const int* __restrict__ offsets, float4* __restrict__ boxes,
+                                 float* __restrict__ scores, int* __restrict__ classes, float* __restrict__ probs, float* __restrict__ vars) {
+  const int seg = blockIdx.x, b = seg / M, m = seg - b * M;
+  const int n = in.count[m][b], o = offsets[seg];
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    const size_t s = (size_t)b * kMaxDet + i;
+    boxes[o + i] = in.boxes[m][s];
+    scores[o + i] = in.scores[m][s];
+    classes[o + i] = in.classes[m][s];
+    vars[o + i] = in.vars[m][s];
+    for (int k = 0; k < K; ++k) probs[(size_t)(o + i) * K + k] = in.probs[m][s * K + k];
+  }
+}
+
+inline int grid_for(long long total, int block) {
+  long long g = (total + block - 1) / block;
+  const long long cap = (long long)sm_count() * 16;
+  return (int)(g < 1 ? 1 : (g > cap ? cap : g));
+}
+
+}  // namespace
+
+// ---------------------------------------------------------------------------------------------- launchers
+int launch_stem_im2col(const float* img, void* A, int B, int Ctot, int c0, int C, int Hi, int Wi, int Hc, int Wc, int Kp,
+                       const StemNorm& nrm, cudaStream_t st) {
+  const int Ho = Hc / 2, Wo = Wc / 2;
+  const long long total = (long long)B * Ho * Wo * (Kp / 8);
+  stem_im2col_kernel<<<grid_for(total, 256), 256, 0, st>>>(img, reinterpret_cast<__half*>(A), B, Ctot, c0, C, Hi, Wi, Ho, Wo, Kp, nrm);
+  PE_LAUNCH_CHECK();
+  return PE_OK;
+}
+
+int launch_maxpool(const void* x, void* y, int B, int H, int W, int C, cudaStream_t st) {
+  const int Ho = (H - 1) / 2 + 1, Wo = (W - 1) / 2 + 1;
+  const long long total = (long long)B * Ho * Wo * (C / 8);
+  maxpool3x3s2_kernel<<<grid_for(total, 256), 256, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(x), reinterpret_cast<__nv_bfloat16*>(y),
+                                                              B, H, W, C, Ho, Wo);
+  PE_LAUNCH_CHECK();
+  return PE_OK;
+}
+
+int launch_subsample2(const void* x, void* y, int B, int H, int W, int C, cudaStream_t st) {
+  const int Ho = (H - 1) / 2 + 1, Wo = (W - 1) / 2 + 1;
+  const long long total = (long long)B * Ho * Wo * (C / 8);
+  subsample2_kernel<<<grid_for(total, 256), 256, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(x), reinterpret_cast<__nv_bfloat16*>(y),
+                                                           B, H, W, C, Ho, Wo);
+  PE_LAUNCH_CHECK();
+  return PE_OK;
+}
+
+int launch_concat_channels(const void* a, const void* b, void* y, long long pixels, int C, cudaStream_t st) {
+  const long long total = pixels * (C / 8) * 2;
+  concat_channels_kernel<<<grid_for(total, 256), 256, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(a),
+                                                                reinterpret_cast<const __nv_bfloat16*>(b),
+                                                                reinterpret_cast<__nv_bfloat16*>(y), pixels, C);
+  PE_LAUNCH_CHECK();
+  return PE_OK;
+}
+
+int launch_rpn_proposals(const RpnLevels& lv, int B, int pre_topk, int post_topk, float nms_thr, float img_h, float img_w,
+                         const RpnScratch& s, int max_props, float4* props, int* prop_count, cudaStream_t st) {
+  if (pre_topk > kTopkCap || pre_topk < 1) return PE_ERR_UNSUPPORTED;
+  rpn_topk_kernel<<<dim3(kRpnLevels, B), kTopkThreads, 0, st>>>(lv, pre_topk, img_h, img_w, s.cand_box, s.cand_score, s.cand_valid, s.cand_count);
+  PE_LAUNCH_CHECK();
+  const size_t smem = 1024 * sizeof(float4) + 1024 * sizeof(float) + 1024 * 32 * sizeof(unsigned);
+  static bool attr = false;
+  if (!attr) {
+    PE_CUDA_CHECK(cudaFuncSetAttribute(segment_nms_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr = true;
+  }
+  segment_nms_kernel<<<B * kRpnLevels, kNmsThreads, smem, st>>>(s.cand_box, s.cand_valid, s.cand_count, kTopkCap, nms_thr, s.keep_idx, s.keep_count);
+  PE_LAUNCH_CHECK();
+  rpn_merge_kernel<<<B, 1024, 0, st>>>(s.cand_box, s.cand_score, s.keep_idx, s.keep_count, post_topk, max_props, props, prop_count);
+  PE_LAUNCH_CHECK();
+  return PE_OK;
+}
+
+int launch_roi_align(const RoiLevels& fl, const float4* props, const int* prop_count, int B, int max_props, int C, void* out,
+                     cudaStream_t st) {
+  if (C % 8) return PE_ERR_INVALID_ARGUMENT;
+  const long long warps = (long long)B * max_props * 49;
+  const long long blocks = (warps + 7) / 8;
+  roi_align_kernel<<<(unsigned)blocks, 256, 0, st>>>(fl, props, prop_count, B, max_props, C, reinterpret_cast<__nv_bfloat16*>(out));
+  PE_LAUNCH_CHECK();
+  return PE_OK;
+}
+
+int launch_head_post(const float* head, int npad, const float4* props, const int* prop_count, int B, int max_props, int K,
+                     const HeadParams& hp, const DetOut& out, cudaStream_t st) {
+  if (hp.max_det > kMaxDet) return PE_ERR_UNSUPPORTED;
+  if (K == 3) head_post_kernel<3><<<B, kHeadThreads, 0, st>>>(head, npad, props, prop_count, max_props, hp, out);
+  else if (K == 1) head_post_kernel<1><<<B, kHeadThreads, 0, st>>>(head, npad, props, prop_count, max_props, hp, out);
+  else return PE_ERR_UNSUPPORTED;
+  PE_LAUNCH_CHECK();
+  return PE_OK;
+}
+
+int launch_pack(const PackIn& in, int B, int M, int K, int* offsets, float4* boxes, float* scores, int* classes, float* probs,
+                float* vars, cudaStream_t st) {
+  pack_offsets_kernel<<<1, 1024, 0, st>>>(in, B, M, offsets);
+  PE_LAUNCH_CHECK();
+  pack_copy_kernel<<<B * M, 128, 0, st>>>(in, B, M, K, offsets, boxes, scores, classes, probs, vars);
+  PE_LAUNCH_CHECK();
+  return PE_OK;
+}
+
+}  // namespace pe

@@ -1,0 +1,484 @@
+// Native detector engine: builds the layer plan of the reference's GeneralizedRCNN inference path
+// (detectron2/modeling/meta_arch/rcnn.py:219-267: ResNet-50/101-FPN backbone, RPN, StandardROIHeads with the
+// fork's variance head) and runs it as a fixed sequence of sm_100a kernels on one stream - no host
+// synchronisation, no Python in the loop.  Weights live in a caller-owned blob whose layout the engine
+// publishes as a manifest (pe_detector_param_*); activations live in a caller-owned workspace.
+#include <math.h>
+#include <stdio.h>
+#include <string.h>
+#include <string>
+#include <vector>
+#include "common.cuh"
+#include "detector_kernels.cuh"
+
+namespace pe {
+namespace {
+
+constexpr int kMaxProps = 1000;  // RPN POST_NMS_TOPK_TEST (configs/Base-RCNN-FPN.yaml:19)
+
+enum ParamKind { kConvBN = 0, kConvBias = 1, kStem = 2, kRpnPred = 3, kFc1 = 4, kLinear = 5, kPredictor = 6 };
+
+struct Param {
+  std::string name;
+  int kind, Cout, KH, KW, Cin;
+  size_t w_off, b_off;
+};
+
+struct Buf {
+  std::string name;
+  size_t off, bytes;
+  int d[4];  // N, H, W, C
+  int elem;  // bytes per element
+};
+
+size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+}  // namespace
+}  // namespace pe
+
+struct pe_detector {
+  pe_detector_config cfg;
+  std::vector<pe::Param> params;
+  std::vector<pe::Buf> bufs;
+  size_t weight_bytes = 0, ws_bytes = 0;
+  int fc;         // channels entering RPN / ROI heads (256, or 512 for middle fusion)
+  int stem_c;     // channels per backbone pass
+  int stem_kp;    // padded K of the stem GEMM
+  int npad;       // padded predictor width
+  int H[6], W[6]; // canvas sizes at strides 2,4,8,16,32,64
+
+  int add_param(const std::string& name, int kind, int Cout, int KH, int KW, int Cin, int welem) {
+    pe::Param p;
+    p.name = name; p.kind = kind; p.Cout = Cout; p.KH = KH; p.KW = KW; p.Cin = Cin;
+    p.w_off = weight_bytes;
+    weight_bytes = pe::align_up(weight_bytes + (size_t)Cout * KH * KW * Cin * welem, 256);
+    p.b_off = weight_bytes;
+    weight_bytes = pe::align_up(weight_bytes + (size_t)Cout * 4, 256);
+    params.push_back(p);
+    return (int)params.size() - 1;
+  }
+  int find_param(const std::string& name) const {
+    for (size_t i = 0; i < params.size(); ++i)
+      if (params[i].name == name) return (int)i;
+    return -1;
+  }
+  size_t add_buf(const std::string& name, int n, int h, int w, int c, int elem) {
+    pe::Buf b;
+    b.name = name; b.off = ws_bytes; b.bytes = (size_t)n * h * w * c * elem; b.d[0] = n; b.d[1] = h; b.d[2] = w; b.d[3] = c; b.elem = elem;
+    ws_bytes = pe::align_up(ws_bytes + b.bytes, 1024);
+    bufs.push_back(b);
+    return b.off;
+  }
+  const pe::Buf* find_buf(const std::string& name) const {
+    for (const auto& b : bufs)
+      if (b.name == name) return &b;
+    return nullptr;
+  }
+};
+
+namespace pe {
+namespace {
+
+const int kStageBlocks50[4] = {3, 4, 6, 3};
+const int kStageBlocks101[4] = {3, 4, 23, 3};
+
+void build_plan(pe_detector* d) {
+  const pe_detector_config& c = d->cfg;
+  const int* blocks = c.depth == 101 ? kStageBlocks101 : kStageBlocks50;
+  d->stem_c = c.middle_fusion ? 3 : c.in_channels;
+  d->stem_kp = (int)align_up((size_t)49 * d->stem_c, 64);
+  d->fc = c.middle_fusion ? 512 : 256;
+  d->npad = (int)align_up((size_t)(c.num_classes + 1 + 4 * c.num_classes + 1), 16);
+  for (int i = 0; i < 6; ++i) {
+    d->H[i] = c.canvas_h >> (i + 1);
+    d->W[i] = c.canvas_w >> (i + 1);
+  }
+  d->H[5] = (d->H[4] - 1) / 2 + 1;
+  d->W[5] = (d->W[4] - 1) / 2 + 1;
+  // ---- parameters (manifest order == blob order)
+  const std::string bu = "backbone.bottom_up";
+  d->add_param(bu + ".stem.conv1", kStem, 64, 1, 1, d->stem_kp, 2);
+  int cin = 64;
+  for (int s = 0; s < 4; ++s) {
+    const int mid = 64 << s, cout = 256 << s;
+    for (int b = 0; b < blocks[s]; ++b) {
+      char q[96];
+      snprintf(q, sizeof(q), "%s.res%d.%d", bu.c_str(), s + 2, b);
+      if (b == 0) d->add_param(std::string(q) + ".shortcut", kConvBN, cout, 1, 1, cin, 2);
+      d->add_param(std::string(q) + ".conv1", kConvBN, mid, 1, 1, cin, 2);
+      d->add_param(std::string(q) + ".conv2", kConvBN, mid, 3, 3, mid, 2);
+      d->add_param(std::string(q) + ".conv3", kConvBN, cout, 1, 1, mid, 2);
+      cin = cout;
+    }
+  }
+  for (int l = 5; l >= 2; --l) {
+    char q[64];
+    snprintf(q, sizeof(q), "backbone.fpn_lateral%d", l);
+    d->add_param(q, kConvBias, 256, 1, 1, 256 << (l - 2), 2);
+    snprintf(q, sizeof(q), "backbone.fpn_output%d", l);
+    d->add_param(q, kConvBias, 256, 3, 3, 256, 2);
+  }
+  d->add_param("proposal_generator.rpn_head.conv", kConvBias, d->fc, 3, 3, d->fc, 2);
+  d->add_param("proposal_generator.rpn_head", kRpnPred, kRpnOutC, 1, 1, d->fc, 2);
+  d->add_param("roi_heads.box_head.fc1", kFc1, 1024, 1, 1, 49 * d->fc, 2);
+  d->add_param("roi_heads.box_head.fc2", kLinear, 1024, 1, 1, 1024, 2);
+  d->add_param("roi_heads.box_predictor", kPredictor, d->npad, 1, 1, 1024, 2);
+
+  // ---- workspace
+  const int B = c.max_batch;
+  const int passes = c.middle_fusion ? 2 : 1;
+  d->add_buf("stem_cols", B, d->H[0], d->W[0], d->stem_kp, 2);
+  d->add_buf("stem_out", B, d->H[0], d->W[0], 64, 2);
+  d->add_buf("pool_out", B, d->H[1], d->W[1], 64, 2);
+  d->add_buf("x0", B, d->H[1], d->W[1], 256, 2);
+  d->add_buf("x1", B, d->H[1], d->W[1], 256, 2);
+  d->add_buf("sc", B, d->H[1], d->W[1], 256, 2);
+  d->add_buf("t1", B, d->H[1], d->W[1], 64, 2);
+  d->add_buf("t2", B, d->H[1], d->W[1], 64, 2);
+  for (int s = 0; s < 4; ++s) {
+    char q[16];
+    snprintf(q, sizeof(q), "res%d", s + 2);
+    d->add_buf(q, B, d->H[s + 1], d->W[s + 1], 256 << s, 2);
+  }
+  for (int p = 0; p < passes; ++p)
+    for (int l = 5; l >= 2; --l) {
+      char q[24];
+      snprintf(q, sizeof(q), "inner%d_%d", l, p);
+      d->add_buf(q, B, d->H[l - 1], d->W[l - 1], 256, 2);
+      snprintf(q, sizeof(q), "pout%d_%d", l, p);
+      d->add_buf(q, B, d->H[l - 1], d->W[l - 1], 256, 2);
+    }
+  for (int l = 2; l <= 6; ++l) {
+    char q[16];
+    snprintf(q, sizeof(q), "p%d", l);
+    if (c.middle_fusion || l == 6) d->add_buf(q, B, d->H[l - 1], d->W[l - 1], d->fc, 2);
+    snprintf(q, sizeof(q), "rpn_out%d", l);
+    d->add_buf(q, B, d->H[l - 1], d->W[l - 1], kRpnOutC, 4);
+  }
+  d->add_buf("rpn_t", B, d->H[1], d->W[1], d->fc, 2);
+  d->add_buf("cand_box", B, kRpnLevels, kTopkSlots, 4, 4);
+  d->add_buf("cand_score", B, kRpnLevels, kTopkSlots, 1, 4);
+  d->add_buf("cand_valid", B, kRpnLevels, kTopkSlots, 1, 1);
+  d->add_buf("cand_count", B, kRpnLevels, 1, 1, 4);
+  d->add_buf("keep_idx", B, kRpnLevels, kTopkSlots, 1, 4);
+  d->add_buf("keep_count", B, kRpnLevels, 1, 1, 4);
+  d->add_buf("proposals", B, kMaxProps, 1, 4, 4);
+  d->add_buf("prop_count", B, 1, 1, 1, 4);
+  d->add_buf("roi_feats", B * kMaxProps, 1, 1, 49 * d->fc, 2);
+  d->add_buf("fc1_out", B * kMaxProps, 1, 1, 1024, 2);
+  d->add_buf("fc2_out", B * kMaxProps, 1, 1, 1024, 2);
+  d->add_buf("head_out", B * kMaxProps, 1, 1, d->npad, 4);
+}
+
+struct Runner {
+  const pe_detector* d;
+  const unsigned char* wts;
+  unsigned char* ws;
+  cudaStream_t st;
+  int B;
+  int status = PE_OK;
+
+  void* buf(const char* name) const { return ws + d->find_buf(name)->off; }
+
+  void conv(const std::string& pname, const void* x, int H, int W, int stride, bool relu, int rmode, const void* res, void* y,
+            bool out_fp32 = false, bool in_fp16 = false) {
+    if (status != PE_OK) return;
+    const int pi = d->find_param(pname);
+    if (pi < 0) { status = PE_ERR_INVALID_ARGUMENT; return; }
+    const Param& p = d->params[pi];
+    pe_conv_desc cd;
+    cd.N = B; cd.H = H; cd.W = W; cd.Cin = p.Cin; cd.Cout = p.Cout; cd.KH = p.KH; cd.KW = p.KW; cd.stride = stride;
+    cd.relu = relu; cd.residual_mode = rmode; cd.out_fp32 = out_fp32; cd.in_fp16 = in_fp16;
+    status = conv2d_launch(cd, x, wts + p.w_off, reinterpret_cast<const float*>(wts + p.b_off), res, y, st);
+  }
+  void linear(const std::string& pname, const void* x, int rows, bool relu, void* y, bool out_fp32) {
+    if (status != PE_OK) return;
+    const Param& p = d->params[d->find_param(pname)];
+    pe_conv_desc cd;
+    cd.N = 1; cd.H = 1; cd.W = rows; cd.Cin = p.Cin; cd.Cout = p.Cout; cd.KH = 1; cd.KW = 1; cd.stride = 1;
+    cd.relu = relu; cd.residual_mode = 0; cd.out_fp32 = out_fp32; cd.in_fp16 = 0;
+    status = conv2d_launch(cd, x, wts + p.w_off, reinterpret_cast<const float*>(wts + p.b_off), nullptr, y, st);
+  }
+  void check(int s) { if (status == PE_OK) status = s; }
+
+  // ResNet bottom-up + FPN for one backbone pass (input channels [c0, c0 + stem_c) of the image tensor)
+  void backbone(const float* images, int Ctot, int c0, int img_h, int img_w, int pass) {
+    const pe_detector_config& c = d->cfg;
+    StemNorm nrm;
+    for (int i = 0; i < 8; ++i) { nrm.mean[i] = 0.f; nrm.std[i] = 1.f; }
+    for (int i = 0; i < d->stem_c; ++i) { nrm.mean[i] = c.pixel_mean[c0 + i]; nrm.std[i] = c.pixel_std[c0 + i]; }
+    check(launch_stem_im2col(images, buf("stem_cols"), B, Ctot, c0, d->stem_c, img_h, img_w, c.canvas_h, c.canvas_w, d->stem_kp, nrm, st));
+    {  // 7x7/2 conv as a GEMM over the im2col matrix (fp16 operands keep the 0..255 pixel range exact enough)
+      if (status == PE_OK) {
+        const Param& p = d->params[d->find_param("backbone.bottom_up.stem.conv1")];
+        pe_conv_desc cd;
+        cd.N = B; cd.H = d->H[0]; cd.W = d->W[0]; cd.Cin = d->stem_kp; cd.Cout = 64; cd.KH = 1; cd.KW = 1; cd.stride = 1;
+        cd.relu = 1; cd.residual_mode = 0; cd.out_fp32 = 0; cd.in_fp16 = 1;
+        status = conv2d_launch(cd, buf("stem_cols"), wts + p.w_off, reinterpret_cast<const float*>(wts + p.b_off), nullptr, buf("stem_out"), st);
+      }
+    }
+    check(launch_maxpool(buf("stem_out"), buf("pool_out"), B, d->H[0], d->W[0], 64, st));
+    const int* blocks = c.depth == 101 ? kStageBlocks101 : kStageBlocks50;
+    const void* x = buf("pool_out");
+    int H = d->H[1], W = d->W[1];
+    for (int s = 0; s < 4; ++s) {
+      for (int b = 0; b < blocks[s]; ++b) {
+        char q[96];
+        snprintf(q, sizeof(q), "backbone.bottom_up.res%d.%d", s + 2, b);
+        const std::string base(q);
+        const int stride = (b == 0 && s > 0) ? 2 : 1;
+        const void* shortcut = x;
+        if (b == 0) {
+          conv(base + ".shortcut", x, H, W, stride, false, 0, nullptr, buf("sc"));
+          shortcut = buf("sc");
+        }
+        conv(base + ".conv1", x, H, W, stride, true, 0, nullptr, buf("t1"));
+        if (stride == 2) { H = (H - 1) / 2 + 1; W = (W - 1) / 2 + 1; }
+        conv(base + ".conv2", buf("t1"), H, W, 1, true, 0, nullptr, buf("t2"));
+        char rq[16];
+        snprintf(rq, sizeof(rq), "res%d", s + 2);
+        void* y = (b == blocks[s] - 1) ? buf(rq) : (x == buf("x0") ? buf("x1") : buf("x0"));
+        conv(base + ".conv3", buf("t2"), H, W, 1, true, 1, shortcut, y);
+        x = y;
+      }
+    }
+    // FPN top-down (fpn.py:110-145)
+    char qi[24], qo[24], qp[24], rq[16];
+    for (int l = 5; l >= 2; --l) {
+      snprintf(qi, sizeof(qi), "inner%d_%d", l, pass);
+      snprintf(qo, sizeof(qo), "pout%d_%d", l, pass);
+      snprintf(rq, sizeof(rq), "res%d", l);
+      char ln[40], on[40];
+      snprintf(ln, sizeof(ln), "backbone.fpn_lateral%d", l);
+      snprintf(on, sizeof(on), "backbone.fpn_output%d", l);
+      if (l == 5) conv(ln, buf(rq), d->H[l - 1], d->W[l - 1], 1, false, 0, nullptr, buf(qi));
+      else {
+        snprintf(qp, sizeof(qp), "inner%d_%d", l + 1, pass);
+        conv(ln, buf(rq), d->H[l - 1], d->W[l - 1], 1, false, 2, buf(qp), buf(qi));
+      }
+      conv(on, buf(qi), d->H[l - 1], d->W[l - 1], 1, false, 0, nullptr, buf(qo));
+    }
+  }
+
+  const void* level_feat(int l) const {  // p2..p6 as seen by RPN / ROI heads
+    char q[24];
+    if (d->cfg.middle_fusion || l == 6) { snprintf(q, sizeof(q), "p%d", l); return buf(q); }
+    snprintf(q, sizeof(q), "pout%d_0", l);
+    return buf(q);
+  }
+
+  int run(const float* images, int img_h, int img_w, float out_h, float out_w, const pe_detections& o) {
+    const pe_detector_config& c = d->cfg;
+    const int Ctot = c.in_channels;
+    if (c.middle_fusion) {  // shared backbone on both halves, channel concat (rcnn.py:240-248)
+      backbone(images, Ctot, 0, img_h, img_w, 0);
+      backbone(images, Ctot, 3, img_h, img_w, 1);
+      for (int l = 2; l <= 5 && status == PE_OK; ++l) {
+        char qa[24], qb[24], qp[16];
+        snprintf(qa, sizeof(qa), "pout%d_0", l);
+        snprintf(qb, sizeof(qb), "pout%d_1", l);
+        snprintf(qp, sizeof(qp), "p%d", l);
+        check(launch_concat_channels(buf(qa), buf(qb), buf(qp), (long long)B * d->H[l - 1] * d->W[l - 1], 256, st));
+      }
+    } else {
+      backbone(images, Ctot, 0, img_h, img_w, 0);
+    }
+    check(launch_subsample2(level_feat(5), buf("p6"), B, d->H[4], d->W[4], d->fc, st));
+    // RPN head on p2..p6 (rpn.py:74-85): 3x3+ReLU, then objectness + deltas as one 16-wide fp32 GEMM
+    RpnLevels lv;
+    for (int l = 2; l <= 6; ++l) {
+      char q[16];
+      snprintf(q, sizeof(q), "rpn_out%d", l);
+      conv("proposal_generator.rpn_head.conv", level_feat(l), d->H[l - 1], d->W[l - 1], 1, true, 0, nullptr, buf("rpn_t"));
+      conv("proposal_generator.rpn_head", buf("rpn_t"), d->H[l - 1], d->W[l - 1], 1, false, 0, nullptr, buf(q), true);
+      lv.out[l - 2] = reinterpret_cast<const float*>(buf(q));
+      lv.H[l - 2] = d->H[l - 1];
+      lv.W[l - 2] = d->W[l - 1];
+      lv.stride[l - 2] = 2 << (l - 1);
+      const double size = 32.0 * (1 << (l - 2));
+      const double ratios[3] = {0.5, 1.0, 2.0};
+      for (int a = 0; a < 3; ++a) {  // anchor_generator.py:151-187
+        const double w = sqrt(size * size / ratios[a]), h = ratios[a] * w;
+        lv.anchor[l - 2][a][0] = (float)(-w / 2.0);
+        lv.anchor[l - 2][a][1] = (float)(-h / 2.0);
+        lv.anchor[l - 2][a][2] = (float)(w / 2.0);
+        lv.anchor[l - 2][a][3] = (float)(h / 2.0);
+      }
+    }
+    RpnScratch rs;
+    rs.cand_box = reinterpret_cast<float4*>(buf("cand_box"));
+    rs.cand_score = reinterpret_cast<float*>(buf("cand_score"));
+    rs.cand_valid = reinterpret_cast<unsigned char*>(buf("cand_valid"));
+    rs.cand_count = reinterpret_cast<int*>(buf("cand_count"));
+    rs.keep_idx = reinterpret_cast<int*>(buf("keep_idx"));
+    rs.keep_count = reinterpret_cast<int*>(buf("keep_count"));
+    float4* props = reinterpret_cast<float4*>(buf("proposals"));
+    int* prop_count = reinterpret_cast<int*>(buf("prop_count"));
+    if (status == PE_OK)
+      check(launch_rpn_proposals(lv, B, c.pre_nms_topk, c.post_nms_topk, c.rpn_nms_thresh, (float)img_h, (float)img_w, rs, kMaxProps,
+                                 props, prop_count, st));
+    // ROI heads (roi_heads.py:595-631)
+    RoiLevels fl;
+    for (int l = 2; l <= 5; ++l) {
+      fl.feat[l - 2] = reinterpret_cast<const __nv_bfloat16*>(level_feat(l));
+      fl.H[l - 2] = d->H[l - 1];
+      fl.W[l - 2] = d->W[l - 1];
+      fl.scale[l - 2] = 1.0f / (float)(2 << (l - 1));
+    }
+    if (status == PE_OK) check(launch_roi_align(fl, props, prop_count, B, kMaxProps, d->fc, buf("roi_feats"), st));
+    linear("roi_heads.box_head.fc1", buf("roi_feats"), B * kMaxProps, true, buf("fc1_out"), false);
+    linear("roi_heads.box_head.fc2", buf("fc1_out"), B * kMaxProps, true, buf("fc2_out"), false);
+    linear("roi_heads.box_predictor", buf("fc2_out"), B * kMaxProps, false, buf("head_out"), true);
+    HeadParams hp;
+    hp.img_h = (float)img_h; hp.img_w = (float)img_w; hp.out_h = out_h; hp.out_w = out_w;
+    hp.scale_x = (float)((double)out_w / (double)img_w);
+    hp.scale_y = (float)((double)out_h / (double)img_h);
+    hp.score_thresh = c.score_thresh; hp.nms_thresh = c.nms_thresh; hp.max_det = c.detections_per_image;
+    DetOut out;
+    out.boxes = reinterpret_cast<float4*>(o.boxes); out.scores = o.scores; out.classes = o.classes; out.logits = o.class_logits;
+    out.probs = o.probs; out.vars = o.vars; out.roi_index = o.roi_index; out.count = o.counts;
+    if (status == PE_OK)
+      check(launch_head_post(reinterpret_cast<const float*>(buf("head_out")), d->npad, props, prop_count, B, kMaxProps, c.num_classes, hp, out, st));
+    return status;
+  }
+};
+
+}  // namespace
+}  // namespace pe
+
+extern "C" PE_API int pe_detector_create(const pe_detector_config* cfg, pe_detector** out) {
+  if (!cfg || !out) return PE_ERR_INVALID_ARGUMENT;
+  if (cfg->depth != 50 && cfg->depth != 101) return PE_ERR_UNSUPPORTED;
+  if (cfg->num_classes != 1 && cfg->num_classes != 3) return PE_ERR_UNSUPPORTED;
+  if (cfg->max_batch < 1 || cfg->canvas_h % 32 || cfg->canvas_w % 32 || cfg->canvas_h < 64 || cfg->canvas_w < 64) return PE_ERR_INVALID_ARGUMENT;
+  if (cfg->middle_fusion ? cfg->in_channels != 6 : (cfg->in_channels < 1 || cfg->in_channels > 4)) return PE_ERR_INVALID_ARGUMENT;
+  if (cfg->pre_nms_topk < 1 || cfg->pre_nms_topk > pe::kTopkSlots || cfg->post_nms_topk < 1 || cfg->post_nms_topk > pe::kMaxProps)
+    return PE_ERR_UNSUPPORTED;
+  if (cfg->detections_per_image < 1 || cfg->detections_per_image > pe::kMaxDet) return PE_ERR_UNSUPPORTED;
+  pe_detector* d = new pe_detector();
+  d->cfg = *cfg;
+  pe::build_plan(d);
+  *out = d;
+  return PE_OK;
+}
+
+extern "C" PE_API void pe_detector_destroy(pe_detector* d) { delete d; }
+
+extern "C" PE_API int pe_detector_num_params(const pe_detector* d) { return d ? (int)d->params.size() : 0; }
+
+extern "C" PE_API int pe_detector_param_info(const pe_detector* d, int i, pe_param_info* info) {
+  if (!d || !info || i < 0 || i >= (int)d->params.size()) return PE_ERR_INVALID_ARGUMENT;
+  const pe::Param& p = d->params[i];
+  memset(info, 0, sizeof(*info));
+  snprintf(info->name, sizeof(info->name), "%s", p.name.c_str());
+  info->kind = p.kind; info->cout = p.Cout; info->kh = p.KH; info->kw = p.KW; info->cin = p.Cin;
+  info->weight_offset = p.w_off; info->bias_offset = p.b_off;
+  return PE_OK;
+}
+
+extern "C" PE_API size_t pe_detector_weight_bytes(const pe_detector* d) { return d ? d->weight_bytes : 0; }
+extern "C" PE_API size_t pe_detector_workspace_bytes(const pe_detector* d) { return d ? d->ws_bytes : 0; }
+
+extern "C" PE_API int pe_detector_buffer_info(const pe_detector* d, const char* name, size_t* offset, int* dims4, int* elem_bytes) {
+  if (!d || !name) return PE_ERR_INVALID_ARGUMENT;
+  const pe::Buf* b = d->find_buf(name);
+  if (!b) return PE_ERR_INVALID_ARGUMENT;
+  if (offset) *offset = b->off;
+  if (dims4) for (int i = 0; i < 4; ++i) dims4[i] = b->d[i];
+  if (elem_bytes) *elem_bytes = b->elem;
+  return PE_OK;
+}
+
+extern "C" PE_API int pe_detector_forward(pe_detector* d, const void* weights, const float* images, int B, int img_h, int img_w,
+                                          float out_h, float out_w, const pe_detections* out, void* workspace, size_t workspace_bytes,
+                                          void* stream) {
+  if (!d || !weights || !images || !out || !workspace) return PE_ERR_INVALID_ARGUMENT;
+  if (B < 1 || B > d->cfg.max_batch) return PE_ERR_INVALID_ARGUMENT;
+  if (img_h < 1 || img_w < 1 || img_h > d->cfg.canvas_h || img_w > d->cfg.canvas_w) return PE_ERR_INVALID_ARGUMENT;
+  if (workspace_bytes < d->ws_bytes) return PE_ERR_WORKSPACE_TOO_SMALL;
+  pe::Runner r;
+  r.d = d;
+  r.wts = reinterpret_cast<const unsigned char*>(weights);
+  r.ws = reinterpret_cast<unsigned char*>(workspace);
+  r.st = reinterpret_cast<cudaStream_t>(stream);
+  r.B = B;
+  return r.run(images, img_h, img_w, out_h, out_w, *out);
+}
+
+extern "C" PE_API int pe_pack_detections(const pe_detections* models, int M, int B, int K, int32_t* det_offsets, float* boxes,
+                                         float* scores, int32_t* classes, float* probs, float* vars, void* stream) {
+  if (!models || M < 1 || M > 4 || B < 1 || !det_offsets) return PE_ERR_INVALID_ARGUMENT;
+  pe::PackIn in;
+  for (int m = 0; m < M; ++m) {
+    in.boxes[m] = reinterpret_cast<const float4*>(models[m].boxes);
+    in.scores[m] = models[m].scores; in.classes[m] = models[m].classes; in.probs[m] = models[m].probs;
+    in.vars[m] = models[m].vars; in.count[m] = models[m].counts;
+  }
+  return pe::launch_pack(in, B, M, K, det_offsets, reinterpret_cast<float4*>(boxes), scores, classes, probs, vars,
+                         reinterpret_cast<cudaStream_t>(stream));
+}
+
+// ---------------------------------------------------------------------------------------------- op-level entry points
+extern "C" PE_API int pe_rpn_proposals(const float* const* rpn_out, const int* H, const int* W, int B, int pre_nms_topk,
+                                       int post_nms_topk, float nms_thresh, float img_h, float img_w, float* proposals,
+                                       int32_t* proposal_counts, void* workspace, size_t workspace_bytes, void* stream) {
+  if (!rpn_out || !H || !W || !proposals || !proposal_counts || !workspace || B < 1) return PE_ERR_INVALID_ARGUMENT;
+  if (workspace_bytes < pe_rpn_proposals_workspace_bytes(B)) return PE_ERR_WORKSPACE_TOO_SMALL;
+  pe::RpnLevels lv;
+  for (int l = 0; l < pe::kRpnLevels; ++l) {
+    lv.out[l] = rpn_out[l]; lv.H[l] = H[l]; lv.W[l] = W[l]; lv.stride[l] = 4 << l;
+    const double size = 32.0 * (1 << l);
+    const double ratios[3] = {0.5, 1.0, 2.0};
+    for (int a = 0; a < 3; ++a) {
+      const double w = sqrt(size * size / ratios[a]), h = ratios[a] * w;
+      lv.anchor[l][a][0] = (float)(-w / 2.0); lv.anchor[l][a][1] = (float)(-h / 2.0);
+      lv.anchor[l][a][2] = (float)(w / 2.0); lv.anchor[l][a][3] = (float)(h / 2.0);
+    }
+  }
+  unsigned char* ws = reinterpret_cast<unsigned char*>(workspace);
+  const size_t n = (size_t)B * pe::kRpnLevels * pe::kTopkSlots;
+  pe::RpnScratch rs;
+  rs.cand_box = reinterpret_cast<float4*>(ws); ws += n * 16;
+  rs.cand_score = reinterpret_cast<float*>(ws); ws += n * 4;
+  rs.keep_idx = reinterpret_cast<int*>(ws); ws += n * 4;
+  rs.cand_count = reinterpret_cast<int*>(ws); ws += (size_t)B * pe::kRpnLevels * 4;
+  rs.keep_count = reinterpret_cast<int*>(ws); ws += (size_t)B * pe::kRpnLevels * 4;
+  rs.cand_valid = ws;
+  return pe::launch_rpn_proposals(lv, B, pre_nms_topk, post_nms_topk, nms_thresh, img_h, img_w, rs, pe::kMaxProps,
+                                  reinterpret_cast<float4*>(proposals), proposal_counts, reinterpret_cast<cudaStream_t>(stream));
+}
+
+extern "C" PE_API size_t pe_rpn_proposals_workspace_bytes(int B) {
+  const size_t n = (size_t)(B > 0 ? B : 0) * pe::kRpnLevels * pe::kTopkSlots;
+  return n * (16 + 4 + 4 + 1) + (size_t)(B > 0 ? B : 0) * pe::kRpnLevels * 8 + 256;
+}
+
+extern "C" PE_API int pe_roi_align_fwd(const void* const* features, const int* H, const int* W, int C, const float* proposals,
+                                       const int32_t* proposal_counts, int B, int max_props, void* out, void* stream) {
+  if (!features || !H || !W || !proposals || !proposal_counts || !out || B < 1 || max_props < 1) return PE_ERR_INVALID_ARGUMENT;
+  pe::RoiLevels fl;
+  for (int l = 0; l < 4; ++l) {
+    fl.feat[l] = reinterpret_cast<const __nv_bfloat16*>(features[l]);
+    fl.H[l] = H[l]; fl.W[l] = W[l]; fl.scale[l] = 1.0f / (float)(4 << l);
+  }
+  return pe::launch_roi_align(fl, reinterpret_cast<const float4*>(proposals), proposal_counts, B, max_props, C, out,
+                              reinterpret_cast<cudaStream_t>(stream));
+}
+
+extern "C" PE_API int pe_head_postprocess(const float* head_out, int npad, const float* proposals, const int32_t* proposal_counts,
+                                          int B, int max_props, int K, float img_h, float img_w, float out_h, float out_w,
+                                          float score_thresh, float nms_thresh, int detections_per_image,
+                                          const pe_detections* out, void* stream) {
+  if (!head_out || !proposals || !proposal_counts || !out || B < 1) return PE_ERR_INVALID_ARGUMENT;
+  if (npad < (K + 1) + 4 * K + 1) return PE_ERR_INVALID_ARGUMENT;
+  pe::HeadParams hp;
+  hp.img_h = img_h; hp.img_w = img_w; hp.out_h = out_h; hp.out_w = out_w;
+  hp.scale_x = (float)((double)out_w / (double)img_w);
+  hp.scale_y = (float)((double)out_h / (double)img_h);
+  hp.score_thresh = score_thresh; hp.nms_thresh = nms_thresh; hp.max_det = detections_per_image;
+  pe::DetOut o;
+  o.boxes = reinterpret_cast<float4*>(out->boxes); o.scores = out->scores; o.classes = out->classes; o.logits = out->class_logits;
+  o.probs = out->probs; o.vars = out->vars; o.roi_index = out->roi_index; o.count = out->counts;
+  return pe::launch_head_post(head_out, npad, reinterpret_cast<const float4*>(proposals), proposal_counts, B, max_props, K, hp, o,
+                              reinterpret_cast<cudaStream_t>(stream));
+}

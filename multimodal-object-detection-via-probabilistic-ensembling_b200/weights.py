@@ -58,7 +58,7 @@ def random_state_dict(depth=50, in_channels=3, num_classes=3, seed=0, middle_fus
     r = "proposal_generator.rpn_head"
     sd[r + ".conv.weight"] = _conv_w(g, fc, fc, 3)
     sd[r + ".conv.bias"] = 0.02 * torch.randn(fc, generator=g)
-    sd[r + ".objectness_logits.weight"] = _conv_w(g, 3, fc, 1, 2.0)
+    sd[r + ".objectness_logits.weight"] = _conv_w(g, 3, fc, 1, 0.3)
     sd[r + ".objectness_logits.bias"] = torch.zeros(3)
     sd[r + ".anchor_deltas.weight"] = _conv_w(g, 12, fc, 1, 0.15)
     sd[r + ".anchor_deltas.bias"] = torch.zeros(12)
@@ -69,7 +69,7 @@ def random_state_dict(depth=50, in_channels=3, num_classes=3, seed=0, middle_fus
     sd[h + ".fc2.bias"] = 0.02 * torch.randn(1024, generator=g)
     q = "roi_heads.box_predictor"
     K = num_classes
-    sd[q + ".cls_score.weight"] = torch.randn(K + 1, 1024, generator=g) * (0.12 * head_gain)
+    sd[q + ".cls_score.weight"] = torch.randn(K + 1, 1024, generator=g) * (0.08 * head_gain)
     sd[q + ".cls_score.bias"] = torch.zeros(K + 1)
     sd[q + ".bbox_pred.weight"] = torch.randn(4 * K, 1024, generator=g) * 0.02
     sd[q + ".bbox_pred.bias"] = torch.zeros(4 * K)
