@@ -194,6 +194,217 @@ def run_fusion(args):
     return out
 
 
+# ------------------------------------------------------------------------------- pairs workload (GPU)
+def detector_gflop(depth=50, H=800, W=1024, K=3, cin=3, props=1000, fc=256):
+    """Algorithmic FLOPs (2 x MAC) of one detector forward, the BASELINE.md §3 accounting."""
+    blocks = {50: (3, 4, 6, 3), 101: (3, 4, 23, 3)}[depth]
+    mac = (H // 2) * (W // 2) * 64 * 49 * cin
+    c_in, h, w = 64, H // 4, W // 4
+    for s, nb in enumerate(blocks):
+        mid, cout = 64 << s, 256 << s
+        for b in range(nb):
+            if b == 0 and s > 0:
+                ho, wo = h // 2, w // 2
+            else:
+                ho, wo = h, w
+            if b == 0:
+                mac += ho * wo * cout * c_in
+            mac += ho * wo * mid * c_in + ho * wo * mid * mid * 9 + ho * wo * cout * mid
+            c_in, h, w = cout, ho, wo
+    conv = mac
+    for l, c in zip((2, 3, 4, 5), (256, 512, 1024, 2048)):
+        hh, ww = H >> l, W >> l
+        conv += hh * ww * 256 * c + hh * ww * 256 * 256 * 9
+    for l in (2, 3, 4, 5, 6):
+        hh, ww = (H >> l, W >> l) if l < 6 else (((H >> 5) - 1) // 2 + 1, ((W >> 5) - 1) // 2 + 1)
+        conv += hh * ww * (fc * fc * 9 + fc * 15)
+    head = props * (49 * fc * 1024 + 1024 * 1024 + 1024 * (K + 1 + 4 * K + 1))
+    return 2e-9 * conv, 2e-9 * head
+
+
+def synth_frames(B, seed):
+    """Synthetic 640x512 pair: RGB = U{0..255}^3, thermal = one plane replicated x3 (what cv2.imread returns for
+    the 8-bit thermal JPEGs)."""
+    rng = np.random.default_rng(seed)
+    rgb = rng.integers(0, 256, size=(B, 512, 640, 3), dtype=np.uint8)
+    th = np.repeat(rng.integers(0, 256, size=(B, 512, 640, 1), dtype=np.uint8), 3, axis=3)
+    return rgb, th
+
+
+def run_pairs(args):
+    import torch
+    from probenb200 import detector, ops, pipeline, weights
+    rank, local_rank, world = dist_env()
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py needs a CUDA device (no CPU fallback exists)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda:%d" % local_rank)
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+    B, K, depth = args.batch, 3, args.depth
+    method = (args.score_fusion, args.box_fusion)
+    nh, nw = detector.resize_shortest_edge_shape(512, 640)
+    canvas = ((nh + 31) // 32 * 32, (nw + 31) // 32 * 32)
+    dets = [detector.Detector(weights.random_state_dict(depth, 3, K, seed=11 + m), depth=depth, num_classes=K, max_batch=B,
+                              canvas=canvas, device=dev) for m in range(2)]
+    pipe = pipeline.ProbEnPipeline(dets, method, frame_size=(512, 640))
+    rgb, th = synth_frames(B, 777 + rank)
+    host = [torch.from_numpy(rgb).pin_memory(), torch.from_numpy(th).pin_memory()]
+    dev_u8 = [h.to(dev) for h in host]
+    e2e_u8 = [torch.empty_like(d) for d in dev_u8]
+    resized = [torch.empty((B, 3, nh, nw), dtype=torch.float32, device=dev) for _ in range(2)]
+    host_out = torch.empty(pipe.out.words * (world if world > 1 else 1), dtype=torch.int32).pin_memory()
+
+    def forward(frames):
+        for m in range(2):
+            ops.resize_frames(frames[m], (nh, nw), round_u8=True, out=resized[m])
+        out = pipe.forward_device(resized)
+        return pipe.gather(out) if world > 1 else out.flat
+
+    def step_device():
+        forward(dev_u8)
+
+    def step_e2e():
+        for m in range(2):
+            e2e_u8[m].copy_(host[m], non_blocking=True)
+        res = forward(e2e_u8)
+        host_out.copy_(res.reshape(-1), non_blocking=True)
+
+    def barrier():
+        if world > 1:
+            import torch.distributed as dist
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(step, steps, warmup):
+        for _ in range(warmup):
+            step()
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0 = time.time()
+        e0.record()
+        for _ in range(steps):
+            step()
+        e1.record()
+        barrier()
+        t1 = time.time()
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            import torch.distributed as dist
+            t = torch.tensor([ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms, t0, t1
+
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+        time.sleep(0.3)
+    ms, t0, t1 = timed(step_device, args.steps, args.warmup)
+    clocks = sampler.stop(t0, t1) if rank == 0 else None
+    ms_e2e, _, _ = timed(step_e2e, args.steps, args.warmup)
+    # instrumented pass: device time of the tensor-core GEMM launches inside one step
+    for d in dets:
+        d.set_profiling(True)
+    step_device()
+    prof = [d.last_profile() for d in dets]
+    step_device()
+    prof = [d.last_profile() for d in dets]
+    for d in dets:
+        d.set_profiling(False)
+    torch.cuda.synchronize()
+    if rank != 0:
+        return None
+    conv_gf, head_gf = detector_gflop(depth, canvas[0], canvas[1], K)
+    flop_step = 2 * B * (conv_gf + head_gf) * 1e9
+    gemm_ms = sum(p[0] for p in prof)
+    launches = sum(p[2] for p in prof) + 2 + 2 + 2 + (1 if world > 1 else 0)  # + resize x2, pack x2, fuse x2 (+ gather)
+    peaks, peak_kind = measured_peaks()
+    peak_tf = peaks.get("bf16_tflops_sustained", peaks["bf16_tflops"])
+    achieved = flop_step / (gemm_ms * 1e-3) / 1e12
+    counts = [int(d_.counts[:B].sum().item()) for d_ in pipe.dets]
+    fused = int(pipe.out.counts[:B].sum().item())
+    value = world * B * args.steps / (ms * 1e-3)
+    out = {
+        "metric": "RGB+thermal image-pairs/sec end-to-end (dual Faster R-CNN R%d-FPN -> ProbEn)" % depth,
+        "value": value, "unit": "pairs/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "bf16 (tensor-core convs/FCs, fp32 accumulate; fp16 stem operands; fp32 box/NMS/fusion math)",
+        "data": "synthetic",
+        "config": {"workload": "FLIR RGB+thermal dual detector -> ProbEn (%s/%s), batch %d pairs/GPU, 512x640 frames resized to "
+                               "%dx%d (canvas %dx%d), R%d-FPN x2, K=3, 1000 proposals, seeded random weights" %
+                               (method[0], method[1], B, nh, nw, canvas[0], canvas[1], depth),
+                   "global_batch": B * world, "parallelism": "dp%d (pairs sharded, one NCCL all-gather of detections)" % world,
+                   "l2": "per-step activation working set (several GB) >> 126 MB L2; no explicit flush needed",
+                   "detections_per_image": [c / B for c in counts], "fused_per_pair": fused / B},
+        "e2e": {"value": world * B * args.steps / (ms_e2e * 1e-3), "unit": "pairs/s",
+                "h2d_bytes_per_step": int(sum(h.numel() for h in host)), "d2h_bytes_per_step": int(host_out.numel() * 4)},
+        "gpu_launches": launches * args.steps,
+        "clocks": clocks,
+        "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf,
+                     "traffic": None, "peak_kind": peak_kind + " (sustained cuBLAS bf16)", "kernel": "conv_gemm_kernel<*> (tcgen05)",
+                     "algorithmic_gflop_per_step": flop_step / 1e9, "gemm_ms_per_step": gemm_ms,
+                     "gemm_launches_per_step": sum(p[3] for p in prof),
+                     "gemm_share_of_step": gemm_ms / (ms / args.steps),
+                     "step_frac_of_peak": flop_step / (ms / args.steps * 1e-3) / 1e12 / peak_tf},
+    }
+    out["cpu_baseline"] = cpu_pairs_baseline(depth, method, n_pairs=1)
+    return out
+
+
+def cpu_pairs_baseline(depth, method, n_pairs=1, threads=None):
+    """The oracle port of the whole reference path (GeneralizedRCNN x2 on torch CPU fp32 + numpy ProbEn) on host cores."""
+    import torch
+    from oracle import detector_oracle as D
+    from oracle import proben_oracle as O
+    from probenb200 import detector, weights
+    threads = threads or os.cpu_count() or 1
+    torch.set_num_threads(threads)
+    nh, nw = detector.resize_shortest_edge_shape(512, 640)
+    sds = [weights.random_state_dict(depth, 3, 3, seed=11 + m) for m in range(2)]
+    cfg = D.DetCfg(depth=depth)
+    rgb, th = synth_frames(n_pairs, 4242)
+    t = time.perf_counter()
+    for i in range(n_pairs):
+        infos = []
+        for m, fr in enumerate((rgb, th)):
+            x = torch.from_numpy(fr[i]).permute(2, 0, 1).float()[None]
+            x = torch.nn.functional.interpolate(x, size=(nh, nw), mode="bilinear", align_corners=False)[0]
+            r = D.detector_forward([x], [(512, 640)], sds[m], cfg)[0]
+            infos.append({"bbox": r["pred_boxes"].tolist(), "score": r["scores"].tolist(), "class": r["pred_classes"].tolist(),
+                          "prob": r["prob_score"].tolist(), "vars": r["vars"].tolist()})
+        O.late_fusion_dispatch(method, infos)
+    dt = time.perf_counter() - t
+    return {"value": n_pairs / dt, "unit": "pairs/s", "cores": threads, "kind": "port",
+            "sample": "%d synthetic pair(s): oracle/detector_oracle.py (torch CPU fp32, batch 1 per modality, %d threads) + "
+                      "oracle/proben_oracle.py" % (n_pairs, threads)}
+
+
+def run_reference_pairs(args):
+    rank, _, world = dist_env()
+    if rank != 0:
+        return None
+    method = (args.score_fusion, args.box_fusion)
+    vals = []
+    for i in range(min(args.warmup, 1) + min(args.steps, 3)):
+        r = cpu_pairs_baseline(args.depth, method, n_pairs=1)
+        if i >= min(args.warmup, 1):
+            vals.append(r)
+    v = float(np.mean([r["value"] for r in vals]))
+    r = vals[-1]
+    r["value"] = v
+    return {
+        "impl": "reference", "metric": "RGB+thermal image-pairs/sec end-to-end (dual Faster R-CNN R%d-FPN -> ProbEn)" % args.depth,
+        "value": v, "unit": "pairs/s", "n_gpus": world, "steps": len(vals), "warmup": min(args.warmup, 1), "ms_per_step": 1e3 / v,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32 (CPU)", "data": "synthetic",
+        "config": {"workload": "FLIR RGB+thermal dual detector -> ProbEn (%s/%s), 1 pair/step (bounded sample), 512x640 frames "
+                               "resized to 800x1000, R%d-FPN x2, K=3" % (method[0], method[1], args.depth)},
+        "cpu_baseline": r, "e2e": {"value": v, "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+
+
 # -------------------------------------------------------------------------------- CPU legs (oracle port)
 def _cpu_fuse_shard(a):
     method, images = a
@@ -255,10 +466,12 @@ def run_reference_fusion(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
-    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="fusion", choices=["fusion"])
+    ap.add_argument("--workload", default="pairs", choices=["pairs", "fusion"])
+    ap.add_argument("--batch", type=int, default=16, help="image pairs per GPU per step (pairs workload)")
+    ap.add_argument("--depth", type=int, default=50, choices=[50, 101])
     ap.add_argument("--images", type=int, default=1 << 20)
     ap.add_argument("--models", type=int, default=2)
     ap.add_argument("--mean-dets", type=float, default=7.5, dest="mean_dets")
@@ -268,7 +481,10 @@ def main():
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3
-    out = run_reference_fusion(args) if args.impl == "reference" else run_fusion(args)
+    if args.workload == "pairs":
+        out = run_reference_pairs(args) if args.impl == "reference" else run_pairs(args)
+    else:
+        out = run_reference_fusion(args) if args.impl == "reference" else run_fusion(args)
     if out is not None:
         print(json.dumps(out))
 

@@ -1,0 +1,87 @@
+#!/usr/bin/env python
+"""Drop-in for the reference's demo/FLIR/demo_probEn.py (same flags, same input files, same printed lines):
+
+    python demo/FLIR/demo_probEn.py --dataset_path /path/to/FLIR/val --prediction_path out/ \
+        --score_fusion probEn --box_fusion v-avg
+
+Reads ``<prediction_path>val_{thermal_only,early_fusion,middle_fusion}_predictions.json`` (schema of
+demo_FLIR_save_predictions.py:166-176), fuses ALL images in one ``pe_fuse_batch`` launch on the GPU
+(the reference loops image by image in numpy, demo_probEn.py:204-292), and evaluates COCO bbox mAP against
+``<dataset_path>/FLIR_thermal_RGBT_pairs_val.json`` when that file exists.  Extra: ``--save_fused FILE`` writes
+the fused detections as JSON.  Image height/width come from the annotation file (the reference imreads every
+thermal JPEG just to learn H, W - demo_probEn.py:269-271); 512 x 640 is assumed when no annotations are given.
+"""
+import json
+import os
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
+
+from probenb200 import evaluation, fusion  # noqa: E402
+from probenb200.opt import config_parser  # noqa: E402
+from probenb200.structures import Boxes, Instances  # noqa: E402
+from probenb200.synth import image_info  # noqa: E402
+
+
+def apply_late_fusion(det_list, method, img_w=640, img_h=512):
+    """Whole-set version of apply_late_fusion_and_evaluate's loop body; returns list over images of
+    ``Instances`` (or None where no model detected anything, which the reference skips)."""
+    n_img = len(det_list[1]["image"]) if len(det_list) > 1 else len(det_list[0]["image"])
+    images = [[image_info(d, i) for d in det_list] for i in range(n_img)]
+    fused = fusion.late_fusion_batch(method, images, img_w=img_w, img_h=img_h)
+    out = []
+    for r in fused:
+        if r is None:
+            out.append(None)
+            continue
+        inst = Instances([img_h, img_w])
+        inst.pred_boxes = Boxes(r[0])
+        import torch
+        inst.scores = torch.from_numpy(r[1])
+        inst.pred_classes = torch.from_numpy(r[2])
+        out.append(inst)
+    return out
+
+
+def main(argv=None):
+    args = config_parser(argv)
+    pred = args.prediction_path
+    files = [pred + "val_thermal_only_predictions.json", pred + "val_early_fusion_predictions.json",
+             pred + "val_middle_fusion_predictions.json"]
+    for i, f in enumerate(files):
+        print("detection file %d:" % (i + 1), f)
+    if not os.path.exists(args.outfolder):
+        os.mkdir(args.outfolder)
+    dets = [json.load(open(f, "r")) for f in files if os.path.isfile(f)]
+    if len(dets) < 2:
+        raise FileNotFoundError("need at least two prediction files under %r" % pred)
+    method = [args.score_fusion, args.box_fusion]
+    print("Method: ", method)
+    start = time.time()
+    results = apply_late_fusion(dets, method)
+    total = time.time() - start
+    print("Average time:", total / max(1, len(results)))
+    image_ids = dets[1]["image_id"] if len(dets) > 1 else dets[0]["image_id"]
+    coco_dets = []
+    for inst, iid in zip(results, image_ids):
+        if inst is not None:
+            coco_dets += evaluation.instances_to_coco_json(inst.pred_boxes.tensor.numpy(), inst.scores.numpy(),
+                                                           inst.pred_classes.numpy(), iid)
+    out_json = os.path.join(args.outfolder, "probEn_%s_%s_fused.json" % tuple(method))
+    json.dump(coco_dets, open(out_json, "w"))
+    val_json = os.path.join(args.dataset_path or "", "FLIR_thermal_RGBT_pairs_val.json")
+    if args.dataset_path and os.path.isfile(val_json):
+        gt = json.load(open(val_json))
+        ev = evaluation.COCOBBoxEval(gt["annotations"], coco_dets, image_ids=[im["id"] for im in gt["images"]])
+        res = ev.evaluate()
+        print("Evaluation results for bbox:")
+        print(" | ".join("%s %.3f" % (k, v) for k, v in res.items()))
+        return res
+    print("no annotation file at %r: fused detections written to %s" % (val_json, out_json))
+    return None
+
+
+if __name__ == "__main__":
+    main()

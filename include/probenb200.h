@@ -148,6 +148,13 @@ PE_API int pe_detector_buffer_info(const pe_detector* d, const char* name, size_
 PE_API int pe_detector_forward(pe_detector* d, const void* weights, const float* images, int B, int img_h, int img_w,
                                float out_h, float out_w, const pe_detections* out, void* workspace, size_t workspace_bytes,
                                void* stream);
+/* Instrumentation for bench.py: CUDA events around every tensor-core GEMM launch of the next forwards. */
+PE_API int pe_detector_set_profiling(pe_detector* d, int enabled);
+PE_API int pe_detector_last_profile(pe_detector* d, float* gemm_ms, float* span_ms, int* launches, int* gemm_launches);
+/* DefaultPredictor's ResizeShortestEdge (engine/defaults.py:186-190): uint8 HWC frames [B,src_h,src_w,C] ->
+ * float32 CHW [B,C,dst_h,dst_w], bilinear with half-pixel centres; round_u8 mimics PIL's uint8 output. */
+PE_API int pe_resize_frames(const uint8_t* frames, float* out, int B, int C, int src_h, int src_w, int dst_h, int dst_w,
+                            int round_u8, void* stream);
 /* Gathers M models' detections into pe_fuse_batch's packed layout (det_offsets [B*M+1] + SoA rows). */
 PE_API int pe_pack_detections(const pe_detections* models, int M, int B, int K, int32_t* det_offsets, float* boxes,
                               float* scores, int32_t* classes, float* probs, float* vars, void* stream);
@@ -158,7 +165,7 @@ PE_API int pe_pack_detections(const pe_detections* models, int M, int B, int K, 
  * pe_rpn_proposals: find_top_rpn_proposals (modeling/proposal_generator/rpn_outputs.py:52-162) + anchors
  *   (anchor_generator.py:130-199, sizes 32..512 x ratios .5/1/2, strides 4..64) + apply_deltas
  *   (box_regression.py:78-115).  rpn_out[l]: [B, H[l], W[l], 16] fp32 channels-last = 3 objectness logits,
- *   12 anchor deltas (a*4+j), 1 pad.  proposals [B, 1000, 4], proposal_counts [B].
+ *   1 pad, 12 anchor deltas (a*4+j).  proposals [B, 1000, 4], proposal_counts [B].
  * pe_roi_align_fwd: ROIPooler + ROIAlign(7x7, sampling_ratio 0, aligned) (modeling/poolers.py:180-235,
  *   layers/csrc/ROIAlign/ROIAlign_cuda.cu:65-139; pybind seam detectron2._C.roi_align_forward, csrc/vision.cpp:89).
  *   features[l]: p2..p5 [B, H[l], W[l], C] bf16; out [B*max_props, 49, C] bf16 (rows past the count are zero).

@@ -61,6 +61,37 @@ __global__ void stem_im2col_kernel(const float* __restrict__ img, __half* __rest
   }
 }
 
+// ---------------------------------------------------------------------------------------------- frame resize
+// DefaultPredictor's ResizeShortestEdge (engine/defaults.py:186-190, data/transforms/transform.py:81-99): bilinear with
+// half-pixel centres (cv2.INTER_LINEAR / PIL BILINEAR geometry), uint8 HWC frames -> float32 CHW network input.
+// round_u8 reproduces the uint8 output quantisation of the PIL path used for 3-channel uint8 images.
+__global__ void resize_frames_kernel(const unsigned char* __restrict__ src, float* __restrict__ dst, int B, int C, int Hs, int Ws,
+                                     int Hd, int Wd, int round_u8) {
+  const long long total = (long long)B * C * Hd * Wd;
+  const float sy = (float)Hs / (float)Hd, sx = (float)Ws / (float)Wd;
+  for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
+    const int x = (int)(t % Wd);
+    long long r = t / Wd;
+    const int y = (int)(r % Hd);
+    r /= Hd;
+    const int c = (int)(r % C), b = (int)(r / C);
+    float fy = ((float)y + 0.5f) * sy - 0.5f, fx = ((float)x + 0.5f) * sx - 0.5f;
+    int y0 = (int)floorf(fy), x0 = (int)floorf(fx);
+    float ly = fy - (float)y0, lx = fx - (float)x0;
+    int y1 = y0 + 1, x1 = x0 + 1;
+    if (y0 < 0) { y0 = 0; y1 = 0; ly = 0.f; }
+    if (x0 < 0) { x0 = 0; x1 = 0; lx = 0.f; }
+    if (y1 >= Hs) { y1 = Hs - 1; if (y0 >= Hs) y0 = Hs - 1; }
+    if (x1 >= Ws) { x1 = Ws - 1; if (x0 >= Ws) x0 = Ws - 1; }
+    const unsigned char* im = src + (size_t)b * Hs * Ws * C;
+    const float v00 = im[((size_t)y0 * Ws + x0) * C + c], v01 = im[((size_t)y0 * Ws + x1) * C + c];
+    const float v10 = im[((size_t)y1 * Ws + x0) * C + c], v11 = im[((size_t)y1 * Ws + x1) * C + c];
+    float v = (1.f - ly) * ((1.f - lx) * v00 + lx * v01) + ly * ((1.f - lx) * v10 + lx * v11);
+    if (round_u8) v = fminf(fmaxf(rintf(v), 0.f), 255.f);
+    dst[t] = v;
+  }
+}
+
 // ---------------------------------------------------------------------------------------------- pooling
 __global__ void maxpool3x3s2_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ y, int B, int H, int W,
                                     int C, int Ho, int Wo) {
@@ -666,6 +697,14 @@ int launch_stem_im2col(const float* img, void* A, int B, int Ctot, int c0, int C
   const int Ho = Hc / 2, Wo = Wc / 2;
   const long long total = (long long)B * Ho * Wo * (Kp / 8);
   stem_im2col_kernel<<<grid_for(total, 256), 256, 0, st>>>(img, reinterpret_cast<__half*>(A), B, Ctot, c0, C, Hi, Wi, Ho, Wo, Kp, nrm);
+  PE_LAUNCH_CHECK();
+  return PE_OK;
+}
+
+int launch_resize_frames(const unsigned char* src, float* dst, int B, int C, int Hs, int Ws, int Hd, int Wd, int round_u8,
+                         cudaStream_t st) {
+  const long long total = (long long)B * C * Hd * Wd;
+  resize_frames_kernel<<<grid_for(total, 256), 256, 0, st>>>(src, dst, B, C, Hs, Ws, Hd, Wd, round_u8);
   PE_LAUNCH_CHECK();
   return PE_OK;
 }

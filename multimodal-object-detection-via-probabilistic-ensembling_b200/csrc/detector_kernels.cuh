@@ -6,7 +6,7 @@
 namespace pe {
 
 constexpr int kRpnLevels = 5;
-constexpr int kRpnOutC = 16;   // 3 objectness logits + 12 anchor deltas + 1 pad, fp32, channels-last
+constexpr int kRpnOutC = 16;   // 3 objectness logits | 1 pad | 12 anchor deltas, fp32, channels-last
 constexpr int kTopkSlots = 1024;
 constexpr int kMaxDet = 100;   // TEST.DETECTIONS_PER_IMAGE (config/defaults.py:560)
 constexpr float kScaleClamp = 4.135166556742356f;  // log(1000/16), box_regression.py:11
@@ -53,6 +53,8 @@ struct PackIn {
 
 int launch_stem_im2col(const float* img, void* A, int B, int Ctot, int c0, int C, int Hi, int Wi, int Hc, int Wc, int Kp,
                        const StemNorm& nrm, cudaStream_t st);
+int launch_resize_frames(const unsigned char* src, float* dst, int B, int C, int Hs, int Ws, int Hd, int Wd, int round_u8,
+                         cudaStream_t st);
 int launch_maxpool(const void* x, void* y, int B, int H, int W, int C, cudaStream_t st);
 int launch_subsample2(const void* x, void* y, int B, int H, int W, int C, cudaStream_t st);
 int launch_concat_channels(const void* a, const void* b, void* y, long long pixels, int C, cudaStream_t st);

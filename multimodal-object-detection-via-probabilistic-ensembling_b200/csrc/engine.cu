@@ -38,6 +38,11 @@ size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
 struct pe_detector {
   pe_detector_config cfg;
+  // optional per-forward instrumentation (pe_detector_set_profiling): CUDA events around every GEMM launch
+  bool profiling = false;
+  std::vector<cudaEvent_t> ev;
+  int ev_used = 0;
+  int last_launches = 0, last_gemm_launches = 0;
   std::vector<pe::Param> params;
   std::vector<pe::Buf> bufs;
   size_t weight_bytes = 0, ws_bytes = 0;
@@ -171,7 +176,7 @@ void build_plan(pe_detector* d) {
 }
 
 struct Runner {
-  const pe_detector* d;
+  pe_detector* d;
   const unsigned char* wts;
   unsigned char* ws;
   cudaStream_t st;
@@ -179,6 +184,25 @@ struct Runner {
   int status = PE_OK;
 
   void* buf(const char* name) const { return ws + d->find_buf(name)->off; }
+
+  int gemm(const pe_conv_desc& cd, const void* x, const void* w, const float* bias, const void* res, void* y) {
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    if (d->profiling) {
+      while ((int)d->ev.size() < d->ev_used + 2) {
+        cudaEvent_t e;
+        if (cudaEventCreate(&e) != cudaSuccess) return PE_ERR_CUDA;
+        d->ev.push_back(e);
+      }
+      e0 = d->ev[d->ev_used++];
+      e1 = d->ev[d->ev_used++];
+      cudaEventRecord(e0, st);
+    }
+    const int s = conv2d_launch(cd, x, w, bias, res, y, st);
+    if (d->profiling) cudaEventRecord(e1, st);
+    d->last_launches++;
+    d->last_gemm_launches++;
+    return s;
+  }
 
   void conv(const std::string& pname, const void* x, int H, int W, int stride, bool relu, int rmode, const void* res, void* y,
             bool out_fp32 = false, bool in_fp16 = false) {
@@ -189,7 +213,7 @@ struct Runner {
     pe_conv_desc cd;
     cd.N = B; cd.H = H; cd.W = W; cd.Cin = p.Cin; cd.Cout = p.Cout; cd.KH = p.KH; cd.KW = p.KW; cd.stride = stride;
     cd.relu = relu; cd.residual_mode = rmode; cd.out_fp32 = out_fp32; cd.in_fp16 = in_fp16;
-    status = conv2d_launch(cd, x, wts + p.w_off, reinterpret_cast<const float*>(wts + p.b_off), res, y, st);
+    status = gemm(cd, x, wts + p.w_off, reinterpret_cast<const float*>(wts + p.b_off), res, y);
   }
   void linear(const std::string& pname, const void* x, int rows, bool relu, void* y, bool out_fp32) {
     if (status != PE_OK) return;
@@ -197,9 +221,9 @@ struct Runner {
     pe_conv_desc cd;
     cd.N = 1; cd.H = 1; cd.W = rows; cd.Cin = p.Cin; cd.Cout = p.Cout; cd.KH = 1; cd.KW = 1; cd.stride = 1;
     cd.relu = relu; cd.residual_mode = 0; cd.out_fp32 = out_fp32; cd.in_fp16 = 0;
-    status = conv2d_launch(cd, x, wts + p.w_off, reinterpret_cast<const float*>(wts + p.b_off), nullptr, y, st);
+    status = gemm(cd, x, wts + p.w_off, reinterpret_cast<const float*>(wts + p.b_off), nullptr, y);
   }
-  void check(int s) { if (status == PE_OK) status = s; }
+  void check(int s, int launches = 1) { if (status == PE_OK) status = s; d->last_launches += launches; }
 
   // ResNet bottom-up + FPN for one backbone pass (input channels [c0, c0 + stem_c) of the image tensor)
   void backbone(const float* images, int Ctot, int c0, int img_h, int img_w, int pass) {
@@ -214,7 +238,7 @@ struct Runner {
         pe_conv_desc cd;
         cd.N = B; cd.H = d->H[0]; cd.W = d->W[0]; cd.Cin = d->stem_kp; cd.Cout = 64; cd.KH = 1; cd.KW = 1; cd.stride = 1;
         cd.relu = 1; cd.residual_mode = 0; cd.out_fp32 = 0; cd.in_fp16 = 1;
-        status = conv2d_launch(cd, buf("stem_cols"), wts + p.w_off, reinterpret_cast<const float*>(wts + p.b_off), nullptr, buf("stem_out"), st);
+        status = gemm(cd, buf("stem_cols"), wts + p.w_off, reinterpret_cast<const float*>(wts + p.b_off), nullptr, buf("stem_out"));
       }
     }
     check(launch_maxpool(buf("stem_out"), buf("pool_out"), B, d->H[0], d->W[0], 64, st));
@@ -316,7 +340,7 @@ struct Runner {
     int* prop_count = reinterpret_cast<int*>(buf("prop_count"));
     if (status == PE_OK)
       check(launch_rpn_proposals(lv, B, c.pre_nms_topk, c.post_nms_topk, c.rpn_nms_thresh, (float)img_h, (float)img_w, rs, kMaxProps,
-                                 props, prop_count, st));
+                                 props, prop_count, st), 3);
     // ROI heads (roi_heads.py:595-631)
     RoiLevels fl;
     for (int l = 2; l <= 5; ++l) {
@@ -362,7 +386,43 @@ extern "C" PE_API int pe_detector_create(const pe_detector_config* cfg, pe_detec
   return PE_OK;
 }
 
-extern "C" PE_API void pe_detector_destroy(pe_detector* d) { delete d; }
+extern "C" PE_API void pe_detector_destroy(pe_detector* d) {
+  if (d) for (cudaEvent_t e : d->ev) cudaEventDestroy(e);
+  delete d;
+}
+
+extern "C" PE_API int pe_detector_set_profiling(pe_detector* d, int enabled) {
+  if (!d) return PE_ERR_INVALID_ARGUMENT;
+  d->profiling = enabled != 0;
+  return PE_OK;
+}
+
+// Synchronises the stream of the last forward through the recorded events and reports the summed device time of
+// the tensor-core GEMM launches, the span from the first to the last of them, and the launch counts.
+extern "C" PE_API int pe_detector_last_profile(pe_detector* d, float* gemm_ms, float* span_ms, int* launches, int* gemm_launches) {
+  if (!d) return PE_ERR_INVALID_ARGUMENT;
+  if (launches) *launches = d->last_launches;
+  if (gemm_launches) *gemm_launches = d->last_gemm_launches;
+  float sum = 0.f, span = 0.f;
+  if (d->profiling && d->ev_used >= 2) {
+    PE_CUDA_CHECK(cudaEventSynchronize(d->ev[d->ev_used - 1]));
+    for (int i = 0; i + 1 < d->ev_used; i += 2) {
+      float ms = 0.f;
+      PE_CUDA_CHECK(cudaEventElapsedTime(&ms, d->ev[i], d->ev[i + 1]));
+      sum += ms;
+    }
+    PE_CUDA_CHECK(cudaEventElapsedTime(&span, d->ev[0], d->ev[d->ev_used - 1]));
+  }
+  if (gemm_ms) *gemm_ms = sum;
+  if (span_ms) *span_ms = span;
+  return PE_OK;
+}
+
+extern "C" PE_API int pe_resize_frames(const uint8_t* frames, float* out, int B, int C, int src_h, int src_w, int dst_h, int dst_w,
+                                       int round_u8, void* stream) {
+  if (!frames || !out || B < 1 || C < 1 || src_h < 1 || src_w < 1 || dst_h < 1 || dst_w < 1) return PE_ERR_INVALID_ARGUMENT;
+  return pe::launch_resize_frames(frames, out, B, C, src_h, src_w, dst_h, dst_w, round_u8, reinterpret_cast<cudaStream_t>(stream));
+}
 
 extern "C" PE_API int pe_detector_num_params(const pe_detector* d) { return d ? (int)d->params.size() : 0; }
 
@@ -396,6 +456,9 @@ extern "C" PE_API int pe_detector_forward(pe_detector* d, const void* weights, c
   if (B < 1 || B > d->cfg.max_batch) return PE_ERR_INVALID_ARGUMENT;
   if (img_h < 1 || img_w < 1 || img_h > d->cfg.canvas_h || img_w > d->cfg.canvas_w) return PE_ERR_INVALID_ARGUMENT;
   if (workspace_bytes < d->ws_bytes) return PE_ERR_WORKSPACE_TOO_SMALL;
+  d->ev_used = 0;
+  d->last_launches = 0;
+  d->last_gemm_launches = 0;
   pe::Runner r;
   r.d = d;
   r.wts = reinterpret_cast<const unsigned char*>(weights);

@@ -71,10 +71,11 @@ def pack_weights(sd, manifest, total_bytes, num_classes):
             wd, bd = sd[name + ".anchor_deltas.weight"].float(), sd[name + ".anchor_deltas.bias"].float()
             w = torch.zeros(p["cout"], p["cin"])
             b = torch.zeros(p["cout"])
+            # rows: 3 objectness | 1 zero pad | 12 deltas (a*4+j) so that each anchor's deltas are one aligned float4
             w[: wo.shape[0]] = wo.reshape(wo.shape[0], -1)
-            w[wo.shape[0]: wo.shape[0] + wd.shape[0]] = wd.reshape(wd.shape[0], -1)
+            w[4: 4 + wd.shape[0]] = wd.reshape(wd.shape[0], -1)
             b[: wo.shape[0]] = bo
-            b[wo.shape[0]: wo.shape[0] + wd.shape[0]] = bd
+            b[4: 4 + wd.shape[0]] = bd
             put(p["weight_offset"], w.to(torch.bfloat16))
         elif kind == 4:
             w, b = sd[name + ".weight"].float(), sd[name + ".bias"].float()
@@ -214,6 +215,17 @@ class Detector:
         _lib.check(st, "pe_detector_forward")
         return out
 
+    def set_profiling(self, enabled):
+        _lib.check(self.lib.pe_detector_set_profiling(self.handle, int(enabled)), "pe_detector_set_profiling")
+
+    def last_profile(self):
+        """(gemm_ms, span_ms, launches, gemm_launches) of the last forward (syncs on its last GEMM event)."""
+        g, s = ctypes.c_float(), ctypes.c_float()
+        n, ng = ctypes.c_int(), ctypes.c_int()
+        _lib.check(self.lib.pe_detector_last_profile(self.handle, ctypes.byref(g), ctypes.byref(s), ctypes.byref(n), ctypes.byref(ng)),
+                   "pe_detector_last_profile")
+        return g.value, s.value, n.value, ng.value
+
     def forward(self, batched_inputs):
         """GeneralizedRCNN.forward-compatible entry (inference only): all images must share one size."""
         imgs = torch.stack([x["image"].to(torch.float32) for x in batched_inputs]).to(self.device)
@@ -225,6 +237,24 @@ class Detector:
         return [{"instances": i} for i in inst]
 
     __call__ = forward
+
+
+class DefaultPredictor:
+    """engine/defaults.py:161-198: one BGR uint8 HxWxC frame in, ``{"instances": Instances}`` out; the resize runs
+    on the GPU (``pe_resize_frames``)."""
+
+    def __init__(self, model, min_size=800, max_size=1333):
+        self.model, self.min_size, self.max_size = model, min_size, max_size
+
+    def __call__(self, original_image):
+        from . import ops
+        import numpy as np
+        h, w = original_image.shape[:2]
+        nh, nw = resize_shortest_edge_shape(h, w, self.min_size, self.max_size)
+        u8 = torch.from_numpy(np.ascontiguousarray(original_image.astype(np.uint8)))[None].to(self.model.device)
+        x = ops.resize_frames(u8, (nh, nw), round_u8=original_image.shape[2] == 3)
+        out = self.model.forward_device(x, (h, w))
+        return {"instances": out.to_instances([(h, w)])[0]}
 
 
 def resize_shortest_edge_shape(h, w, short=800, max_size=1333):

@@ -48,7 +48,7 @@ MAX_PROPOSALS = 1000
 
 
 def rpn_proposals(rpn_out, image_size, pre_nms_topk=1000, post_nms_topk=1000, nms_thresh=0.7):
-    """``pe_rpn_proposals``: rpn_out = list of 5 fp32 tensors [B, H_l, W_l, 16] (3 logits | 12 deltas | pad).
+    """``pe_rpn_proposals``: rpn_out = list of 5 fp32 tensors [B, H_l, W_l, 16] (3 logits | pad | 12 deltas).
     Returns (proposals [B,1000,4], counts [B]).  find_top_rpn_proposals of the reference."""
     lib = _lib.load()
     _lib.require_cuda(*rpn_out)
@@ -94,4 +94,20 @@ def head_postprocess(head_out, proposals, counts, K, image_size, out_size, score
                                  float(score_thresh), float(nms_thresh), int(detections_per_image), ctypes.byref(det),
                                  _lib.current_stream_ptr(proposals.device))
     _lib.check(st, "pe_head_postprocess")
+    return out
+
+
+def resize_frames(frames_u8, dst_hw, round_u8=True, out=None):
+    """``pe_resize_frames``: uint8 [B,H,W,C] CUDA frames -> float32 [B,C,dst_h,dst_w] (DefaultPredictor's
+    ResizeShortestEdge + HWC->CHW float32, engine/defaults.py:186-192)."""
+    lib = _lib.load()
+    _lib.require_cuda(frames_u8)
+    if frames_u8.dtype != torch.uint8 or frames_u8.dim() != 4:
+        raise RuntimeError("probenb200.resize_frames: expected uint8 [B,H,W,C]")
+    B, H, W, C = frames_u8.shape
+    if out is None:
+        out = torch.empty((B, C, dst_hw[0], dst_hw[1]), dtype=torch.float32, device=frames_u8.device)
+    st = lib.pe_resize_frames(_lib.ptr(frames_u8), _lib.ptr(out), B, C, H, W, int(dst_hw[0]), int(dst_hw[1]), int(round_u8),
+                              _lib.current_stream_ptr(frames_u8.device))
+    _lib.check(st, "pe_resize_frames")
     return out

@@ -14,13 +14,13 @@ pytestmark = pytest.mark.gpu
 
 
 def pack_rpn(logits, deltas):
-    """oracle NCHW logits (N,3,H,W) + deltas (N,12,H,W) -> [N,H,W,16] fp32 channels-last."""
+    """oracle NCHW logits (N,3,H,W) + deltas (N,12,H,W) -> [N,H,W,16] fp32 channels-last (3 logits|pad|12 deltas)."""
     out = []
     for lg, dl in zip(logits, deltas):
         N, _, H, W = lg.shape
         t = torch.zeros((N, H, W, 16))
         t[..., 0:3] = lg.permute(0, 2, 3, 1)
-        t[..., 3:15] = dl.permute(0, 2, 3, 1)
+        t[..., 4:16] = dl.permute(0, 2, 3, 1)
         out.append(t.contiguous().cuda())
     return out
 

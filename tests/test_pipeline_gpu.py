@@ -1,0 +1,46 @@
+"""Dual detector -> pack -> ProbEn on the GPU: the fused output must equal the CPU oracle's fusion of the GPU
+detectors' OWN detections (checks pe_pack_detections + pe_fuse_batch integration exactly), and the resize kernel
+must match torch's bilinear (half-pixel) interpolation."""
+import numpy as np
+import pytest
+import torch
+
+import proben_cases as pc
+from oracle import proben_oracle as O
+from probenb200 import detector, ops, pipeline, weights
+
+pytestmark = pytest.mark.gpu
+
+
+def test_resize_matches_torch_bilinear():
+    g = torch.Generator().manual_seed(0)
+    u8 = torch.randint(0, 256, (2, 64, 80, 3), dtype=torch.uint8, generator=g)
+    got = ops.resize_frames(u8.cuda(), (100, 125), round_u8=False).cpu()
+    want = torch.nn.functional.interpolate(u8.permute(0, 3, 1, 2).float(), size=(100, 125), mode="bilinear", align_corners=False)
+    assert float((got - want).abs().max()) < 1e-3
+    got8 = ops.resize_frames(u8.cuda(), (100, 125), round_u8=True).cpu()
+    assert float((got8 - want.round().clamp(0, 255)).abs().max()) <= 1.0  # rounding ties may differ by one level
+
+
+def test_pipeline_fusion_equals_oracle_on_gpu_detections():
+    B, K = 2, 3
+    dets = [detector.Detector(weights.random_state_dict(50, 3, K, seed=20 + m), depth=50, num_classes=K, max_batch=B,
+                              canvas=(224, 256)) for m in range(2)]
+    pipe = pipeline.ProbEnPipeline(dets, ("probEn", "v-avg"), frame_size=(128, 160))
+    g = torch.Generator().manual_seed(1)
+    imgs = [(torch.rand(B, 3, 200, 250, generator=g) * 255).cuda() for _ in range(2)]
+    out = pipe.forward_device(imgs)
+    torch.cuda.synchronize()
+    fused = pipeline.FusedOutput.split(out.flat, B, 2)
+    per_model = [d.to_instances([(128, 160)] * B) for d in pipe.dets]
+    assert sum(len(i) for i in per_model[0]) > 0 and sum(len(i) for i in per_model[1]) > 0
+    for b in range(B):
+        infos = []
+        for m in range(2):
+            inst = per_model[m][b]
+            infos.append({"bbox": inst.pred_boxes.tensor.double().tolist(), "score": inst.scores.double().tolist(),
+                          "class": inst.pred_classes.tolist(), "prob": inst.prob_score.double().tolist(),
+                          "vars": inst.vars.double().tolist()})
+        want = O.late_fusion_dispatch(("probEn", "v-avg"), infos, img_w=160, img_h=128)
+        got = None if fused[b] is None else tuple(t.numpy() for t in fused[b])
+        pc.assert_same_detections(got, want, 1e-4, "pipeline img %d" % b)
