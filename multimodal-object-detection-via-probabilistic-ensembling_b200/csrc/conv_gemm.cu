@@ -35,7 +35,7 @@ struct ConvArgs {
   int N, Ho, Wo, Cin, Cout;
   int KH, KW, pad;
   int TH, TW, tiles_h, tiles_w, tiles_n;
-  int k_chunks;  // Cin / 64
+  int k_chunks;  // ceil(Cin / 64)
   int relu, residual_mode, out_fp32, in_fp16;
   int res_H, res_W;  // residual spatial size (mode 2: the coarser map)
   const float* bias;
@@ -89,6 +89,16 @@ __device__ __forceinline__ void tma_load_2d(const CUtensorMap* map, uint64_t* ba
       ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
       : "memory");
 }
+__device__ __forceinline__ void tma_store_4d(const CUtensorMap* map, const void* src, int c0, int c1, int c2, int c3) {
+  asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
+               ::"l"(map), "r"(smem_u32(src)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+               : "memory");
+}
+__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int kPending>
+__device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(kPending) : "memory"); }
+__device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
 }
@@ -140,14 +150,17 @@ __device__ __forceinline__ void tmem_dealloc(uint32_t taddr) {
 }
 
 // ---------------------------------------------------------------------------------------------- configuration
-template <int BLOCK_N>
+constexpr int kIoBytes = kBlockM * 128;  // one 128-row x 64-channel bf16 staging tile (128B-swizzled)
+
+template <int BLOCK_N, bool kStaged>
 struct TileCfg {
   static constexpr int kABytes = kBlockM * kBlockK * 2;   // 16 KB
   static constexpr int kBBytes = BLOCK_N * kBlockK * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
   static constexpr int kStages = BLOCK_N >= 256 ? 4 : (BLOCK_N >= 128 ? 6 : 8);
   static constexpr int kTmemCols = 2 * BLOCK_N < 32 ? 32 : 2 * BLOCK_N;
-  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*alignment slack*/ + 256 /*barriers*/;
+  static constexpr int kIoTotal = kStaged ? 2 * kIoBytes : 0;
+  static constexpr int kSmemBytes = kStages * kStageBytes + kIoTotal + 1024 /*alignment slack*/ + 256 /*barriers*/;
 };
 
 // ---------------------------------------------------------------------------------------------- epilogue helpers
@@ -159,18 +172,25 @@ __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
 }
 
 // ---------------------------------------------------------------------------------------------- kernel
-template <int BLOCK_N>
+// kStaged (bf16 outputs, BLOCK_N >= 64): the epilogue works on 64-channel sub-tiles staged in two 16 KB
+// 128B-swizzled smem buffers: the residual sub-tile is TMA-loaded into the buffer (one sub-tile ahead), each
+// thread adds its accumulator row in place, and one elected thread TMA-stores the buffer (OOB rows/columns of
+// ragged tiles are clipped by the TMA unit).  Otherwise (fp32 / narrow outputs) rows are written directly.
+template <int BLOCK_N, bool kStaged>
 __global__ void __launch_bounds__(kThreads, 1)
-conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, const ConvArgs a) {
-  using Cfg = TileCfg<BLOCK_N>;
+conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+                 const __grid_constant__ CUtensorMap map_out, const __grid_constant__ CUtensorMap map_res, const ConvArgs a) {
+  using Cfg = TileCfg<BLOCK_N, kStaged>;
   extern __shared__ unsigned char smem_dyn[];
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~(uintptr_t)1023);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::kStages * Cfg::kStageBytes);
+  unsigned char* io_stage = smem + Cfg::kStages * Cfg::kStageBytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(io_stage + Cfg::kIoTotal);
   uint64_t* full_bar = bars;
   uint64_t* empty_bar = bars + Cfg::kStages;
   uint64_t* tmem_full = bars + 2 * Cfg::kStages;
   uint64_t* tmem_empty = tmem_full + 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+  uint64_t* res_bar = tmem_empty + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(res_bar + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int tiles_m = a.N * a.tiles_h * a.tiles_w;
@@ -180,6 +200,10 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&map_a);
     tma_prefetch_desc(&map_b);
+    if (kStaged) {
+      tma_prefetch_desc(&map_out);
+      if (a.residual_mode == 1) tma_prefetch_desc(&map_res);
+    }
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < Cfg::kStages; ++s) {
@@ -189,6 +213,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
     for (int s = 0; s < 2; ++s) {
       mbar_init(&tmem_full[s], 1);
       mbar_init(&tmem_empty[s], 4);  // one arrive per epilogue warp
+      mbar_init(&res_bar[s], 1);
     }
     fence_barrier_init();
   }
@@ -215,7 +240,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
               unsigned char* sb = sa + Cfg::kABytes;
               mbar_expect_tx(&full_bar[stage], Cfg::kStageBytes);
               tma_load_4d(&map_a, &full_bar[stage], sa, kc * kBlockK, w0 + kw, h0 + kh, img);
-              tma_load_2d(&map_b, &full_bar[stage], sb, ((kh * a.KW + kw) * a.k_chunks + kc) * kBlockK, n0);
+              tma_load_2d(&map_b, &full_bar[stage], sb, (kh * a.KW + kw) * a.Cin + kc * kBlockK, n0);
               if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
             }
       }
@@ -257,70 +282,178 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
     const int ph = row / a.TW, pw = row - ph * a.TW;
     int acc = 0;
     uint32_t acc_phase = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-      const int nt = tile % a.tiles_n, mt = tile / a.tiles_n;
-      const int tw = mt % a.tiles_w, th = (mt / a.tiles_w) % a.tiles_h, img = mt / (a.tiles_w * a.tiles_h);
-      const int h = th * a.TH + ph, w = tw * a.TW + pw, n0 = nt * BLOCK_N;
-      const bool pix_ok = h < a.Ho && w < a.Wo;
-      const size_t opix = ((size_t)img * a.Ho + h) * a.Wo + w;
-      size_t rpix = opix;
-      if (a.residual_mode == 2) rpix = ((size_t)img * a.res_H + (h >> 1)) * a.res_W + (w >> 1);
-      mbar_wait(&tmem_full[acc], acc_phase);
-      tc_fence_after();
-#pragma unroll 1
-      for (int c0 = 0; c0 < BLOCK_N; c0 += 16) {
-        uint32_t v[16];
-        tmem_ld_32x32b_x16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BLOCK_N + c0), v);
-        tmem_ld_wait();
-        const int ch = n0 + c0;
-        if (pix_ok && ch < a.Cout) {  // Cout is a multiple of 8; a 16-wide chunk may be half valid
-          const int nvalid = a.Cout - ch >= 16 ? 16 : 8;
-          float f[16];
+    if constexpr (kStaged) {
+      constexpr int kSub = BLOCK_N / 64;
+      const bool elected = (warp == kEpilogueWarp0) && (lane == 0);
+      const bool res_tma = a.residual_mode == 1;
+      const int subs = a.Cout - 0 >= BLOCK_N ? kSub : (a.Cout + 63) / 64;  // Cout % 64 == 0 on this path
+      uint32_t g = 0;  // running sub-tile counter: buffer g & 1, residual barrier parity (g >> 1) & 1
+      auto tile_coords = [&](int tile, int& n0, int& w0, int& h0, int& img) {
+        const int nt = tile % a.tiles_n, mt = tile / a.tiles_n;
+        n0 = nt * BLOCK_N;
+        w0 = (mt % a.tiles_w) * a.TW;
+        h0 = ((mt / a.tiles_w) % a.tiles_h) * a.TH;
+        img = mt / (a.tiles_w * a.tiles_h);
+      };
+      auto sub_count = [&](int n0) { const int left = (a.Cout - n0) / 64; return left < kSub ? left : kSub; };
+      if (elected && res_tma && (int)blockIdx.x < num_tiles) {
+        int n0, w0, h0, img;
+        tile_coords(blockIdx.x, n0, w0, h0, img);
+        mbar_expect_tx(&res_bar[0], kIoBytes);
+        tma_load_4d(&map_res, &res_bar[0], io_stage, n0, w0, h0, img);
+      }
+      (void)subs;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        int n0, w0, h0, img;
+        tile_coords(tile, n0, w0, h0, img);
+        const int nsub = sub_count(n0);
+        const int h = h0 + ph, w = w0 + pw;
+        const bool pix_ok = h < a.Ho && w < a.Wo;
+        mbar_wait(&tmem_full[acc], acc_phase);
+        tc_fence_after();
+        for (int s2 = 0; s2 < nsub; ++s2, ++g) {
+          const uint32_t p = g & 1u;
+          unsigned char* io = io_stage + p * kIoBytes;
+          const int ch0 = n0 + s2 * 64;
+          // residual for the FPN top-down path comes straight from the coarser map (nearest 2x)
+          uint4 rr[8];
+          if (a.residual_mode == 2 && pix_ok) {
+            const size_t rpix = ((size_t)img * a.res_H + (h >> 1)) * a.res_W + (w >> 1);
+            const uint4* rp = reinterpret_cast<const uint4*>(a.residual + rpix * a.Cout + ch0);
 #pragma unroll
-          for (int i = 0; i < 16; ++i) f[i] = __uint_as_float(v[i]);
-          if (a.bias) {
+            for (int i = 0; i < 8; ++i) rr[i] = __ldg(rp + i);
+          }
+          uint32_t v[64];
+          const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BLOCK_N + s2 * 64);
+          tmem_ld_32x32b_x16(taddr, v);
+          tmem_ld_32x32b_x16(taddr + 16, v + 16);
+          tmem_ld_32x32b_x16(taddr + 32, v + 32);
+          tmem_ld_32x32b_x16(taddr + 48, v + 48);
+          tmem_ld_wait();
+          if (s2 == nsub - 1) {  // accumulator fully read: hand the TMEM stage back to the MMA warp
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+          }
+          if (res_tma) mbar_wait(&res_bar[p], (g >> 1) & 1u);
+          else epi_bar_sync();  // buffer p is free (elected thread waited for its last TMA store)
+          uint4* myrow = reinterpret_cast<uint4*>(io + row * 128);
 #pragma unroll
-            for (int i = 0; i < 16; i += 4) {
-              if (i < nvalid) {
-                const float4 b4 = __ldg(reinterpret_cast<const float4*>(a.bias + ch + i));
-                f[i] += b4.x; f[i + 1] += b4.y; f[i + 2] += b4.z; f[i + 3] += b4.w;
+          for (int c = 0; c < 8; ++c) {
+            float f[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) f[i] = __uint_as_float(v[c * 8 + i]);
+            if (a.bias) {
+              const float4 b0 = __ldg(reinterpret_cast<const float4*>(a.bias + ch0 + c * 8));
+              const float4 b1 = __ldg(reinterpret_cast<const float4*>(a.bias + ch0 + c * 8 + 4));
+              f[0] += b0.x; f[1] += b0.y; f[2] += b0.z; f[3] += b0.w;
+              f[4] += b1.x; f[5] += b1.y; f[6] += b1.z; f[7] += b1.w;
+            }
+            uint4* slot = myrow + (c ^ (row & 7));  // 128B swizzle: 16-byte chunk index XOR (row mod 8)
+            if (a.residual_mode) {
+              const uint4 r = res_tma ? *slot : rr[c];
+              if (res_tma || pix_ok) {
+                f[0] += bf16_lo(r.x); f[1] += bf16_hi(r.x); f[2] += bf16_lo(r.y); f[3] += bf16_hi(r.y);
+                f[4] += bf16_lo(r.z); f[5] += bf16_hi(r.z); f[6] += bf16_lo(r.w); f[7] += bf16_hi(r.w);
               }
             }
-          }
-          if (a.residual_mode) {
-            const uint4* rp = reinterpret_cast<const uint4*>(a.residual + rpix * a.Cout + ch);
+            if (a.relu) {
 #pragma unroll
-            for (int i = 0; i < 16; i += 8) {
-              if (i < nvalid) {
-                const uint4 r = __ldg(rp + i / 8);
-                f[i] += bf16_lo(r.x); f[i + 1] += bf16_hi(r.x); f[i + 2] += bf16_lo(r.y); f[i + 3] += bf16_hi(r.y);
-                f[i + 4] += bf16_lo(r.z); f[i + 5] += bf16_hi(r.z); f[i + 6] += bf16_lo(r.w); f[i + 7] += bf16_hi(r.w);
+              for (int i = 0; i < 8; ++i) f[i] = fmaxf(f[i], 0.f);
+            }
+            *slot = make_uint4(pack_bf16(f[0], f[1]), pack_bf16(f[2], f[3]), pack_bf16(f[4], f[5]), pack_bf16(f[6], f[7]));
+          }
+          fence_proxy_async();
+          epi_bar_sync();
+          if (elected) {
+            tma_store_4d(&map_out, io, ch0, w0, h0, img);
+            tma_store_commit();
+            tma_store_wait_read<1>();  // the store issued one sub-tile ago has released the other buffer
+            if (res_tma) {             // prefetch the next sub-tile's residual into it
+              int nn0 = n0, nw0 = w0, nh0 = h0, nimg = img, ns = s2 + 1;
+              bool more = true;
+              if (ns == nsub) {
+                const int nt = tile + gridDim.x;
+                more = nt < num_tiles;
+                if (more) tile_coords(nt, nn0, nw0, nh0, nimg);
+                ns = 0;
+              }
+              if (more) {
+                mbar_expect_tx(&res_bar[p ^ 1u], kIoBytes);
+                tma_load_4d(&map_res, &res_bar[p ^ 1u], io_stage + (p ^ 1u) * kIoBytes, nn0 + ns * 64, nw0, nh0, nimg);
               }
             }
-          }
-          if (a.relu) {
-#pragma unroll
-            for (int i = 0; i < 16; ++i) f[i] = fmaxf(f[i], 0.f);
-          }
-          if (a.out_fp32) {
-            float4* op = reinterpret_cast<float4*>(reinterpret_cast<float*>(a.out) + opix * a.Cout + ch);
-#pragma unroll
-            for (int i = 0; i < 16; i += 4)
-              if (i < nvalid) op[i / 4] = make_float4(f[i], f[i + 1], f[i + 2], f[i + 3]);
-          } else {
-            uint4* op = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(a.out) + opix * a.Cout + ch);
-#pragma unroll
-            for (int i = 0; i < 16; i += 8)
-              if (i < nvalid)
-                op[i / 8] = make_uint4(pack_bf16(f[i], f[i + 1]), pack_bf16(f[i + 2], f[i + 3]),
-                                       pack_bf16(f[i + 4], f[i + 5]), pack_bf16(f[i + 6], f[i + 7]));
           }
         }
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&tmem_empty[acc]);
-      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      if (elected) tma_store_wait_all();
+    } else {
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int nt = tile % a.tiles_n, mt = tile / a.tiles_n;
+        const int tw = mt % a.tiles_w, th = (mt / a.tiles_w) % a.tiles_h, img = mt / (a.tiles_w * a.tiles_h);
+        const int h = th * a.TH + ph, w = tw * a.TW + pw, n0 = nt * BLOCK_N;
+        const bool pix_ok = h < a.Ho && w < a.Wo;
+        const size_t opix = ((size_t)img * a.Ho + h) * a.Wo + w;
+        size_t rpix = opix;
+        if (a.residual_mode == 2) rpix = ((size_t)img * a.res_H + (h >> 1)) * a.res_W + (w >> 1);
+        mbar_wait(&tmem_full[acc], acc_phase);
+        tc_fence_after();
+#pragma unroll 1
+        for (int c0 = 0; c0 < BLOCK_N; c0 += 16) {
+          uint32_t v[16];
+          tmem_ld_32x32b_x16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BLOCK_N + c0), v);
+          tmem_ld_wait();
+          const int ch = n0 + c0;
+          if (pix_ok && ch < a.Cout) {  // Cout is a multiple of 8; a 16-wide chunk may be half valid
+            const int nvalid = a.Cout - ch >= 16 ? 16 : 8;
+            float f[16];
+#pragma unroll
+            for (int i = 0; i < 16; ++i) f[i] = __uint_as_float(v[i]);
+            if (a.bias) {
+#pragma unroll
+              for (int i = 0; i < 16; i += 4) {
+                if (i < nvalid) {
+                  const float4 b4 = __ldg(reinterpret_cast<const float4*>(a.bias + ch + i));
+                  f[i] += b4.x; f[i + 1] += b4.y; f[i + 2] += b4.z; f[i + 3] += b4.w;
+                }
+              }
+            }
+            if (a.residual_mode) {
+              const uint4* rp = reinterpret_cast<const uint4*>(a.residual + rpix * a.Cout + ch);
+#pragma unroll
+              for (int i = 0; i < 16; i += 8) {
+                if (i < nvalid) {
+                  const uint4 r = __ldg(rp + i / 8);
+                  f[i] += bf16_lo(r.x); f[i + 1] += bf16_hi(r.x); f[i + 2] += bf16_lo(r.y); f[i + 3] += bf16_hi(r.y);
+                  f[i + 4] += bf16_lo(r.z); f[i + 5] += bf16_hi(r.z); f[i + 6] += bf16_lo(r.w); f[i + 7] += bf16_hi(r.w);
+                }
+              }
+            }
+            if (a.relu) {
+#pragma unroll
+              for (int i = 0; i < 16; ++i) f[i] = fmaxf(f[i], 0.f);
+            }
+            if (a.out_fp32) {
+              float4* op = reinterpret_cast<float4*>(reinterpret_cast<float*>(a.out) + opix * a.Cout + ch);
+#pragma unroll
+              for (int i = 0; i < 16; i += 4)
+                if (i < nvalid) op[i / 4] = make_float4(f[i], f[i + 1], f[i + 2], f[i + 3]);
+            } else {
+              uint4* op = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(a.out) + opix * a.Cout + ch);
+#pragma unroll
+              for (int i = 0; i < 16; i += 8)
+                if (i < nvalid)
+                  op[i / 8] = make_uint4(pack_bf16(f[i], f[i + 1]), pack_bf16(f[i + 2], f[i + 3]),
+                                         pack_bf16(f[i + 4], f[i + 5]), pack_bf16(f[i + 6], f[i + 7]));
+            }
+          }
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      }
     }
   }
   tc_fence_before();
@@ -374,17 +507,19 @@ void pick_patch(int Ho, int Wo, int* TH, int* TW) {
   *TW = bw;
 }
 
-template <int BLOCK_N>
-int launch_conv(const CUtensorMap& ma, const CUtensorMap& mb, const ConvArgs& a, cudaStream_t st) {
-  using Cfg = TileCfg<BLOCK_N>;
+template <int BLOCK_N, bool kStaged>
+int launch_conv(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& mo, const CUtensorMap& mr, const ConvArgs& a,
+                cudaStream_t st) {
+  using Cfg = TileCfg<BLOCK_N, kStaged>;
   static bool attr_done = false;
   if (!attr_done) {
-    PE_CUDA_CHECK(cudaFuncSetAttribute(conv_gemm_kernel<BLOCK_N>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
+    PE_CUDA_CHECK(cudaFuncSetAttribute(conv_gemm_kernel<BLOCK_N, kStaged>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       Cfg::kSmemBytes));
     attr_done = true;
   }
   const int tiles = a.N * a.tiles_h * a.tiles_w * a.tiles_n;
   const int grid = tiles < sm_count() ? tiles : sm_count();
-  conv_gemm_kernel<BLOCK_N><<<grid, kThreads, Cfg::kSmemBytes, st>>>(ma, mb, a);
+  conv_gemm_kernel<BLOCK_N, kStaged><<<grid, kThreads, Cfg::kSmemBytes, st>>>(ma, mb, mo, mr, a);
   PE_LAUNCH_CHECK();
   return PE_OK;
 }
@@ -393,7 +528,7 @@ int launch_conv(const CUtensorMap& ma, const CUtensorMap& mb, const ConvArgs& a,
 
 int conv2d_launch(const pe_conv_desc& d, const void* x, const void* w, const float* bias, const void* residual, void* y,
                   cudaStream_t st) {
-  if (d.N < 1 || d.H < 1 || d.W < 1 || d.Cin < 64 || d.Cin % 64 || d.Cout < 8 || d.Cout % 8) return PE_ERR_INVALID_ARGUMENT;
+  if (d.N < 1 || d.H < 1 || d.W < 1 || d.Cin < 8 || d.Cin % 8 || d.Cout < 8 || d.Cout % 8) return PE_ERR_INVALID_ARGUMENT;
   if (!((d.KH == 1 && d.KW == 1) || (d.KH == 3 && d.KW == 3))) return PE_ERR_UNSUPPORTED;
   if (d.stride != 1 && !(d.stride == 2 && d.KH == 1)) return PE_ERR_UNSUPPORTED;
   if (d.residual_mode < 0 || d.residual_mode > 2 || (d.residual_mode && !residual)) return PE_ERR_INVALID_ARGUMENT;
@@ -412,7 +547,7 @@ int conv2d_launch(const pe_conv_desc& d, const void* x, const void* w, const flo
   a.tiles_w = ceil_div(a.Wo, a.TW);
   const int bn = d.Cout >= 256 ? 256 : (d.Cout >= 128 ? 128 : (d.Cout >= 64 ? 64 : (d.Cout > 16 ? 32 : 16)));
   a.tiles_n = ceil_div(d.Cout, bn);
-  a.k_chunks = d.Cin / kBlockK;
+  a.k_chunks = ceil_div(d.Cin, kBlockK);  // a ragged last chunk is zero-filled by TMA (A and W alike)
   a.relu = d.relu;
   a.residual_mode = d.residual_mode;
   a.out_fp32 = d.out_fp32;
@@ -437,12 +572,29 @@ int conv2d_launch(const pe_conv_desc& d, const void* x, const void* w, const flo
     cuuint32_t box[2] = {(cuuint32_t)kBlockK, (cuuint32_t)bn};
     if (!make_map(&mb, w, 2, dims, strides, box)) return PE_ERR_CUDA;
   }
+  // bf16 outputs with whole 64-channel groups take the smem-staged TMA-store epilogue
+  const bool staged = !d.out_fp32 && bn >= 64 && d.Cout % 64 == 0;
+  CUtensorMap mo = ma, mr = ma;
+  if (staged) {
+    cuuint64_t dims[4] = {(cuuint64_t)d.Cout, (cuuint64_t)a.Wo, (cuuint64_t)a.Ho, (cuuint64_t)d.N};
+    cuuint64_t strides[3] = {(cuuint64_t)d.Cout * 2, (cuuint64_t)a.Wo * d.Cout * 2, (cuuint64_t)a.Ho * a.Wo * d.Cout * 2};
+    cuuint32_t box[4] = {64, (cuuint32_t)a.TW, (cuuint32_t)a.TH, 1};
+    if (!make_map(&mo, y, 4, dims, strides, box)) return PE_ERR_CUDA;
+    if (d.residual_mode == 1 && !make_map(&mr, residual, 4, dims, strides, box)) return PE_ERR_CUDA;
+  }
+  if (staged) {
+    switch (bn) {
+      case 256: return launch_conv<256, true>(ma, mb, mo, mr, a, st);
+      case 128: return launch_conv<128, true>(ma, mb, mo, mr, a, st);
+      default: return launch_conv<64, true>(ma, mb, mo, mr, a, st);
+    }
+  }
   switch (bn) {
-    case 256: return launch_conv<256>(ma, mb, a, st);
-    case 128: return launch_conv<128>(ma, mb, a, st);
-    case 64: return launch_conv<64>(ma, mb, a, st);
-    case 32: return launch_conv<32>(ma, mb, a, st);
-    default: return launch_conv<16>(ma, mb, a, st);
+    case 256: return launch_conv<256, false>(ma, mb, mo, mr, a, st);
+    case 128: return launch_conv<128, false>(ma, mb, mo, mr, a, st);
+    case 64: return launch_conv<64, false>(ma, mb, mo, mr, a, st);
+    case 32: return launch_conv<32, false>(ma, mb, mo, mr, a, st);
+    default: return launch_conv<16, false>(ma, mb, mo, mr, a, st);
   }
 }
 

@@ -31,33 +31,41 @@ __device__ __forceinline__ uint32_t packbf(float a, float b) {
 __device__ __forceinline__ bool finite4(float4 b) { return isfinite(b.x) && isfinite(b.y) && isfinite(b.z) && isfinite(b.w); }
 
 // ---------------------------------------------------------------------------------------------- stem im2col
-__global__ void stem_im2col_kernel(const float* __restrict__ img, __half* __restrict__ A, int B, int Ctot, int c0, int C,
-                                   int Hi, int Wi, int Ho, int Wo, int Kp, StemNorm nrm) {
-  const int groups = Kp >> 3;
-  const long long total = (long long)B * Ho * Wo * groups;
+// Stage 1: normalise (rcnn.py:269-286) into a zero-bordered fp16 HWC4 canvas [B, Hc+6, Wc+8, 4]: image pixel (y, x)
+// sits at (y+3, x+3); the border supplies both the conv's 3-pixel zero padding and the /32 canvas padding.
+__global__ void stem_canvas_kernel(const float* __restrict__ img, __half* __restrict__ canvas, int B, int Ctot, int c0, int C,
+                                   int Hi, int Wi, int Hp, int Wp, StemNorm nrm) {
+  const long long total = (long long)B * Hp * Wp;
   for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
-    const int g = (int)(t % groups);
-    long long pix = t / groups;
-    const int wo = (int)(pix % Wo);
-    pix /= Wo;
-    const int ho = (int)(pix % Ho), b = (int)(pix / Ho);
-    __align__(16) __half v[8];
+    const int xp = (int)(t % Wp);
+    long long r = t / Wp;
+    const int yp = (int)(r % Hp), b = (int)(r / Hp);
+    const int y = yp - 3, x = xp - 3;
+    __align__(8) __half v[4];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const int k = g * 8 + j;
+    for (int c = 0; c < 4; ++c) {
       float val = 0.f;
-      if (k < 49 * C) {
-        const int tap = k / C, c = k - tap * C;
-        const int kh = tap / 7, kw = tap - kh * 7;
-        const int y = 2 * ho - 3 + kh, x = 2 * wo - 3 + kw;
-        if (y >= 0 && y < Hi && x >= 0 && x < Wi) {
-          const float p = __ldg(img + (((size_t)b * Ctot + c0 + c) * Hi + y) * Wi + x);
-          val = __fdiv_rn(p - nrm.mean[c], nrm.std[c]);
-        }
-      }
-      v[j] = __float2half_rn(val);
+      if (c < C && y >= 0 && y < Hi && x >= 0 && x < Wi)
+        val = __fdiv_rn(__ldg(img + (((size_t)b * Ctot + c0 + c) * Hi + y) * Wi + x) - nrm.mean[c], nrm.std[c]);
+      v[c] = __float2half_rn(val);
     }
-    *reinterpret_cast<uint4*>(A + (size_t)t * 8) = *reinterpret_cast<const uint4*>(v);
+    *reinterpret_cast<uint2*>(canvas + (size_t)t * 4) = *reinterpret_cast<const uint2*>(v);
+  }
+}
+
+// Stage 2: A[pixel][kh*32 + kw*4 + c] = canvas[2*ho + kh][2*wo + kw][c] for kh < 7, kw < 8 (kw = 7 and c >= C meet
+// zero weights): every (pixel, kh) is one contiguous 64-byte run of the canvas -> four 16-byte copies.
+__global__ void stem_im2col_kernel(const __half* __restrict__ canvas, __half* __restrict__ A, int B, int Ho, int Wo, int Hp, int Wp) {
+  const long long total = (long long)B * Ho * Wo * 28;
+  for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
+    const int part = (int)(t % 28);
+    long long pix = t / 28;
+    const int kh = part >> 2, quad = part & 3;
+    const int wo = (int)(pix % Wo);
+    const long long r = pix / Wo;
+    const int ho = (int)(r % Ho), b = (int)(r / Ho);
+    const uint4* src = reinterpret_cast<const uint4*>(canvas + (((size_t)b * Hp + 2 * ho + kh) * Wp + 2 * wo) * 4) + quad;
+    reinterpret_cast<uint4*>(A)[t] = __ldg(src);
   }
 }
 
@@ -309,28 +317,43 @@ __device__ __forceinline__ bool iou_gt(float4 a, float aa, float4 b, float ab, f
   return __fdiv_rn(inter, __fsub_rn(__fadd_rn(aa, ab), inter)) > thr;
 }
 
-constexpr int kNmsThreads = 1024;
+constexpr int kNmsThreads = 256;
+constexpr int kNmsRowsPerBlock = 64;
 
-// One block per score-sorted segment of <= 1024 boxes.  keep_idx gets the surviving positions in order.
-__global__ void __launch_bounds__(kNmsThreads) segment_nms_kernel(const float4* __restrict__ boxes, const unsigned char* __restrict__ valid,
-                                                                  const int* __restrict__ counts, int seg_stride, float thr,
-                                                                  int* __restrict__ keep_idx, int* __restrict__ keep_count) {
-  extern __shared__ __align__(16) unsigned char nms_smem[];
-  float4* sb = reinterpret_cast<float4*>(nms_smem);
-  float* sa = reinterpret_cast<float*>(sb + 1024);
-  unsigned* mask = reinterpret_cast<unsigned*>(sa + 1024);  // [n][32]
-  const int seg = blockIdx.x, tid = threadIdx.x, lane = tid & 31;
+// "inter / (area_a + area_b - inter) > thr" with torchvision's float32 rounding: decided without the division
+// unless the margin is within float32 round-off of the threshold.
+__device__ __forceinline__ bool iou_gt_fast(float4 a, float aa, float4 b, float ab, float thr) {
+  const float w = fmaxf(0.f, __fsub_rn(fminf(a.z, b.z), fmaxf(a.x, b.x)));
+  const float h = fmaxf(0.f, __fsub_rn(fminf(a.w, b.w), fmaxf(a.y, b.y)));
+  const float inter = __fmul_rn(w, h);
+  const float uni = __fsub_rn(__fadd_rn(aa, ab), inter);
+  const float d = inter - thr * uni;
+  if (fabsf(d) > 4e-7f * fabsf(uni) && uni > 0.f) return d > 0.f;
+  return __fdiv_rn(inter, uni) > thr;
+}
+
+// Suppression bitmask of score-sorted segments of <= 1024 boxes: block (seg, slice) fills rows
+// [slice*64, slice*64+64) of mask[seg][1024][32] (word w of row i: boxes j = 32w.. with j > i, iou(i, j) > thr).
+__global__ void __launch_bounds__(kNmsThreads) nms_mask_kernel(const float4* __restrict__ boxes, const int* __restrict__ counts,
+                                                               int seg_stride, float thr, unsigned* __restrict__ mask) {
+  __shared__ float4 sb[1024];
+  __shared__ float sa[1024];
+  const int seg = blockIdx.x, tid = threadIdx.x;
   const int n = counts[seg];
+  const int r0 = blockIdx.y * kNmsRowsPerBlock;
+  if (r0 >= n) return;
   const size_t base = (size_t)seg * seg_stride;
-  for (int i = tid; i < n; i += blockDim.x) {
+  for (int i = r0 + tid; i < n; i += blockDim.x) {  // only columns j > r0 are ever compared
     const float4 b = boxes[base + i];
     sb[i] = b;
     sa[i] = __fmul_rn(__fsub_rn(b.z, b.x), __fsub_rn(b.w, b.y));
   }
   __syncthreads();
   const int Wn = (n + 31) >> 5;
-  for (int item = tid; item < n * Wn; item += blockDim.x) {
-    const int i = item / Wn, w = item - i * Wn;
+  const int rows = min(kNmsRowsPerBlock, n - r0);
+  unsigned* mrow = mask + (size_t)seg * 1024 * 32;
+  for (int item = tid; item < rows * Wn; item += blockDim.x) {
+    const int i = r0 + item / Wn, w = item % Wn;
     unsigned bits = 0;
     if (w >= (i >> 5)) {
       const float4 bi = sb[i];
@@ -339,11 +362,25 @@ __global__ void __launch_bounds__(kNmsThreads) segment_nms_kernel(const float4* 
 #pragma unroll 4
       for (int t = 0; t < 32; ++t) {
         const int j = j0 + t;
-        if (j > i && j < n && iou_gt(bi, ai, sb[j], sa[j], thr)) bits |= 1u << t;
+        if (j > i && j < n && iou_gt_fast(bi, ai, sb[j], sa[j], thr)) bits |= 1u << t;
       }
     }
-    mask[i * 32 + w] = bits;
+    mrow[i * 32 + w] = bits;
   }
+}
+
+// Greedy scan over the bitmask: the block stages the rows in shared memory, warp 0 walks them in score order.
+__global__ void __launch_bounds__(1024) nms_scan_kernel(const unsigned* __restrict__ mask, const unsigned char* __restrict__ valid,
+                                                        const int* __restrict__ counts, int seg_stride, int* __restrict__ keep_idx,
+                                                        int* __restrict__ keep_count) {
+  extern __shared__ __align__(16) unsigned char nms_smem[];
+  unsigned* sm = reinterpret_cast<unsigned*>(nms_smem);  // [n][32]
+  const int seg = blockIdx.x, tid = threadIdx.x, lane = tid & 31;
+  const int n = counts[seg];
+  const size_t base = (size_t)seg * seg_stride;
+  const int Wn = (n + 31) >> 5;
+  const uint4* src = reinterpret_cast<const uint4*>(mask + (size_t)seg * 1024 * 32);
+  for (int i = tid; i < n * 8; i += blockDim.x) reinterpret_cast<uint4*>(sm)[i] = __ldg(src + i);
   __syncthreads();
   if (tid < 32) {
     unsigned removed = 0;  // lane w owns word w; invalid boxes start out removed
@@ -356,7 +393,7 @@ __global__ void __launch_bounds__(kNmsThreads) segment_nms_kernel(const float4* 
     for (int i = 0; i < n; ++i) {
       const unsigned rw = __shfl_sync(kFullMask, removed, i >> 5);
       if ((rw >> (i & 31)) & 1u) continue;
-      if (lane < Wn) removed |= mask[i * 32 + lane];
+      if (lane < Wn) removed |= sm[i * 32 + lane];
       if (lane == 0) keep_idx[base + kept] = i;
       ++kept;
     }
@@ -692,11 +729,16 @@ inline int grid_for(long long total, int block) {
 }  // namespace
 
 // ---------------------------------------------------------------------------------------------- launchers
-int launch_stem_im2col(const float* img, void* A, int B, int Ctot, int c0, int C, int Hi, int Wi, int Hc, int Wc, int Kp,
+int launch_stem_im2col(const float* img, void* canvas, void* A, int B, int Ctot, int c0, int C, int Hi, int Wi, int Hc, int Wc,
                        const StemNorm& nrm, cudaStream_t st) {
-  const int Ho = Hc / 2, Wo = Wc / 2;
-  const long long total = (long long)B * Ho * Wo * (Kp / 8);
-  stem_im2col_kernel<<<grid_for(total, 256), 256, 0, st>>>(img, reinterpret_cast<__half*>(A), B, Ctot, c0, C, Hi, Wi, Ho, Wo, Kp, nrm);
+  if (C > 4) return PE_ERR_UNSUPPORTED;
+  const int Ho = Hc / 2, Wo = Wc / 2, Hp = Hc + 6, Wp = Wc + 8;
+  stem_canvas_kernel<<<grid_for((long long)B * Hp * Wp, 256), 256, 0, st>>>(img, reinterpret_cast<__half*>(canvas), B, Ctot, c0, C, Hi, Wi,
+                                                                              Hp, Wp, nrm);
+  PE_LAUNCH_CHECK();
+  const long long total = (long long)B * Ho * Wo * 28;
+  stem_im2col_kernel<<<grid_for(total, 256), 256, 0, st>>>(reinterpret_cast<const __half*>(canvas), reinterpret_cast<__half*>(A), B, Ho, Wo,
+                                                            Hp, Wp);
   PE_LAUNCH_CHECK();
   return PE_OK;
 }
@@ -741,13 +783,15 @@ int launch_rpn_proposals(const RpnLevels& lv, int B, int pre_topk, int post_topk
   if (pre_topk > kTopkCap || pre_topk < 1) return PE_ERR_UNSUPPORTED;
   rpn_topk_kernel<<<dim3(kRpnLevels, B), kTopkThreads, 0, st>>>(lv, pre_topk, img_h, img_w, s.cand_box, s.cand_score, s.cand_valid, s.cand_count);
   PE_LAUNCH_CHECK();
-  const size_t smem = 1024 * sizeof(float4) + 1024 * sizeof(float) + 1024 * 32 * sizeof(unsigned);
+  const size_t smem = 1024 * 32 * sizeof(unsigned);
   static bool attr = false;
   if (!attr) {
-    PE_CUDA_CHECK(cudaFuncSetAttribute(segment_nms_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    PE_CUDA_CHECK(cudaFuncSetAttribute(nms_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr = true;
   }
-  segment_nms_kernel<<<B * kRpnLevels, kNmsThreads, smem, st>>>(s.cand_box, s.cand_valid, s.cand_count, kTopkCap, nms_thr, s.keep_idx, s.keep_count);
+  nms_mask_kernel<<<dim3(B * kRpnLevels, 1024 / kNmsRowsPerBlock), kNmsThreads, 0, st>>>(s.cand_box, s.cand_count, kTopkCap, nms_thr, s.nms_mask);
+  PE_LAUNCH_CHECK();
+  nms_scan_kernel<<<B * kRpnLevels, 1024, smem, st>>>(s.nms_mask, s.cand_valid, s.cand_count, kTopkCap, s.keep_idx, s.keep_count);
   PE_LAUNCH_CHECK();
   rpn_merge_kernel<<<B, 1024, 0, st>>>(s.cand_box, s.cand_score, s.keep_idx, s.keep_count, post_topk, max_props, props, prop_count);
   PE_LAUNCH_CHECK();

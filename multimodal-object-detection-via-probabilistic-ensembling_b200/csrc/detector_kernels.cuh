@@ -26,6 +26,7 @@ struct RpnScratch {
   int* cand_count;            // [B, 5]
   int* keep_idx;              // [B, 5, 1024]
   int* keep_count;            // [B, 5]
+  unsigned* nms_mask;         // [B, 5, 1024, 32] suppression bitmask
 };
 
 struct RoiLevels {
@@ -51,8 +52,9 @@ struct PackIn {
   const int* count[4];
 };
 
-int launch_stem_im2col(const float* img, void* A, int B, int Ctot, int c0, int C, int Hi, int Wi, int Hc, int Wc, int Kp,
+int launch_stem_im2col(const float* img, void* canvas, void* A, int B, int Ctot, int c0, int C, int Hi, int Wi, int Hc, int Wc,
                        const StemNorm& nrm, cudaStream_t st);
+constexpr int kStemK = 224;  // 7 rows x (8 px x 4 ch): K of the stem GEMM (147 real taps, the rest meet zero weights)
 int launch_resize_frames(const unsigned char* src, float* dst, int B, int C, int Hs, int Ws, int Hd, int Wd, int round_u8,
                          cudaStream_t st);
 int launch_maxpool(const void* x, void* y, int B, int H, int W, int C, cudaStream_t st);

@@ -91,7 +91,7 @@ void build_plan(pe_detector* d) {
   const pe_detector_config& c = d->cfg;
   const int* blocks = c.depth == 101 ? kStageBlocks101 : kStageBlocks50;
   d->stem_c = c.middle_fusion ? 3 : c.in_channels;
-  d->stem_kp = (int)align_up((size_t)49 * d->stem_c, 64);
+  d->stem_kp = kStemK;
   d->fc = c.middle_fusion ? 512 : 256;
   d->npad = (int)align_up((size_t)(c.num_classes + 1 + 4 * c.num_classes + 1), 16);
   for (int i = 0; i < 6; ++i) {
@@ -132,6 +132,7 @@ void build_plan(pe_detector* d) {
   // ---- workspace
   const int B = c.max_batch;
   const int passes = c.middle_fusion ? 2 : 1;
+  d->add_buf("stem_canvas", B, c.canvas_h + 6, c.canvas_w + 8, 4, 2);
   d->add_buf("stem_cols", B, d->H[0], d->W[0], d->stem_kp, 2);
   d->add_buf("stem_out", B, d->H[0], d->W[0], 64, 2);
   d->add_buf("pool_out", B, d->H[1], d->W[1], 64, 2);
@@ -167,6 +168,7 @@ void build_plan(pe_detector* d) {
   d->add_buf("cand_count", B, kRpnLevels, 1, 1, 4);
   d->add_buf("keep_idx", B, kRpnLevels, kTopkSlots, 1, 4);
   d->add_buf("keep_count", B, kRpnLevels, 1, 1, 4);
+  d->add_buf("nms_mask", B, kRpnLevels, 1024, 32, 4);
   d->add_buf("proposals", B, kMaxProps, 1, 4, 4);
   d->add_buf("prop_count", B, 1, 1, 1, 4);
   d->add_buf("roi_feats", B * kMaxProps, 1, 1, 49 * d->fc, 2);
@@ -231,7 +233,7 @@ struct Runner {
     StemNorm nrm;
     for (int i = 0; i < 8; ++i) { nrm.mean[i] = 0.f; nrm.std[i] = 1.f; }
     for (int i = 0; i < d->stem_c; ++i) { nrm.mean[i] = c.pixel_mean[c0 + i]; nrm.std[i] = c.pixel_std[c0 + i]; }
-    check(launch_stem_im2col(images, buf("stem_cols"), B, Ctot, c0, d->stem_c, img_h, img_w, c.canvas_h, c.canvas_w, d->stem_kp, nrm, st));
+    check(launch_stem_im2col(images, buf("stem_canvas"), buf("stem_cols"), B, Ctot, c0, d->stem_c, img_h, img_w, c.canvas_h, c.canvas_w, nrm, st), 2);
     {  // 7x7/2 conv as a GEMM over the im2col matrix (fp16 operands keep the 0..255 pixel range exact enough)
       if (status == PE_OK) {
         const Param& p = d->params[d->find_param("backbone.bottom_up.stem.conv1")];
@@ -336,11 +338,12 @@ struct Runner {
     rs.cand_count = reinterpret_cast<int*>(buf("cand_count"));
     rs.keep_idx = reinterpret_cast<int*>(buf("keep_idx"));
     rs.keep_count = reinterpret_cast<int*>(buf("keep_count"));
+    rs.nms_mask = reinterpret_cast<unsigned*>(buf("nms_mask"));
     float4* props = reinterpret_cast<float4*>(buf("proposals"));
     int* prop_count = reinterpret_cast<int*>(buf("prop_count"));
     if (status == PE_OK)
       check(launch_rpn_proposals(lv, B, c.pre_nms_topk, c.post_nms_topk, c.rpn_nms_thresh, (float)img_h, (float)img_w, rs, kMaxProps,
-                                 props, prop_count, st), 3);
+                                 props, prop_count, st), 4);
     // ROI heads (roi_heads.py:595-631)
     RoiLevels fl;
     for (int l = 2; l <= 5; ++l) {
@@ -502,6 +505,7 @@ extern "C" PE_API int pe_rpn_proposals(const float* const* rpn_out, const int* H
   const size_t n = (size_t)B * pe::kRpnLevels * pe::kTopkSlots;
   pe::RpnScratch rs;
   rs.cand_box = reinterpret_cast<float4*>(ws); ws += n * 16;
+  rs.nms_mask = reinterpret_cast<unsigned*>(ws); ws += n * 32 * 4;
   rs.cand_score = reinterpret_cast<float*>(ws); ws += n * 4;
   rs.keep_idx = reinterpret_cast<int*>(ws); ws += n * 4;
   rs.cand_count = reinterpret_cast<int*>(ws); ws += (size_t)B * pe::kRpnLevels * 4;
@@ -513,7 +517,7 @@ extern "C" PE_API int pe_rpn_proposals(const float* const* rpn_out, const int* H
 
 extern "C" PE_API size_t pe_rpn_proposals_workspace_bytes(int B) {
   const size_t n = (size_t)(B > 0 ? B : 0) * pe::kRpnLevels * pe::kTopkSlots;
-  return n * (16 + 4 + 4 + 1) + (size_t)(B > 0 ? B : 0) * pe::kRpnLevels * 8 + 256;
+  return n * (16 + 4 + 4 + 1 + 128) + (size_t)(B > 0 ? B : 0) * pe::kRpnLevels * 8 + 256;
 }
 
 extern "C" PE_API int pe_roi_align_fwd(const void* const* features, const int* H, const int* W, int C, const float* proposals,

@@ -61,10 +61,12 @@ def pack_weights(sd, manifest, total_bytes, num_classes):
             assert tuple(w.shape) == (p["cout"], p["kh"], p["kw"], p["cin"]), (name, tuple(w.shape), p)
             put(p["weight_offset"], w.to(torch.bfloat16))
         elif kind == 2:
+            # stem: K index = kh*32 + kw*4 + c over a 7 x 8 x 4 window (kw = 7 and c >= C are zero)
             w, b = _fold_bn(sd, name)
-            w = w.permute(0, 2, 3, 1).reshape(w.shape[0], -1)
-            wp = torch.zeros(p["cout"], p["cin"])
-            wp[:, : w.shape[1]] = w
+            wp = torch.zeros(p["cout"], 7, 8, 4)
+            wp[:, :, :7, : w.shape[1]] = w.permute(0, 2, 3, 1)
+            wp = wp.reshape(p["cout"], -1)
+            assert wp.shape[1] == p["cin"], (wp.shape, p["cin"])
             put(p["weight_offset"], wp.to(torch.float16))
         elif kind == 3:
             wo, bo = sd[name + ".objectness_logits.weight"].float(), sd[name + ".objectness_logits.bias"].float()

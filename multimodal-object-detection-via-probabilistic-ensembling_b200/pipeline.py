@@ -55,7 +55,7 @@ class FusedOutput:
 class ProbEnPipeline:
     """``detectors``: list of M ``Detector`` objects (same num_classes); model order = fusion order."""
 
-    def __init__(self, detectors, method=("probEn", "v-avg"), iou_thr=0.5, frame_size=(512, 640)):
+    def __init__(self, detectors, method=("probEn", "v-avg"), iou_thr=0.5, frame_size=(512, 640), concurrent=True):
         self.lib = _lib.load()
         self.detectors = list(detectors)
         self.M = len(self.detectors)
@@ -68,10 +68,16 @@ class ProbEnPipeline:
         self.codes = _method_codes(method)
         self.iou_thr = float(iou_thr)
         self.frame_h, self.frame_w = frame_size
-        big = max(self.detectors, key=lambda d: d.ws_bytes)
-        for d in self.detectors:  # all models run back to back on one stream: one scratch arena is enough
-            if d is not big:
-                d.share_workspace(big)
+        # every model runs on its own stream with its own scratch arena, so the latency-bound stages of one
+        # detector (top-k, NMS, head post-processing: a handful of CTAs) overlap the other detector's GEMMs
+        self.streams = [torch.cuda.Stream(device=self.device) for _ in range(self.M)] if concurrent and self.M > 1 else None
+        if self.streams is None:
+            big = max(self.detectors, key=lambda d: d.ws_bytes)
+            for d in self.detectors:
+                if d is not big:
+                    d.share_workspace(big)
+        self.ev_start = torch.cuda.Event()
+        self.ev_done = [torch.cuda.Event() for _ in range(self.M)]
         self.dets = [DetectionBuffers(self.B, self.K, self.device) for _ in range(self.M)]
         self.det_structs = (_lib.Detections * self.M)(*[d.struct() for d in self.dets])
         N = self.B * self.M * MAX_DET
@@ -90,9 +96,20 @@ class ProbEnPipeline:
         B = images[0].shape[0]
         if B != self.B:
             raise RuntimeError("pipeline was built for batch %d" % self.B)
+        main = torch.cuda.current_stream(self.device)
         stream = _lib.current_stream_ptr(self.device)
-        for det, img, buf in zip(self.detectors, images, self.dets):
-            det.forward_device(img, (self.frame_h, self.frame_w), out=buf)
+        if self.streams is None:
+            for det, img, buf in zip(self.detectors, images, self.dets):
+                det.forward_device(img, (self.frame_h, self.frame_w), out=buf)
+        else:
+            self.ev_start.record(main)
+            for m, (det, img, buf) in enumerate(zip(self.detectors, images, self.dets)):
+                with torch.cuda.stream(self.streams[m]):
+                    self.streams[m].wait_event(self.ev_start)
+                    det.forward_device(img, (self.frame_h, self.frame_w), out=buf)
+                    self.ev_done[m].record(self.streams[m])
+            for m in range(self.M):
+                main.wait_event(self.ev_done[m])
         o = self.out
         st = self.lib.pe_pack_detections(self.det_structs, self.M, B, self.K, _lib.ptr(o.offsets), _lib.ptr(self.in_boxes),
                                          _lib.ptr(self.in_scores), _lib.ptr(self.in_classes), _lib.ptr(self.in_probs),
