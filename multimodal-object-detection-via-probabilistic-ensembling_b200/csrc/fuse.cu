@@ -151,163 +151,238 @@ __device__ __forceinline__ void probEn_finish(const float* S, bool bad, float* s
   *cls = am;
 }
 
-// ---- warp-per-image kernel ---------------------------------------------------------------------------
+// ---- packed-warp kernel ----------------------------------------------------------------------------------
+// One warp walks a window of kWin consecutive images and packs as many of them as fit into its 32 lanes
+// (lane <-> detection); every warp collective below runs per segment through member masks, so ~2 typical
+// images (about 15 detections each) share every instruction.  No sort: the next cluster head of a segment is
+// the maximum remaining score (redux.sync max + ballot), ties resolved by lane index.
 
 __device__ __forceinline__ float4 shfl4(float4 v, int src) {
   return make_float4(__shfl_sync(kFullMask, v.x, src), __shfl_sync(kFullMask, v.y, src),
                      __shfl_sync(kFullMask, v.z, src), __shfl_sync(kFullMask, v.w, src));
 }
+__device__ __forceinline__ unsigned score_key(float s) {  // order-preserving float -> uint, never 0 for real scores
+  const unsigned u = __float_as_uint(s);
+  return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
 
-template <int K>
-__global__ void __launch_bounds__(kBlockThreads) fuse_warp_kernel(const FuseArgs a) {
+__device__ __forceinline__ float key_score(unsigned k) {
+  return __uint_as_float((k & 0x80000000u) ? (k & 0x7fffffffu) : ~k);
+}
+
+constexpr int kWin = 4;
+
+// SCORE: PE_SCORE_* ; kNms: the ('max','argmax') torchvision-NMS path
+template <int K, int SCORE, bool kNms>
+__global__ void __launch_bounds__(kBlockThreads) fuse_packed_kernel(const FuseArgs a) {
   const int lane = threadIdx.x & 31;
   const int warps_total = (gridDim.x * blockDim.x) >> 5;
-  const bool nms_path = a.score_mode == PE_SCORE_MAX && a.box_mode == PE_BOX_ARGMAX;
+  const int win = a.M <= 7 ? kWin : 1;
+  const int nwin = (a.B + win - 1) / win;
 
-  for (int img = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; img < a.B; img += warps_total) {
-    const int o = lane <= a.M ? __ldg(a.offs + (size_t)img * a.M + lane) : 0;
-    const int base = __shfl_sync(kFullMask, o, 0);
-    const int n = __shfl_sync(kFullMask, o, a.M) - base;
+  for (int wi = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; wi < nwin; wi += warps_total) {
+    const int img0 = wi * win;
+    const int nimg = min(win, a.B - img0);
+    // offsets of the window: lane L holds offs[img0*M + L]
+    const int no = nimg * a.M;
+    const int o = lane <= no ? __ldg(a.offs + (size_t)img0 * a.M + lane) : 0;
     const int len = __shfl_down_sync(kFullMask, o, 1) - o;
-    const int live = __popc(__ballot_sync(kFullMask, lane < a.M && len > 0));
-    if (n <= 0) {
-      if (lane == 0) a.out_counts[img] = 0;
-      continue;
-    }
-    if (n > 32) {
-      if (lane == 0) {
-        if (n > kMaxBlockDets) a.out_counts[img] = -1;
-        else a.big_list[atomicAdd(a.big_count, 1)] = img;
+    const unsigned nonempty = __ballot_sync(kFullMask, lane < no && len > 0);
+    int cur = 0;
+    while (cur < nimg) {
+      // ---- greedy packing of images cur.. into the 32 lanes (warp-uniform scalar logic)
+      int seg_img[kWin], seg_lo[kWin], seg_n[kWin], seg_live[kWin], seg_base[kWin];
+      int nseg = 0, used = 0;
+      while (cur < nimg) {
+        const int base = __shfl_sync(kFullMask, o, cur * a.M);
+        const int n = __shfl_sync(kFullMask, o, (cur + 1) * a.M) - base;
+        if (n <= 0 || n > 32) {
+          if (lane == 0) {
+            if (n <= 0) a.out_counts[img0 + cur] = 0;
+            else if (n > kMaxBlockDets) a.out_counts[img0 + cur] = -1;
+            else a.big_list[atomicAdd(a.big_count, 1)] = img0 + cur;
+          }
+          ++cur;
+          continue;
+        }
+        if (used + n > 32) break;
+        seg_img[nseg] = img0 + cur;
+        seg_lo[nseg] = used;
+        seg_n[nseg] = n;
+        seg_base[nseg] = base;
+        seg_live[nseg] = __popc((nonempty >> (cur * a.M)) & ((1u << a.M) - 1u));
+        used += n;
+        ++nseg;
+        ++cur;
+        if (nseg == kWin) break;
       }
-      continue;
-    }
-    const bool act = lane < n;
-    const int row = base + (act ? lane : 0);
-    const float4 box = __ldg(a.boxes + row);
-    const float score = __ldg(a.scores + row);
-    const int cls = __ldg(a.classes + row);
-    if (live == 1) {  // single contributing model: pass-through in input order (demo_probEn.py:240-252)
-      if (act) {
+      if (nseg == 0) continue;
+      // ---- lane -> (segment, row)
+      int sg = -1, lo = 0, n = 0, base = 0, live = 0, my_img = 0;
+#pragma unroll
+      for (int s2 = 0; s2 < kWin; ++s2)
+        if (s2 < nseg && lane >= seg_lo[s2] && lane < seg_lo[s2] + seg_n[s2]) {
+          sg = s2; lo = seg_lo[s2]; n = seg_n[s2]; base = seg_base[s2]; live = seg_live[s2]; my_img = seg_img[s2];
+        }
+      const bool act = sg >= 0;
+      const unsigned segmask = act ? (n == 32 ? kFullMask : (((1u << n) - 1u) << lo)) : (1u << lane);
+      const int row = act ? base + (lane - lo) : 0;
+      const float4 box = act ? __ldg(a.boxes + row) : make_float4(0.f, 0.f, 0.f, 0.f);
+      const float score = act ? __ldg(a.scores + row) : 0.f;
+      const int cls = act ? __ldg(a.classes + row) : 0;
+      const bool cluster = act && live >= 2;
+      if (act && live == 1) {  // single contributing model: pass-through in input order (demo_probEn.py:240-252)
         a.out_boxes[row] = box;
         a.out_scores[row] = score;
         a.out_classes[row] = cls;
+        if (lane == lo) a.out_counts[my_img] = n;
       }
-      if (lane == 0) a.out_counts[img] = n;
-      continue;
-    }
+      if (!__any_sync(kFullMask, cluster)) continue;
 
-    // ---- order: rank by counting.  bayes: ties -> higher index first; nms: stable (lower index first)
-    int rank = 0;
-    for (int k = 0; k < n; ++k) {
-      const float sk = __shfl_sync(kFullMask, score, k);
-      rank += (sk > score) || (sk == score && (nms_path ? k < lane : k > lane));
-    }
-
-    float4 mbox = box;  // box used for matching
-    float area;
-    if (nms_path) {
-      float mc = act ? fmaxf(fmaxf(box.x, box.y), fmaxf(box.z, box.w)) : -INFINITY;
-#pragma unroll
-      for (int s = 16; s > 0; s >>= 1) mc = fmaxf(mc, __shfl_xor_sync(kFullMask, mc, s));
-      mbox = offset_box(box, __fmul_rn((float)cls, __fadd_rn(mc, 1.f)));
-      area = nms_area(mbox);
-    } else {
-      area = (box.z - box.x + 1.f) * (box.w - box.y + 1.f);
-    }
-
-    // ---- greedy clustering over heads in rank order
-    unsigned removed = n == 32 ? 0u : ~((1u << n) - 1u);
-    unsigned my_cluster = 0;
-    int my_pos = -1, nheads = 0;
-    while (true) {
-      const unsigned key = ((removed >> lane) & 1u) ? 0xffffffffu : ((unsigned)rank << 5 | (unsigned)lane);
-      const unsigned mn = __reduce_min_sync(kFullMask, key);
-      if (mn == 0xffffffffu) break;
-      const int hl = mn & 31;
-      const float4 hb = shfl4(mbox, hl);
-      const int hc = __shfl_sync(kFullMask, cls, hl);
-      const float ha = __shfl_sync(kFullMask, area, hl);
-      bool m = false;
-      if (!((removed >> lane) & 1u) && lane != hl)
-        m = nms_path ? match_nms(hb, ha, mbox, area, a.thr)
-                     : match_bayes(hb, hc, ha, mbox, cls, area, a.img_w, a.img_h, a.thr);
-      const unsigned mm = __ballot_sync(kFullMask, m);
-      if (lane == hl) { my_cluster = mm; my_pos = nheads; }
-      removed |= mm | (1u << hl);
-      ++nheads;
-    }
-    if (lane == 0) a.out_counts[img] = nheads;
-
-    if (nms_path) {  // survivors keep their own record (demo_probEn.py:66-69)
-      if (my_pos >= 0) {
-        a.out_boxes[base + my_pos] = box;
-        a.out_scores[base + my_pos] = score;
-        a.out_classes[base + my_pos] = cls;
+      float4 mbox = box;
+      float area;
+      if (kNms) {  // torchvision batched_nms coordinate trick: boxes + class * (max coordinate + 1), float32
+        float mc = cluster ? fmaxf(fmaxf(box.x, box.y), fmaxf(box.z, box.w)) : -INFINITY;
+        mc = key_score(__reduce_max_sync(segmask, score_key(mc)));  // segment max through order-preserving keys
+        mbox = offset_box(box, __fmul_rn((float)cls, __fadd_rn(mc, 1.f)));
+        area = nms_area(mbox);
+      } else {
+        area = (box.z - box.x + 1.f) * (box.w - box.y + 1.f);
       }
-      continue;
-    }
 
-    // ---- fold members into heads
-    float pr[K];
-#pragma unroll
-    for (int k = 0; k < K; ++k) pr[k] = act ? __ldg(a.probs + (size_t)row * K + k) : 0.5f / K;
-    const float var = act ? __ldg(a.vars + row) : 1.f;
-    const DetAux<K> me = make_aux<K>(pr, score, var, a.box_mode);
-
-    float S[K + 1];
-#pragma unroll
-    for (int k = 0; k <= K; ++k) S[k] = me.lg[k];
-    bool bad = me.bad;
-    float pmax = me.pmax;
-    double ssum = (double)score, wsum = me.wgt;
-    double bx = me.wgt * (double)box.x, by = me.wgt * (double)box.y, bz = me.wgt * (double)box.z,
-           bw = me.wgt * (double)box.w;
-    int cnt = 1;
-    int best_rank = 0x7fffffff;  // argmax box: earliest member whose score ties the head's
-    float4 best_box = box;
-    unsigned rem = my_cluster;
-    while (__any_sync(kFullMask, rem != 0u)) {
-      const bool has = rem != 0u;
-      const int src = has ? __ffs(rem) - 1 : lane;
-      rem &= rem - 1u;
-      const float4 ob = shfl4(box, src);
-      const float os = __shfl_sync(kFullMask, score, src);
-      const int orank = __shfl_sync(kFullMask, rank, src);
-      const double ow = __shfl_sync(kFullMask, me.wgt, src);
-      const float opmax = __shfl_sync(kFullMask, me.pmax, src);
-      const bool obad = __shfl_sync(kFullMask, (int)me.bad, src);
-      float ol[K + 1];
-#pragma unroll
-      for (int k = 0; k <= K; ++k) ol[k] = __shfl_sync(kFullMask, me.lg[k], src);
-      if (has) {
-#pragma unroll
-        for (int k = 0; k <= K; ++k) S[k] += ol[k];
-        bad |= obad;
-        pmax = fmaxf(pmax, opmax);
-        ssum += (double)os;
-        wsum += ow;
-        bx += ow * (double)ob.x; by += ow * (double)ob.y; bz += ow * (double)ob.z; bw += ow * (double)ob.w;
-        ++cnt;
-        if (os == score && orank < best_rank) { best_rank = orank; best_box = ob; }
-      }
-    }
-    if (my_pos >= 0) {
-      float fs = score;
-      int fc = cls;
-      float4 fb = box;
-      if (cnt > 1) {
-        if (a.score_mode == PE_SCORE_PROBEN) probEn_finish<K>(S, bad, &fs, &fc);
-        else if (a.score_mode == PE_SCORE_AVG) fs = (float)(ssum / (double)cnt);
-        else fs = pmax;
-        if (a.box_mode == PE_BOX_ARGMAX) fb = best_box;
-        else {
-          const double inv = 1.0 / wsum;
-          fb = make_float4((float)(bx * inv), (float)(by * inv), (float)(bz * inv), (float)(bw * inv));
+      // ---- greedy clustering: per segment, head = max remaining score (ties: higher lane for the bayesian
+      //      order, lower lane for torchvision's stable sort)
+      bool removed = !cluster;
+      unsigned my_cluster = 0;
+      int my_pos = -1, nheads = 0;
+      const unsigned skey = score_key(score);
+      while (true) {
+        const unsigned key = removed ? 0u : skey;
+        const unsigned m = __reduce_max_sync(segmask, key);
+        if (!__any_sync(kFullMask, m != 0u)) break;
+        const unsigned cand = __ballot_sync(segmask, key == m && !removed);
+        const int hl = m ? (kNms ? __ffs(cand) - 1 : 31 - __clz(cand)) : lane;
+        const float4 hb = shfl4(mbox, hl);
+        const int hc = __shfl_sync(kFullMask, cls, hl);
+        const float ha = __shfl_sync(kFullMask, area, hl);
+        bool mt = false;
+        if (!removed && lane != hl)
+          mt = kNms ? match_nms(hb, ha, mbox, area, a.thr) : match_bayes(hb, hc, ha, mbox, cls, area, a.img_w, a.img_h, a.thr);
+        const unsigned mm = __ballot_sync(segmask, mt);
+        if (m != 0u) {
+          if (lane == hl) { my_cluster = mm; my_pos = nheads; removed = true; }
+          removed |= mt;
+          ++nheads;
         }
       }
-      a.out_boxes[base + my_pos] = fb;
-      a.out_scores[base + my_pos] = fs;
-      a.out_classes[base + my_pos] = fc;
+      if (cluster && lane == lo) a.out_counts[my_img] = nheads;
+
+      if (kNms) {  // survivors keep their own record (demo_probEn.py:66-69)
+        if (my_pos >= 0) {
+          a.out_boxes[base + my_pos] = box;
+          a.out_scores[base + my_pos] = score;
+          a.out_classes[base + my_pos] = cls;
+        }
+        continue;
+      }
+
+      // ---- per-detection terms, then fold members into their head
+      float lg[K + 1];
+      float pmax = -INFINITY;
+      {
+        double sp = 0.0;
+        bool bad = false;
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+          const float p = cluster ? __ldg(a.probs + (size_t)row * K + k) : 0.25f;
+          sp = __dadd_rn(sp, (double)p);
+          lg[k] = __logf(p);
+          bad |= p < 0.f;
+          pmax = fmaxf(pmax, p);
+        }
+        const double bg = __dsub_rn(1.0, sp);
+        lg[K] = __logf((float)bg);
+        if (bad || bg < 0.0) lg[0] = __int_as_float(0x7fc00000);  // the reference's log(negative) -> NaN posterior
+      }
+      float wgt = 1.f;
+      if (a.box_mode == PE_BOX_VAVG) wgt = cluster ? __frcp_rn(__ldg(a.vars + row)) : 1.f;
+      else if (a.box_mode == PE_BOX_SAVG) wgt = score;
+
+      float S[K + 1];
+#pragma unroll
+      for (int k = 0; k <= K; ++k) S[k] = lg[k];
+      float ssum = score, wsum = wgt, pm = pmax;
+      float dx = 0.f, dy = 0.f, dz = 0.f, dw = 0.f;  // sum of w * (member box - head box): small, exact-ish in fp32
+      int cnt = 1;
+      int best_lane = -1;  // argmax box: first member in cluster order (= highest lane) whose score ties the head's
+      unsigned rem = my_cluster;
+      while (__any_sync(kFullMask, rem != 0u)) {
+        const bool has = rem != 0u;
+        const int src = has ? 31 - __clz(rem) : lane;
+        if (has) rem &= ~(1u << src);
+        const float4 ob = shfl4(box, src);
+        const float ow = __shfl_sync(kFullMask, wgt, src);
+        float ol[K + 1];
+        float os = 0.f, opm = 0.f;
+        if (SCORE == PE_SCORE_PROBEN) {
+#pragma unroll
+          for (int k = 0; k <= K; ++k) ol[k] = __shfl_sync(kFullMask, lg[k], src);
+        } else if (SCORE == PE_SCORE_MAX) {
+          opm = __shfl_sync(kFullMask, pmax, src);
+        }
+        if (SCORE == PE_SCORE_AVG || a.box_mode == PE_BOX_ARGMAX) os = __shfl_sync(kFullMask, score, src);
+        if (has) {
+          if (SCORE == PE_SCORE_PROBEN) {
+#pragma unroll
+            for (int k = 0; k <= K; ++k) S[k] += ol[k];
+          } else if (SCORE == PE_SCORE_MAX) {
+            pm = fmaxf(pm, opm);
+          } else {
+            ssum += os;
+          }
+          wsum += ow;
+          dx += ow * (ob.x - box.x); dy += ow * (ob.y - box.y); dz += ow * (ob.z - box.z); dw += ow * (ob.w - box.w);
+          ++cnt;
+          if (os == score && best_lane < 0) best_lane = src;
+        }
+      }
+      float4 abox = box;  // argmax box: the tied member's box if there is one, else the head's own
+      if (a.box_mode == PE_BOX_ARGMAX) abox = shfl4(box, best_lane >= 0 ? best_lane : lane);
+      if (my_pos >= 0) {
+        float fs = score;
+        int fc = cls;
+        float4 fb = box;
+        if (cnt > 1) {
+          if (SCORE == PE_SCORE_PROBEN) {
+            float mx = S[0];
+            int am = 0;
+#pragma unroll
+            for (int k = 1; k <= K; ++k)
+              if (S[k] > mx) { mx = S[k]; am = k; }
+            float den = 0.f;
+#pragma unroll
+            for (int k = 0; k <= K; ++k) den += __expf(S[k] - mx);
+            fs = __fdividef(1.f, den);
+            fc = am;
+            bool nan_any = false;
+#pragma unroll
+            for (int k = 0; k <= K; ++k) nan_any |= S[k] != S[k];
+            if (nan_any || fs != fs) { fs = __int_as_float(0x7fc00000); fc = 0; }
+          } else if (SCORE == PE_SCORE_AVG) {
+            fs = ssum / (float)cnt;
+          } else {
+            fs = pm;
+          }
+          if (a.box_mode == PE_BOX_ARGMAX) fb = abox;
+          else {
+            const float inv = 1.f / wsum;
+            fb = make_float4(box.x + dx * inv, box.y + dy * inv, box.z + dz * inv, box.w + dw * inv);
+          }
+        }
+        a.out_boxes[base + my_pos] = fb;
+        a.out_scores[base + my_pos] = fs;
+        a.out_classes[base + my_pos] = fc;
+      }
     }
   }
 }
@@ -505,10 +580,14 @@ int launch_fuse(const FuseArgs& a, cudaStream_t st) {
   const int warps_per_block = kBlockThreads / 32;
   const int sms = sm_count();
   // persistent-style grid: a multiple of the SM count, at most 8 resident blocks per SM worth of warps
-  long long want = ceil_div<long long>(a.B, warps_per_block);
+  long long want = ceil_div<long long>(ceil_div<long long>(a.B, kWin), warps_per_block);
   long long cap = (long long)sms * 8;
   int grid = (int)(want < cap ? (want > 0 ? want : 1) : cap);
-  fuse_warp_kernel<K><<<grid, kBlockThreads, 0, st>>>(a);
+  const bool nms = a.score_mode == PE_SCORE_MAX && a.box_mode == PE_BOX_ARGMAX;
+  if (nms) fuse_packed_kernel<K, PE_SCORE_MAX, true><<<grid, kBlockThreads, 0, st>>>(a);
+  else if (a.score_mode == PE_SCORE_PROBEN) fuse_packed_kernel<K, PE_SCORE_PROBEN, false><<<grid, kBlockThreads, 0, st>>>(a);
+  else if (a.score_mode == PE_SCORE_AVG) fuse_packed_kernel<K, PE_SCORE_AVG, false><<<grid, kBlockThreads, 0, st>>>(a);
+  else fuse_packed_kernel<K, PE_SCORE_MAX, false><<<grid, kBlockThreads, 0, st>>>(a);
   PE_LAUNCH_CHECK();
   static bool attr_set[8] = {false};
   if (!attr_set[K]) {
