@@ -148,6 +148,11 @@ PE_API int pe_detector_buffer_info(const pe_detector* d, const char* name, size_
 PE_API int pe_detector_forward(pe_detector* d, const void* weights, const float* images, int B, int img_h, int img_w,
                                float out_h, float out_w, const pe_detections* out, void* workspace, size_t workspace_bytes,
                                void* stream);
+/* Same, from raw uint8 HWC frames [B, src_h, src_w, in_channels]: DefaultPredictor's resize to (img_h, img_w)
+ * (pe_resize_frames arithmetic) is fused into the stem's input staging, so no float32 image is materialised. */
+PE_API int pe_detector_forward_frames(pe_detector* d, const void* weights, const uint8_t* frames, int B, int src_h, int src_w,
+                                      int img_h, int img_w, int round_u8, float out_h, float out_w, const pe_detections* out,
+                                      void* workspace, size_t workspace_bytes, void* stream);
 /* Instrumentation for bench.py: CUDA events around every tensor-core GEMM launch of the next forwards. */
 PE_API int pe_detector_set_profiling(pe_detector* d, int enabled);
 PE_API int pe_detector_last_profile(pe_detector* d, float* gemm_ms, float* span_ms, int* launches, int* gemm_launches);

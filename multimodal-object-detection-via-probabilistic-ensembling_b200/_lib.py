@@ -62,6 +62,8 @@ SIGNATURES.update({
     "pe_detector_buffer_info": (c_int, [c_void_p, c_char_p, ctypes.POINTER(c_size_t), ctypes.POINTER(c_int * 4), ctypes.POINTER(c_int)]),
     "pe_detector_forward": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_float, c_float,
                                     ctypes.POINTER(Detections), c_void_p, c_size_t, c_void_p]),
+    "pe_detector_forward_frames": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_float, c_float,
+                                           ctypes.POINTER(Detections), c_void_p, c_size_t, c_void_p]),
     "pe_pack_detections": (c_int, [ctypes.POINTER(Detections), c_int, c_int, c_int] + [c_void_p] * 7),
     "pe_detector_set_profiling": (c_int, [c_void_p, c_int]),
     "pe_detector_last_profile": (c_int, [c_void_p, ctypes.POINTER(c_float), ctypes.POINTER(c_float), ctypes.POINTER(c_int), ctypes.POINTER(c_int)]),

@@ -37,6 +37,7 @@ struct ConvArgs {
   int TH, TW, tiles_h, tiles_w, tiles_n;
   int k_chunks;  // ceil(Cin / 64)
   int relu, residual_mode, out_fp32, in_fp16;
+  int stages, io_bufs;  // smem pipeline depth / number of 16 KB epilogue staging buffers (runtime split of the smem budget)
   int res_H, res_W;  // residual spatial size (mode 2: the coarser map)
   const float* bias;
   const __nv_bfloat16* residual;
@@ -151,16 +152,19 @@ __device__ __forceinline__ void tmem_dealloc(uint32_t taddr) {
 
 // ---------------------------------------------------------------------------------------------- configuration
 constexpr int kIoBytes = kBlockM * 128;  // one 128-row x 64-channel bf16 staging tile (128B-swizzled)
+constexpr int kCoarseBytes = 32 * 128;   // 32 coarse pixels x 64 channels: the FPN top-down residual of one sub-tile
+constexpr int kMaxIoBufs = 8;
 
 template <int BLOCK_N, bool kStaged>
 struct TileCfg {
   static constexpr int kABytes = kBlockM * kBlockK * 2;   // 16 KB
   static constexpr int kBBytes = BLOCK_N * kBlockK * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
-  static constexpr int kStages = BLOCK_N >= 256 ? 4 : (BLOCK_N >= 128 ? 6 : 8);
+  static constexpr int kMaxStages = BLOCK_N >= 256 ? 4 : (BLOCK_N >= 128 ? 6 : 8);
   static constexpr int kTmemCols = 2 * BLOCK_N < 32 ? 32 : 2 * BLOCK_N;
-  static constexpr int kIoTotal = kStaged ? 2 * kIoBytes : 0;
-  static constexpr int kSmemBytes = kStages * kStageBytes + kIoTotal + 1024 /*alignment slack*/ + 256 /*barriers*/;
+  // dynamic smem budget shared by the operand pipeline and (staged epilogue) the io buffers
+  static constexpr int kBudget = kMaxStages * kStageBytes + (kStaged ? 2 * kIoBytes : 0);
+  static constexpr int kSmemBytes = kBudget + 1024 /*alignment slack*/ + 512 /*barriers*/;
 };
 
 // ---------------------------------------------------------------------------------------------- epilogue helpers
@@ -183,14 +187,16 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
   using Cfg = TileCfg<BLOCK_N, kStaged>;
   extern __shared__ unsigned char smem_dyn[];
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~(uintptr_t)1023);
-  unsigned char* io_stage = smem + Cfg::kStages * Cfg::kStageBytes;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(io_stage + Cfg::kIoTotal);
+  const int n_stages = a.stages;
+  unsigned char* io_stage = smem + n_stages * Cfg::kStageBytes;
+  unsigned char* coarse_stage = io_stage + (kStaged ? a.io_bufs * kIoBytes : 0);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::kBudget);
   uint64_t* full_bar = bars;
-  uint64_t* empty_bar = bars + Cfg::kStages;
-  uint64_t* tmem_full = bars + 2 * Cfg::kStages;
+  uint64_t* empty_bar = bars + 8;
+  uint64_t* tmem_full = bars + 16;
   uint64_t* tmem_empty = tmem_full + 2;
   uint64_t* res_bar = tmem_empty + 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(res_bar + 2);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(res_bar + kMaxIoBufs);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int tiles_m = a.N * a.tiles_h * a.tiles_w;
@@ -202,19 +208,19 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
     tma_prefetch_desc(&map_b);
     if (kStaged) {
       tma_prefetch_desc(&map_out);
-      if (a.residual_mode == 1) tma_prefetch_desc(&map_res);
+      if (a.residual_mode) tma_prefetch_desc(&map_res);
     }
   }
   if (warp == 1 && lane == 0) {
-    for (int s = 0; s < Cfg::kStages; ++s) {
+    for (int s = 0; s < n_stages; ++s) {
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], 1);
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&tmem_full[s], 1);
       mbar_init(&tmem_empty[s], 4);  // one arrive per epilogue warp
-      mbar_init(&res_bar[s], 1);
     }
+    for (int s = 0; s < kMaxIoBufs; ++s) mbar_init(&res_bar[s], 1);
     fence_barrier_init();
   }
   if (warp == 2) tmem_alloc<Cfg::kTmemCols>(tmem_slot);
@@ -241,7 +247,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
               mbar_expect_tx(&full_bar[stage], Cfg::kStageBytes);
               tma_load_4d(&map_a, &full_bar[stage], sa, kc * kBlockK, w0 + kw, h0 + kh, img);
               tma_load_2d(&map_b, &full_bar[stage], sb, (kh * a.KW + kw) * a.Cin + kc * kBlockK, n0);
-              if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
+              if (++stage == n_stages) { stage = 0; phase ^= 1; }
             }
       }
     }
@@ -270,7 +276,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
           }
           umma_commit(&empty_bar[stage]);  // frees the smem stage once these MMAs retire
           if (it == k_iters - 1) umma_commit(&tmem_full[acc]);
-          if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
+          if (++stage == n_stages) { stage = 0; phase ^= 1; }
         }
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       }
@@ -285,9 +291,9 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
     if constexpr (kStaged) {
       constexpr int kSub = BLOCK_N / 64;
       const bool elected = (warp == kEpilogueWarp0) && (lane == 0);
-      const bool res_tma = a.residual_mode == 1;
-      const int subs = a.Cout - 0 >= BLOCK_N ? kSub : (a.Cout + 63) / 64;  // Cout % 64 == 0 on this path
-      uint32_t g = 0;  // running sub-tile counter: buffer g & 1, residual barrier parity (g >> 1) & 1
+      const int rmode = a.residual_mode;  // 1: same-size residual tile, 2: coarser map (nearest 2x), both via TMA
+      const uint32_t R = (uint32_t)a.io_bufs;
+      const uint32_t res_bytes = rmode == 2 ? kCoarseBytes : kIoBytes;
       auto tile_coords = [&](int tile, int& n0, int& w0, int& h0, int& img) {
         const int nt = tile % a.tiles_n, mt = tile / a.tiles_n;
         n0 = nt * BLOCK_N;
@@ -296,33 +302,34 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
         img = mt / (a.tiles_w * a.tiles_h);
       };
       auto sub_count = [&](int n0) { const int left = (a.Cout - n0) / 64; return left < kSub ? left : kSub; };
-      if (elected && res_tma && (int)blockIdx.x < num_tiles) {
+      // residual prefetch cursor (elected thread only): runs R-1 sub-tiles ahead of the consumer
+      int pf_tile = blockIdx.x, pf_sub = 0;
+      uint32_t pf_g = 0;
+      auto prefetch_residual = [&]() {
+        if (pf_tile >= num_tiles) return;
         int n0, w0, h0, img;
-        tile_coords(blockIdx.x, n0, w0, h0, img);
-        mbar_expect_tx(&res_bar[0], kIoBytes);
-        tma_load_4d(&map_res, &res_bar[0], io_stage, n0, w0, h0, img);
-      }
-      (void)subs;
+        tile_coords(pf_tile, n0, w0, h0, img);
+        const uint32_t pb = pf_g % R;
+        mbar_expect_tx(&res_bar[pb], res_bytes);
+        if (rmode == 1) tma_load_4d(&map_res, &res_bar[pb], io_stage + pb * kIoBytes, n0 + pf_sub * 64, w0, h0, img);
+        else tma_load_4d(&map_res, &res_bar[pb], coarse_stage + pb * kCoarseBytes, n0 + pf_sub * 64, w0 >> 1, h0 >> 1, img);
+        ++pf_g;
+        if (++pf_sub == sub_count(n0)) { pf_sub = 0; pf_tile += gridDim.x; }
+      };
+      if (elected && rmode)
+        for (uint32_t i = 0; i + 1 < R; ++i) prefetch_residual();
+      const int crow = (ph >> 1) * (a.TW >> 1) + (pw >> 1);  // this thread's pixel in the coarse (mode 2) tile
+      uint32_t g = 0;  // running sub-tile counter: buffer g % R, residual barrier parity (g / R) & 1
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
         int n0, w0, h0, img;
         tile_coords(tile, n0, w0, h0, img);
         const int nsub = sub_count(n0);
-        const int h = h0 + ph, w = w0 + pw;
-        const bool pix_ok = h < a.Ho && w < a.Wo;
         mbar_wait(&tmem_full[acc], acc_phase);
         tc_fence_after();
         for (int s2 = 0; s2 < nsub; ++s2, ++g) {
-          const uint32_t p = g & 1u;
+          const uint32_t p = g % R;
           unsigned char* io = io_stage + p * kIoBytes;
           const int ch0 = n0 + s2 * 64;
-          // residual for the FPN top-down path comes straight from the coarser map (nearest 2x)
-          uint4 rr[8];
-          if (a.residual_mode == 2 && pix_ok) {
-            const size_t rpix = ((size_t)img * a.res_H + (h >> 1)) * a.res_W + (w >> 1);
-            const uint4* rp = reinterpret_cast<const uint4*>(a.residual + rpix * a.Cout + ch0);
-#pragma unroll
-            for (int i = 0; i < 8; ++i) rr[i] = __ldg(rp + i);
-          }
           uint32_t v[64];
           const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BLOCK_N + s2 * 64);
           tmem_ld_32x32b_x16(taddr, v);
@@ -335,9 +342,10 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
             __syncwarp();
             if (lane == 0) mbar_arrive(&tmem_empty[acc]);
           }
-          if (res_tma) mbar_wait(&res_bar[p], (g >> 1) & 1u);
-          else epi_bar_sync();  // buffer p is free (elected thread waited for its last TMA store)
+          if (rmode) mbar_wait(&res_bar[p], (g / R) & 1u);
+          if (rmode != 1) epi_bar_sync();  // buffer p is free (the elected thread waited for its last TMA store)
           uint4* myrow = reinterpret_cast<uint4*>(io + row * 128);
+          const uint4* crs = reinterpret_cast<const uint4*>(coarse_stage + p * kCoarseBytes + crow * 128);
 #pragma unroll
           for (int c = 0; c < 8; ++c) {
             float f[8];
@@ -350,12 +358,10 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
               f[4] += b1.x; f[5] += b1.y; f[6] += b1.z; f[7] += b1.w;
             }
             uint4* slot = myrow + (c ^ (row & 7));  // 128B swizzle: 16-byte chunk index XOR (row mod 8)
-            if (a.residual_mode) {
-              const uint4 r = res_tma ? *slot : rr[c];
-              if (res_tma || pix_ok) {
-                f[0] += bf16_lo(r.x); f[1] += bf16_hi(r.x); f[2] += bf16_lo(r.y); f[3] += bf16_hi(r.y);
-                f[4] += bf16_lo(r.z); f[5] += bf16_hi(r.z); f[6] += bf16_lo(r.w); f[7] += bf16_hi(r.w);
-              }
+            if (rmode) {
+              const uint4 r = rmode == 1 ? *slot : crs[c ^ (crow & 7)];
+              f[0] += bf16_lo(r.x); f[1] += bf16_hi(r.x); f[2] += bf16_lo(r.y); f[3] += bf16_hi(r.y);
+              f[4] += bf16_lo(r.z); f[5] += bf16_hi(r.z); f[6] += bf16_lo(r.w); f[7] += bf16_hi(r.w);
             }
             if (a.relu) {
 #pragma unroll
@@ -368,21 +374,8 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
           if (elected) {
             tma_store_4d(&map_out, io, ch0, w0, h0, img);
             tma_store_commit();
-            tma_store_wait_read<1>();  // the store issued one sub-tile ago has released the other buffer
-            if (res_tma) {             // prefetch the next sub-tile's residual into it
-              int nn0 = n0, nw0 = w0, nh0 = h0, nimg = img, ns = s2 + 1;
-              bool more = true;
-              if (ns == nsub) {
-                const int nt = tile + gridDim.x;
-                more = nt < num_tiles;
-                if (more) tile_coords(nt, nn0, nw0, nh0, nimg);
-                ns = 0;
-              }
-              if (more) {
-                mbar_expect_tx(&res_bar[p ^ 1u], kIoBytes);
-                tma_load_4d(&map_res, &res_bar[p ^ 1u], io_stage + (p ^ 1u) * kIoBytes, nn0 + ns * 64, nw0, nh0, nimg);
-              }
-            }
+            tma_store_wait_read<1>();      // the store issued one sub-tile ago has released its buffer ...
+            if (rmode) prefetch_residual();  // ... which receives the residual of the sub-tile R-1 ahead
           }
         }
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
@@ -493,10 +486,10 @@ bool make_map(CUtensorMap* m, const void* base, int rank, const cuuint64_t* dims
   return r == CUDA_SUCCESS;
 }
 
-void pick_patch(int Ho, int Wo, int* TH, int* TW) {
+void pick_patch(int Ho, int Wo, int max_tw, int* TH, int* TW) {
   long best = -1;
   int bh = 8, bw = 16;
-  for (int tw = 8; tw <= 128; tw <<= 1) {
+  for (int tw = 8; tw <= max_tw; tw <<= 1) {
     const int th = kBlockM / tw;
     const long cover = (long)ceil_div(Ho, th) * th * ceil_div(Wo, tw) * tw;
     // prefer least padded work, then the squarer patch
@@ -542,7 +535,7 @@ int conv2d_launch(const pe_conv_desc& d, const void* x, const void* w, const flo
   a.KH = d.KH;
   a.KW = d.KW;
   a.pad = d.KH / 2;
-  pick_patch(a.Ho, a.Wo, &a.TH, &a.TW);
+  pick_patch(a.Ho, a.Wo, d.residual_mode == 2 ? 64 : 128, &a.TH, &a.TW);  // mode 2 needs even TH, TW
   a.tiles_h = ceil_div(a.Ho, a.TH);
   a.tiles_w = ceil_div(a.Wo, a.TW);
   const int bn = d.Cout >= 256 ? 256 : (d.Cout >= 128 ? 128 : (d.Cout >= 64 ? 64 : (d.Cout > 16 ? 32 : 16)));
@@ -581,6 +574,39 @@ int conv2d_launch(const pe_conv_desc& d, const void* x, const void* w, const flo
     cuuint32_t box[4] = {64, (cuuint32_t)a.TW, (cuuint32_t)a.TH, 1};
     if (!make_map(&mo, y, 4, dims, strides, box)) return PE_ERR_CUDA;
     if (d.residual_mode == 1 && !make_map(&mr, residual, 4, dims, strides, box)) return PE_ERR_CUDA;
+    if (d.residual_mode == 2) {  // coarser FPN level: one (TH/2 x TW/2) box supplies the whole patch
+      cuuint64_t cdims[4] = {(cuuint64_t)d.Cout, (cuuint64_t)a.res_W, (cuuint64_t)a.res_H, (cuuint64_t)d.N};
+      cuuint64_t cstr[3] = {(cuuint64_t)d.Cout * 2, (cuuint64_t)a.res_W * d.Cout * 2, (cuuint64_t)a.res_H * a.res_W * d.Cout * 2};
+      cuuint32_t cbox[4] = {64, (cuuint32_t)(a.TW / 2), (cuuint32_t)(a.TH / 2), 1};
+      if (!make_map(&mr, residual, 4, cdims, cstr, cbox)) return PE_ERR_CUDA;
+    }
+  }
+  {  // split the smem budget: short K loops need few operand stages and profit from a deep residual/store queue
+    const int stage_bytes = kBlockM * kBlockK * 2 + bn * kBlockK * 2;
+    const int max_stages = bn >= 256 ? 4 : (bn >= 128 ? 6 : 8);
+    const int k_iters = d.KH * d.KW * a.k_chunks;
+    a.stages = max_stages;
+    a.io_bufs = 2;
+    if (staged) {
+      const int budget = max_stages * stage_bytes + 2 * kIoBytes;
+      int st_want;
+      if (d.residual_mode) {  // the residual queue needs the smem more than a deep operand pipeline does
+        st_want = k_iters / 2 + 1;
+        if (st_want < 2) st_want = 2;
+        if (st_want > max_stages) st_want = max_stages;
+        if (st_want == max_stages && max_stages > 3) st_want = max_stages - 1;
+      } else {
+        st_want = k_iters + 1 < max_stages ? k_iters + 1 : max_stages;
+        if (st_want < 2) st_want = 2;
+        if (st_want < max_stages) st_want = (st_want + max_stages + 1) / 2;
+      }
+      const int io_bytes = kIoBytes + (d.residual_mode == 2 ? kCoarseBytes : 0);
+      int io = (budget - st_want * stage_bytes) / io_bytes;
+      if (io > kMaxIoBufs) io = kMaxIoBufs;
+      if (io < 2) { io = 2; st_want = (budget - 2 * io_bytes) / stage_bytes; }
+      a.stages = st_want;
+      a.io_bufs = io;
+    }
   }
   if (staged) {
     switch (bn) {

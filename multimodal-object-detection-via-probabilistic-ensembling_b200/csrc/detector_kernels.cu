@@ -53,6 +53,47 @@ __global__ void stem_canvas_kernel(const float* __restrict__ img, __half* __rest
   }
 }
 
+// Stage 1': the same canvas straight from raw uint8 HWC frames: bilinear resize (resize_frames_kernel's arithmetic, i.e.
+// DefaultPredictor's ResizeShortestEdge) + normalisation fused, so the float32 network input never exists in HBM.
+__device__ __forceinline__ float resize_sample(const unsigned char* __restrict__ im, int Hs, int Ws, int C, int c, int y, int x,
+                                               float sy, float sx, int round_u8) {
+  float fy = ((float)y + 0.5f) * sy - 0.5f, fx = ((float)x + 0.5f) * sx - 0.5f;
+  int y0 = (int)floorf(fy), x0 = (int)floorf(fx);
+  float ly = fy - (float)y0, lx = fx - (float)x0;
+  int y1 = y0 + 1, x1 = x0 + 1;
+  if (y0 < 0) { y0 = 0; y1 = 0; ly = 0.f; }
+  if (x0 < 0) { x0 = 0; x1 = 0; lx = 0.f; }
+  if (y1 >= Hs) { y1 = Hs - 1; if (y0 >= Hs) y0 = Hs - 1; }
+  if (x1 >= Ws) { x1 = Ws - 1; if (x0 >= Ws) x0 = Ws - 1; }
+  const float v00 = im[((size_t)y0 * Ws + x0) * C + c], v01 = im[((size_t)y0 * Ws + x1) * C + c];
+  const float v10 = im[((size_t)y1 * Ws + x0) * C + c], v11 = im[((size_t)y1 * Ws + x1) * C + c];
+  float v = (1.f - ly) * ((1.f - lx) * v00 + lx * v01) + ly * ((1.f - lx) * v10 + lx * v11);
+  if (round_u8) v = fminf(fmaxf(rintf(v), 0.f), 255.f);
+  return v;
+}
+
+__global__ void stem_canvas_u8_kernel(const unsigned char* __restrict__ frames, __half* __restrict__ canvas, int B, int Ctot, int c0,
+                                      int C, int Hs, int Ws, int Hi, int Wi, int Hp, int Wp, int round_u8, StemNorm nrm) {
+  const long long total = (long long)B * Hp * Wp;
+  const float sy = (float)Hs / (float)Hi, sx = (float)Ws / (float)Wi;
+  for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
+    const int xp = (int)(t % Wp);
+    long long r = t / Wp;
+    const int yp = (int)(r % Hp), b = (int)(r / Hp);
+    const int y = yp - 3, x = xp - 3;
+    __align__(8) __half v[4];
+    const bool inside = y >= 0 && y < Hi && x >= 0 && x < Wi;
+    const unsigned char* im = frames + (size_t)b * Hs * Ws * Ctot;
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      float val = 0.f;
+      if (c < C && inside) val = __fdiv_rn(resize_sample(im, Hs, Ws, Ctot, c0 + c, y, x, sy, sx, round_u8) - nrm.mean[c], nrm.std[c]);
+      v[c] = __float2half_rn(val);
+    }
+    *reinterpret_cast<uint2*>(canvas + (size_t)t * 4) = *reinterpret_cast<const uint2*>(v);
+  }
+}
+
 // Stage 2: A[pixel][kh*32 + kw*4 + c] = canvas[2*ho + kh][2*wo + kw][c] for kh < 7, kw < 8 (kw = 7 and c >= C meet
 // zero weights): every (pixel, kh) is one contiguous 64-byte run of the canvas -> four 16-byte copies.
 __global__ void stem_im2col_kernel(const __half* __restrict__ canvas, __half* __restrict__ A, int B, int Ho, int Wo, int Hp, int Wp) {
@@ -735,6 +776,20 @@ int launch_stem_im2col(const float* img, void* canvas, void* A, int B, int Ctot,
   const int Ho = Hc / 2, Wo = Wc / 2, Hp = Hc + 6, Wp = Wc + 8;
   stem_canvas_kernel<<<grid_for((long long)B * Hp * Wp, 256), 256, 0, st>>>(img, reinterpret_cast<__half*>(canvas), B, Ctot, c0, C, Hi, Wi,
                                                                               Hp, Wp, nrm);
+  PE_LAUNCH_CHECK();
+  const long long total = (long long)B * Ho * Wo * 28;
+  stem_im2col_kernel<<<grid_for(total, 256), 256, 0, st>>>(reinterpret_cast<const __half*>(canvas), reinterpret_cast<__half*>(A), B, Ho, Wo,
+                                                            Hp, Wp);
+  PE_LAUNCH_CHECK();
+  return PE_OK;
+}
+
+int launch_stem_im2col_u8(const unsigned char* frames, void* canvas, void* A, int B, int Ctot, int c0, int C, int Hs, int Ws, int Hi,
+                          int Wi, int Hc, int Wc, int round_u8, const StemNorm& nrm, cudaStream_t st) {
+  if (C > 4) return PE_ERR_UNSUPPORTED;
+  const int Ho = Hc / 2, Wo = Wc / 2, Hp = Hc + 6, Wp = Wc + 8;
+  stem_canvas_u8_kernel<<<grid_for((long long)B * Hp * Wp, 256), 256, 0, st>>>(frames, reinterpret_cast<__half*>(canvas), B, Ctot, c0, C, Hs,
+                                                                                 Ws, Hi, Wi, Hp, Wp, round_u8, nrm);
   PE_LAUNCH_CHECK();
   const long long total = (long long)B * Ho * Wo * 28;
   stem_im2col_kernel<<<grid_for(total, 256), 256, 0, st>>>(reinterpret_cast<const __half*>(canvas), reinterpret_cast<__half*>(A), B, Ho, Wo,

@@ -227,13 +227,21 @@ struct Runner {
   }
   void check(int s, int launches = 1) { if (status == PE_OK) status = s; d->last_launches += launches; }
 
+  // raw uint8 frames (resized on the fly) instead of a float32 tensor when frames != nullptr
+  const unsigned char* frames = nullptr;
+  int src_h = 0, src_w = 0, round_u8 = 0;
+
   // ResNet bottom-up + FPN for one backbone pass (input channels [c0, c0 + stem_c) of the image tensor)
   void backbone(const float* images, int Ctot, int c0, int img_h, int img_w, int pass) {
     const pe_detector_config& c = d->cfg;
     StemNorm nrm;
     for (int i = 0; i < 8; ++i) { nrm.mean[i] = 0.f; nrm.std[i] = 1.f; }
     for (int i = 0; i < d->stem_c; ++i) { nrm.mean[i] = c.pixel_mean[c0 + i]; nrm.std[i] = c.pixel_std[c0 + i]; }
-    check(launch_stem_im2col(images, buf("stem_canvas"), buf("stem_cols"), B, Ctot, c0, d->stem_c, img_h, img_w, c.canvas_h, c.canvas_w, nrm, st), 2);
+    if (frames)
+      check(launch_stem_im2col_u8(frames, buf("stem_canvas"), buf("stem_cols"), B, Ctot, c0, d->stem_c, src_h, src_w, img_h, img_w, c.canvas_h,
+                                  c.canvas_w, round_u8, nrm, st), 2);
+    else
+      check(launch_stem_im2col(images, buf("stem_canvas"), buf("stem_cols"), B, Ctot, c0, d->stem_c, img_h, img_w, c.canvas_h, c.canvas_w, nrm, st), 2);
     {  // 7x7/2 conv as a GEMM over the im2col matrix (fp16 operands keep the 0..255 pixel range exact enough)
       if (status == PE_OK) {
         const Param& p = d->params[d->find_param("backbone.bottom_up.stem.conv1")];
@@ -469,6 +477,29 @@ extern "C" PE_API int pe_detector_forward(pe_detector* d, const void* weights, c
   r.st = reinterpret_cast<cudaStream_t>(stream);
   r.B = B;
   return r.run(images, img_h, img_w, out_h, out_w, *out);
+}
+
+extern "C" PE_API int pe_detector_forward_frames(pe_detector* d, const void* weights, const uint8_t* frames, int B, int src_h, int src_w,
+                                                 int img_h, int img_w, int round_u8, float out_h, float out_w, const pe_detections* out,
+                                                 void* workspace, size_t workspace_bytes, void* stream) {
+  if (!d || !weights || !frames || !out || !workspace) return PE_ERR_INVALID_ARGUMENT;
+  if (B < 1 || B > d->cfg.max_batch || src_h < 1 || src_w < 1) return PE_ERR_INVALID_ARGUMENT;
+  if (img_h < 1 || img_w < 1 || img_h > d->cfg.canvas_h || img_w > d->cfg.canvas_w) return PE_ERR_INVALID_ARGUMENT;
+  if (workspace_bytes < d->ws_bytes) return PE_ERR_WORKSPACE_TOO_SMALL;
+  d->ev_used = 0;
+  d->last_launches = 0;
+  d->last_gemm_launches = 0;
+  pe::Runner r;
+  r.d = d;
+  r.wts = reinterpret_cast<const unsigned char*>(weights);
+  r.ws = reinterpret_cast<unsigned char*>(workspace);
+  r.st = reinterpret_cast<cudaStream_t>(stream);
+  r.B = B;
+  r.frames = frames;
+  r.src_h = src_h;
+  r.src_w = src_w;
+  r.round_u8 = round_u8;
+  return r.run(nullptr, img_h, img_w, out_h, out_w, *out);
 }
 
 extern "C" PE_API int pe_pack_detections(const pe_detections* models, int M, int B, int K, int32_t* det_offsets, float* boxes,

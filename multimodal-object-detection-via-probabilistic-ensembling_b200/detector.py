@@ -217,6 +217,21 @@ class Detector:
         _lib.check(st, "pe_detector_forward")
         return out
 
+    def forward_frames_device(self, frames_u8, net_hw, out=None, round_u8=True):
+        """frames_u8: [B, H, W, C] uint8 CUDA tensor (raw frames); resized to ``net_hw`` inside the engine
+        (DefaultPredictor semantics); detections are reported in the frame's own H x W coordinates."""
+        _lib.require_cuda(frames_u8)
+        if frames_u8.dtype != torch.uint8 or frames_u8.dim() != 4 or frames_u8.shape[3] != self.in_channels:
+            raise RuntimeError("probenb200.Detector: frames must be uint8 [B,H,W,%d]" % self.in_channels)
+        B, H, W, _ = frames_u8.shape
+        out = out or self.out
+        det = out.struct()
+        st = self.lib.pe_detector_forward_frames(self.handle, _lib.ptr(self.weights), _lib.ptr(frames_u8), B, H, W, int(net_hw[0]), int(net_hw[1]),
+                                                 int(round_u8), float(H), float(W), ctypes.byref(det), _lib.ptr(self.workspace), self.ws_bytes,
+                                                 _lib.current_stream_ptr(frames_u8.device))
+        _lib.check(st, "pe_detector_forward_frames")
+        return out
+
     def set_profiling(self, enabled):
         _lib.check(self.lib.pe_detector_set_profiling(self.handle, int(enabled)), "pe_detector_set_profiling")
 

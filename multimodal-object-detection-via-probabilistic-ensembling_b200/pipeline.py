@@ -90,23 +90,29 @@ class ProbEnPipeline:
         self.ws_bytes = int(self.lib.pe_fuse_workspace_bytes(self.B))
         self.fuse_ws = torch.empty(self.ws_bytes, dtype=torch.uint8, device=self.device)
 
-    def forward_device(self, images):
-        """images: list of M float32 CUDA tensors [B, C_m, h, w] (already resized).  Asynchronous.
+    def forward_device(self, images, net_hw=None):
+        """images: list of M CUDA tensors, either float32 [B, C_m, h, w] (already resized) or - with ``net_hw`` -
+        raw uint8 frames [B, H, W, C_m] that the engine resizes to ``net_hw`` on the fly.  Asynchronous.
         Returns the ``FusedOutput`` (boxes in the frame_size coordinate system)."""
         B = images[0].shape[0]
+        def run(det, img, buf):
+            if net_hw is not None:
+                det.forward_frames_device(img, net_hw, out=buf)
+            else:
+                det.forward_device(img, (self.frame_h, self.frame_w), out=buf)
         if B != self.B:
             raise RuntimeError("pipeline was built for batch %d" % self.B)
         main = torch.cuda.current_stream(self.device)
         stream = _lib.current_stream_ptr(self.device)
         if self.streams is None:
             for det, img, buf in zip(self.detectors, images, self.dets):
-                det.forward_device(img, (self.frame_h, self.frame_w), out=buf)
+                run(det, img, buf)
         else:
             self.ev_start.record(main)
             for m, (det, img, buf) in enumerate(zip(self.detectors, images, self.dets)):
                 with torch.cuda.stream(self.streams[m]):
                     self.streams[m].wait_event(self.ev_start)
-                    det.forward_device(img, (self.frame_h, self.frame_w), out=buf)
+                    run(det, img, buf)
                     self.ev_done[m].record(self.streams[m])
             for m in range(self.M):
                 main.wait_event(self.ev_done[m])

@@ -37,6 +37,10 @@ CASES = [
     (1, 100, 128, 256, 256, 3, 1, False, 0, False), # many tiles per CTA (persistent loop, both acc stages)
     (4, 7, 9, 512, 1024, 1, 1, True, 1, False),     # tiny maps, 4 n-tiles
     (1, 1, 300, 1024, 32, 1, 1, False, 0, True),    # predictor-like linear, N tile 32
+    (2, 200, 256, 64, 256, 1, 1, True, 1, False),   # res2.conv3-like: K=64, 5+ tiles per CTA, deep residual queue
+    (1, 100, 128, 256, 256, 1, 1, False, 2, False), # FPN lateral + top-down through the coarse TMA residual
+    (3, 50, 64, 256, 1024, 1, 1, True, 1, False),   # res4.conv3-like: 4 n-tiles, 4 k-chunks
+    (1, 56, 64, 224, 64, 1, 1, True, 0, False),     # ragged K (224 = 3.5 chunks): TMA zero fill on both operands
 ]
 
 

@@ -44,3 +44,18 @@ def test_pipeline_fusion_equals_oracle_on_gpu_detections():
         want = O.late_fusion_dispatch(("probEn", "v-avg"), infos, img_w=160, img_h=128)
         got = None if fused[b] is None else tuple(t.numpy() for t in fused[b])
         pc.assert_same_detections(got, want, 1e-4, "pipeline img %d" % b)
+
+
+def test_fused_frame_resize_equals_two_step_path():
+    """pe_detector_forward_frames (uint8 frames, resize fused into the stem staging) must reproduce
+    pe_resize_frames + pe_detector_forward bit for bit."""
+    B, K = 2, 3
+    det = detector.Detector(weights.random_state_dict(50, 3, K, seed=31), depth=50, num_classes=K, max_batch=B, canvas=(224, 256))
+    g = torch.Generator().manual_seed(2)
+    u8 = torch.randint(0, 256, (B, 128, 160, 3), dtype=torch.uint8, generator=g).cuda()
+    x = ops.resize_frames(u8, (200, 250), round_u8=True)
+    a = det.forward_device(x, (128, 160), out=detector.DetectionBuffers(B, K, det.device))
+    b = det.forward_frames_device(u8, (200, 250), out=detector.DetectionBuffers(B, K, det.device))
+    torch.cuda.synchronize()
+    assert torch.equal(a.counts, b.counts) and int(a.counts.sum()) > 0
+    assert torch.equal(a.boxes, b.boxes) and torch.equal(a.scores, b.scores) and torch.equal(a.classes, b.classes)
