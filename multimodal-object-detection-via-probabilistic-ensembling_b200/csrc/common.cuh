@@ -37,4 +37,6 @@ __host__ __device__ constexpr T ceil_div(T a, T b) { return (a + b - 1) / b; }
 int conv2d_launch(const pe_conv_desc& d, const void* x, const void* w, const float* bias, const void* residual, void* y,
                   cudaStream_t st);
 
+int conv_stem_launch(const void* canvas, const void* w, const float* bias, void* y, int B, int Hc, int Wc, cudaStream_t st);
+
 }  // namespace pe

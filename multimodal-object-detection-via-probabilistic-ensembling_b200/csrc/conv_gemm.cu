@@ -37,6 +37,7 @@ struct ConvArgs {
   int TH, TW, tiles_h, tiles_w, tiles_n;
   int k_chunks;  // ceil(Cin / 64)
   int relu, residual_mode, out_fp32, in_fp16;
+  int stem_mode;        // 7x7/2 stem straight from the padded HWC4 canvas: 64-byte K chunks (8 px x 4 ch), 5-D TMA
   int stages, io_bufs;  // smem pipeline depth / number of 16 KB epilogue staging buffers (runtime split of the smem budget)
   int res_H, res_W;  // residual spatial size (mode 2: the coarser map)
   const float* bias;
@@ -84,6 +85,12 @@ __device__ __forceinline__ void tma_load_4d(const CUtensorMap* map, uint64_t* ba
       ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
       : "memory");
 }
+__device__ __forceinline__ void tma_load_5d(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, int c1, int c2, int c3, int c4) {
+  asm volatile(
+      "cp.async.bulk.tensor.5d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+      : "memory");
+}
 __device__ __forceinline__ void tma_load_2d(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, int c1) {
   asm volatile(
       "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
@@ -105,13 +112,14 @@ __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
 }
 
 // K-major, 128B-swizzled smem tile: rows of 128 B, 8-row groups 1024 B apart (cute UMMA::SmemDescriptor).
-__device__ __forceinline__ uint64_t umma_smem_desc(uint32_t smem_addr) {
+// sw64: rows of 64 B, 8-row groups 512 B apart, SWIZZLE_64B (the stem's 32-element K chunks).
+__device__ __forceinline__ uint64_t umma_smem_desc(uint32_t smem_addr, bool sw64 = false) {
   uint64_t d = 0;
-  d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);  // start address, bits [0,14)
-  d |= (uint64_t)1 << 16;                       // leading byte offset (unused for swizzled K-major) = 1
-  d |= (uint64_t)(1024 >> 4) << 32;             // stride byte offset = 1024 B
-  d |= (uint64_t)1 << 46;                       // descriptor version (Blackwell)
-  d |= (uint64_t)2 << 61;                       // SWIZZLE_128B
+  d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);            // start address, bits [0,14)
+  d |= (uint64_t)1 << 16;                                 // leading byte offset (unused for swizzled K-major) = 1
+  d |= (uint64_t)((sw64 ? 512 : 1024) >> 4) << 32;        // stride byte offset between 8-row groups
+  d |= (uint64_t)1 << 46;                                 // descriptor version (Blackwell)
+  d |= (uint64_t)(sw64 ? 4 : 2) << 61;                    // SWIZZLE_64B : SWIZZLE_128B
   return d;
 }
 // kind::f16 instruction descriptor: (bf16 | fp16) x same -> fp32, both operands K-major, M x N tile.
@@ -195,13 +203,14 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
   uint64_t* empty_bar = bars + 8;
   uint64_t* tmem_full = bars + 16;
   uint64_t* tmem_empty = tmem_full + 2;
-  uint64_t* res_bar = tmem_empty + 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(res_bar + kMaxIoBufs);
+  uint64_t* io_ready = tmem_empty + 2;
+  uint64_t* io_written = io_ready + kMaxIoBufs;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(io_written + kMaxIoBufs);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int tiles_m = a.N * a.tiles_h * a.tiles_w;
   const int num_tiles = tiles_m * a.tiles_n;
-  const int k_iters = a.KH * a.KW * a.k_chunks;
+  const int k_iters = a.stem_mode ? 7 : a.KH * a.KW * a.k_chunks;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&map_a);
@@ -220,7 +229,10 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
       mbar_init(&tmem_full[s], 1);
       mbar_init(&tmem_empty[s], 4);  // one arrive per epilogue warp
     }
-    for (int s = 0; s < kMaxIoBufs; ++s) mbar_init(&res_bar[s], 1);
+    for (int s = 0; s < kMaxIoBufs; ++s) {
+      mbar_init(&io_ready[s], 1);
+      mbar_init(&io_written[s], 128);
+    }
     fence_barrier_init();
   }
   if (warp == 2) tmem_alloc<Cfg::kTmemCols>(tmem_slot);
@@ -238,6 +250,18 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
         const int nt = tile % a.tiles_n, mt = tile / a.tiles_n;
         const int tw = mt % a.tiles_w, th = (mt / a.tiles_w) % a.tiles_h, img = mt / (a.tiles_w * a.tiles_h);
         const int h0 = th * a.TH - a.pad, w0 = tw * a.TW - a.pad, n0 = nt * BLOCK_N;
+        if (a.stem_mode) {  // 7 row taps, each one 64-byte chunk per pixel: A rows (2*ho + kh) of the canvas
+          for (int kh = 0; kh < 7; ++kh) {
+            mbar_wait(&empty_bar[stage], phase ^ 1);
+            unsigned char* sa = smem + stage * Cfg::kStageBytes;
+            unsigned char* sb = sa + Cfg::kABytes;
+            mbar_expect_tx(&full_bar[stage], (kBlockM + BLOCK_N) * 64);
+            tma_load_5d(&map_a, &full_bar[stage], sa, 0, w0, kh & 1, h0 + (kh >> 1), img);
+            tma_load_2d(&map_b, &full_bar[stage], sb, kh * 32, n0);
+            if (++stage == n_stages) { stage = 0; phase ^= 1; }
+          }
+          continue;
+        }
         for (int kh = 0; kh < a.KH; ++kh)
           for (int kw = 0; kw < a.KW; ++kw)
             for (int kc = 0; kc < a.k_chunks; ++kc) {
@@ -268,11 +292,13 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
           tc_fence_after();
           const uint32_t sa = smem_u32(smem + stage * Cfg::kStageBytes);
           const uint32_t sb = sa + Cfg::kABytes;
-          const uint64_t da = umma_smem_desc(sa), db = umma_smem_desc(sb);
+          const bool sw64 = a.stem_mode != 0;
+          const uint64_t da = umma_smem_desc(sa, sw64), db = umma_smem_desc(sb, sw64);
+          const int n_mma = sw64 ? 2 : kBlockK / kUmmaK;
 #pragma unroll
           for (int k = 0; k < kBlockK / kUmmaK; ++k) {
             // advance 32 B (= 2 x 16 B) along K inside the swizzle atom
-            umma_bf16(d_tmem, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (it | k) != 0);
+            if (k < n_mma) umma_bf16(d_tmem, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (it | k) != 0);
           }
           umma_commit(&empty_bar[stage]);  // frees the smem stage once these MMAs retire
           if (it == k_iters - 1) umma_commit(&tmem_full[acc]);
@@ -281,17 +307,14 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       }
     }
-  } else if (warp >= kEpilogueWarp0) {
-    // ================================ epilogue ================================
-    const int q = warp - kEpilogueWarp0;  // TMEM lane quarter owned by this warp
-    const int row = q * 32 + lane;
-    const int ph = row / a.TW, pw = row - ph * a.TW;
-    int acc = 0;
-    uint32_t acc_phase = 0;
-    if constexpr (kStaged) {
+  } else if (kStaged && warp == 3) {
+    // ================================ io warp (staged epilogue) ================================
+    // Owns the 16 KB staging buffers: hands them to the epilogue warps (io_ready: free, or - on residual layers -
+    // filled with the TMA-loaded residual sub-tile, running up to io_bufs sub-tiles ahead) and TMA-stores them once
+    // all 128 epilogue threads have written their rows (io_written).  The epilogue warps never wait on a store.
+    if (lane == 0) {
       constexpr int kSub = BLOCK_N / 64;
-      const bool elected = (warp == kEpilogueWarp0) && (lane == 0);
-      const int rmode = a.residual_mode;  // 1: same-size residual tile, 2: coarser map (nearest 2x), both via TMA
+      const int rmode = a.residual_mode;
       const uint32_t R = (uint32_t)a.io_bufs;
       const uint32_t res_bytes = rmode == 2 ? kCoarseBytes : kIoBytes;
       auto tile_coords = [&](int tile, int& n0, int& w0, int& h0, int& img) {
@@ -302,28 +325,59 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
         img = mt / (a.tiles_w * a.tiles_h);
       };
       auto sub_count = [&](int n0) { const int left = (a.Cout - n0) / 64; return left < kSub ? left : kSub; };
-      // residual prefetch cursor (elected thread only): runs R-1 sub-tiles ahead of the consumer
-      int pf_tile = blockIdx.x, pf_sub = 0;
-      uint32_t pf_g = 0;
-      auto prefetch_residual = [&]() {
-        if (pf_tile >= num_tiles) return;
+      int rd_tile = blockIdx.x, rd_sub = 0;  // cursor of the next sub-tile to be made ready
+      uint32_t rd_g = 0;
+      auto make_ready = [&]() {
+        if (rd_tile >= num_tiles) return;
         int n0, w0, h0, img;
-        tile_coords(pf_tile, n0, w0, h0, img);
-        const uint32_t pb = pf_g % R;
-        mbar_expect_tx(&res_bar[pb], res_bytes);
-        if (rmode == 1) tma_load_4d(&map_res, &res_bar[pb], io_stage + pb * kIoBytes, n0 + pf_sub * 64, w0, h0, img);
-        else tma_load_4d(&map_res, &res_bar[pb], coarse_stage + pb * kCoarseBytes, n0 + pf_sub * 64, w0 >> 1, h0 >> 1, img);
-        ++pf_g;
-        if (++pf_sub == sub_count(n0)) { pf_sub = 0; pf_tile += gridDim.x; }
+        tile_coords(rd_tile, n0, w0, h0, img);
+        const uint32_t pb = rd_g % R;
+        if (rmode == 0) {
+          mbar_arrive(&io_ready[pb]);
+        } else {
+          mbar_expect_tx(&io_ready[pb], res_bytes);
+          if (rmode == 1) tma_load_4d(&map_res, &io_ready[pb], io_stage + pb * kIoBytes, n0 + rd_sub * 64, w0, h0, img);
+          else tma_load_4d(&map_res, &io_ready[pb], coarse_stage + pb * kCoarseBytes, n0 + rd_sub * 64, w0 >> 1, h0 >> 1, img);
+        }
+        ++rd_g;
+        if (++rd_sub == sub_count(n0)) { rd_sub = 0; rd_tile += gridDim.x; }
       };
-      if (elected && rmode)
-        for (uint32_t i = 0; i + 1 < R; ++i) prefetch_residual();
-      const int crow = (ph >> 1) * (a.TW >> 1) + (pw >> 1);  // this thread's pixel in the coarse (mode 2) tile
-      uint32_t g = 0;  // running sub-tile counter: buffer g % R, residual barrier parity (g / R) & 1
+      for (uint32_t i = 0; i < R; ++i) make_ready();
+      uint32_t g = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
         int n0, w0, h0, img;
         tile_coords(tile, n0, w0, h0, img);
         const int nsub = sub_count(n0);
+        for (int s2 = 0; s2 < nsub; ++s2, ++g) {
+          const uint32_t p = g % R;
+          mbar_wait(&io_written[p], (g / R) & 1u);
+          tma_store_4d(&map_out, io_stage + p * kIoBytes, n0 + s2 * 64, w0, h0, img);
+          tma_store_commit();
+          if (g >= 1) {
+            tma_store_wait_read<1>();  // store g-1 has drained its buffer: recycle it for sub-tile g-1+R
+            make_ready();
+          }
+        }
+      }
+      tma_store_wait_all();
+    }
+  } else if (warp >= kEpilogueWarp0) {
+    // ================================ epilogue ================================
+    const int q = warp - kEpilogueWarp0;  // TMEM lane quarter owned by this warp
+    const int row = q * 32 + lane;
+    const int ph = row / a.TW, pw = row - ph * a.TW;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    if constexpr (kStaged) {
+      constexpr int kSub = BLOCK_N / 64;
+      const int rmode = a.residual_mode;  // 1: same-size residual tile, 2: coarser map (nearest 2x); both arrive by TMA
+      const uint32_t R = (uint32_t)a.io_bufs;
+      const int crow = (ph >> 1) * (a.TW >> 1) + (pw >> 1);  // this thread's pixel in the coarse (mode 2) tile
+      uint32_t g = 0;  // running sub-tile counter: buffer g % R, barrier parity (g / R) & 1
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int n0 = (tile % a.tiles_n) * BLOCK_N;
+        const int left = (a.Cout - n0) / 64;
+        const int nsub = left < kSub ? left : kSub;
         mbar_wait(&tmem_full[acc], acc_phase);
         tc_fence_after();
         for (int s2 = 0; s2 < nsub; ++s2, ++g) {
@@ -342,8 +396,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
             __syncwarp();
             if (lane == 0) mbar_arrive(&tmem_empty[acc]);
           }
-          if (rmode) mbar_wait(&res_bar[p], (g / R) & 1u);
-          if (rmode != 1) epi_bar_sync();  // buffer p is free (the elected thread waited for its last TMA store)
+          mbar_wait(&io_ready[p], (g / R) & 1u);  // buffer free and (residual layers) its residual sub-tile landed
           uint4* myrow = reinterpret_cast<uint4*>(io + row * 128);
           const uint4* crs = reinterpret_cast<const uint4*>(coarse_stage + p * kCoarseBytes + crow * 128);
 #pragma unroll
@@ -369,18 +422,11 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
             }
             *slot = make_uint4(pack_bf16(f[0], f[1]), pack_bf16(f[2], f[3]), pack_bf16(f[4], f[5]), pack_bf16(f[6], f[7]));
           }
-          fence_proxy_async();
-          epi_bar_sync();
-          if (elected) {
-            tma_store_4d(&map_out, io, ch0, w0, h0, img);
-            tma_store_commit();
-            tma_store_wait_read<1>();      // the store issued one sub-tile ago has released its buffer ...
-            if (rmode) prefetch_residual();  // ... which receives the residual of the sub-tile R-1 ahead
-          }
+          fence_proxy_async();            // make the generic-proxy row writes visible to the TMA store
+          mbar_arrive(&io_written[p]);    // 128 arrivals release the buffer to the io warp
         }
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       }
-      if (elected) tma_store_wait_all();
     } else {
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
         const int nt = tile % a.tiles_n, mt = tile / a.tiles_n;
@@ -545,6 +591,7 @@ int conv2d_launch(const pe_conv_desc& d, const void* x, const void* w, const flo
   a.residual_mode = d.residual_mode;
   a.out_fp32 = d.out_fp32;
   a.in_fp16 = d.in_fp16;
+  a.stem_mode = 0;
   a.res_H = (a.Ho + 1) / 2;
   a.res_W = (a.Wo + 1) / 2;
   a.bias = bias;
@@ -622,6 +669,56 @@ int conv2d_launch(const pe_conv_desc& d, const void* x, const void* w, const flo
     case 32: return launch_conv<32, false>(ma, mb, mo, mr, a, st);
     default: return launch_conv<16, false>(ma, mb, mo, mr, a, st);
   }
+}
+
+// 7x7 stride-2 stem (resnet.py:369-384) straight from the zero-bordered fp16 HWC4 canvas [B, Hc+6, Wc+8, 4]
+// (detector_kernels.cu: stem_canvas*): out[b][ho][wo][co] = sum_kh sum_j canvas[b][2ho+kh][8wo + j] * w[co][kh][j],
+// j = kw*4 + c over an 8-pixel window (kw = 7 and c >= C carry zero weights).  The A operand is read through a
+// 5-D tensor map whose wo dimension has a 16-byte stride (overlapping 64-byte windows) and whose row dimension
+// is split into (parity, row/2), so no im2col matrix is ever written.
+int conv_stem_launch(const void* canvas, const void* w, const float* bias, void* y, int B, int Hc, int Wc, cudaStream_t st) {
+  if (!canvas || !w || !y || B < 1 || Hc % 32 || Wc % 32) return PE_ERR_INVALID_ARGUMENT;
+  const int Hp = Hc + 6, Wp = Wc + 8;
+  ConvArgs a;
+  a.N = B; a.Ho = Hc / 2; a.Wo = Wc / 2; a.Cin = 224; a.Cout = 64;
+  a.KH = 7; a.KW = 1; a.pad = 0;
+  pick_patch(a.Ho, a.Wo, 128, &a.TH, &a.TW);
+  a.tiles_h = ceil_div(a.Ho, a.TH);
+  a.tiles_w = ceil_div(a.Wo, a.TW);
+  a.tiles_n = 1;
+  a.k_chunks = 1;
+  a.relu = 1; a.residual_mode = 0; a.out_fp32 = 0; a.in_fp16 = 1; a.stem_mode = 1;
+  a.res_H = a.res_W = 0;
+  a.bias = bias; a.residual = nullptr; a.out = y;
+  a.stages = 8; a.io_bufs = 2;
+  EncodeTiledFn fn = get_encode_fn();
+  if (!fn) return PE_ERR_CUDA;
+  cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+  CUtensorMap ma, mb, mo;
+  {
+    const cuuint64_t pitch = (cuuint64_t)Wp * 8;
+    cuuint64_t dims[5] = {32, (cuuint64_t)a.Wo, 2, (cuuint64_t)(Hp / 2), (cuuint64_t)B};
+    cuuint64_t strides[4] = {16, pitch, 2 * pitch, (cuuint64_t)Hp * pitch};
+    cuuint32_t box[5] = {32, (cuuint32_t)a.TW, 1, (cuuint32_t)a.TH, 1};
+    if (fn(&ma, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 5, const_cast<void*>(canvas), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+           CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+      return PE_ERR_CUDA;
+  }
+  {
+    cuuint64_t dims[2] = {224, 64};
+    cuuint64_t strides[1] = {448};
+    cuuint32_t box[2] = {32, 64};
+    if (fn(&mb, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(w), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+           CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+      return PE_ERR_CUDA;
+  }
+  {
+    cuuint64_t dims[4] = {64, (cuuint64_t)a.Wo, (cuuint64_t)a.Ho, (cuuint64_t)B};
+    cuuint64_t strides[3] = {128, (cuuint64_t)a.Wo * 128, (cuuint64_t)a.Ho * a.Wo * 128};
+    cuuint32_t box[4] = {64, (cuuint32_t)a.TW, (cuuint32_t)a.TH, 1};
+    if (!make_map(&mo, y, 4, dims, strides, box)) return PE_ERR_CUDA;
+  }
+  return launch_conv<64, true>(ma, mb, mo, mo, a, st);
 }
 
 }  // namespace pe

@@ -30,6 +30,29 @@ __device__ __forceinline__ uint32_t packbf(float a, float b) {
 }
 __device__ __forceinline__ bool finite4(float4 b) { return isfinite(b.x) && isfinite(b.y) && isfinite(b.z) && isfinite(b.w); }
 
+// One bilinear sample of DefaultPredictor's resize (half-pixel centres).  Written with explicit round-to-nearest
+// intrinsics so that every kernel that resizes (stand-alone or fused into the stem staging) produces the same bits.
+__device__ __forceinline__ float resize_sample(const unsigned char* __restrict__ im, int Hs, int Ws, int C, int c, int y, int x,
+                                               float sy, float sx, int round_u8) {
+  const float fy = __fsub_rn(__fmul_rn(__fadd_rn((float)y, 0.5f), sy), 0.5f);
+  const float fx = __fsub_rn(__fmul_rn(__fadd_rn((float)x, 0.5f), sx), 0.5f);
+  int y0 = (int)floorf(fy), x0 = (int)floorf(fx);
+  float ly = __fsub_rn(fy, (float)y0), lx = __fsub_rn(fx, (float)x0);
+  int y1 = y0 + 1, x1 = x0 + 1;
+  if (y0 < 0) { y0 = 0; y1 = 0; ly = 0.f; }
+  if (x0 < 0) { x0 = 0; x1 = 0; lx = 0.f; }
+  if (y1 >= Hs) { y1 = Hs - 1; if (y0 >= Hs) y0 = Hs - 1; }
+  if (x1 >= Ws) { x1 = Ws - 1; if (x0 >= Ws) x0 = Ws - 1; }
+  const float v00 = im[((size_t)y0 * Ws + x0) * C + c], v01 = im[((size_t)y0 * Ws + x1) * C + c];
+  const float v10 = im[((size_t)y1 * Ws + x0) * C + c], v11 = im[((size_t)y1 * Ws + x1) * C + c];
+  const float hx = __fsub_rn(1.f, lx), hy = __fsub_rn(1.f, ly);
+  const float top = __fadd_rn(__fmul_rn(hx, v00), __fmul_rn(lx, v01));
+  const float bot = __fadd_rn(__fmul_rn(hx, v10), __fmul_rn(lx, v11));
+  float v = __fadd_rn(__fmul_rn(hy, top), __fmul_rn(ly, bot));
+  if (round_u8) v = fminf(fmaxf(rintf(v), 0.f), 255.f);
+  return v;
+}
+
 // ---------------------------------------------------------------------------------------------- stem im2col
 // Stage 1: normalise (rcnn.py:269-286) into a zero-bordered fp16 HWC4 canvas [B, Hc+6, Wc+8, 4]: image pixel (y, x)
 // sits at (y+3, x+3); the border supplies both the conv's 3-pixel zero padding and the /32 canvas padding.
@@ -55,23 +78,6 @@ __global__ void stem_canvas_kernel(const float* __restrict__ img, __half* __rest
 
 // Stage 1': the same canvas straight from raw uint8 HWC frames: bilinear resize (resize_frames_kernel's arithmetic, i.e.
 // DefaultPredictor's ResizeShortestEdge) + normalisation fused, so the float32 network input never exists in HBM.
-__device__ __forceinline__ float resize_sample(const unsigned char* __restrict__ im, int Hs, int Ws, int C, int c, int y, int x,
-                                               float sy, float sx, int round_u8) {
-  float fy = ((float)y + 0.5f) * sy - 0.5f, fx = ((float)x + 0.5f) * sx - 0.5f;
-  int y0 = (int)floorf(fy), x0 = (int)floorf(fx);
-  float ly = fy - (float)y0, lx = fx - (float)x0;
-  int y1 = y0 + 1, x1 = x0 + 1;
-  if (y0 < 0) { y0 = 0; y1 = 0; ly = 0.f; }
-  if (x0 < 0) { x0 = 0; x1 = 0; lx = 0.f; }
-  if (y1 >= Hs) { y1 = Hs - 1; if (y0 >= Hs) y0 = Hs - 1; }
-  if (x1 >= Ws) { x1 = Ws - 1; if (x0 >= Ws) x0 = Ws - 1; }
-  const float v00 = im[((size_t)y0 * Ws + x0) * C + c], v01 = im[((size_t)y0 * Ws + x1) * C + c];
-  const float v10 = im[((size_t)y1 * Ws + x0) * C + c], v11 = im[((size_t)y1 * Ws + x1) * C + c];
-  float v = (1.f - ly) * ((1.f - lx) * v00 + lx * v01) + ly * ((1.f - lx) * v10 + lx * v11);
-  if (round_u8) v = fminf(fmaxf(rintf(v), 0.f), 255.f);
-  return v;
-}
-
 __global__ void stem_canvas_u8_kernel(const unsigned char* __restrict__ frames, __half* __restrict__ canvas, int B, int Ctot, int c0,
                                       int C, int Hs, int Ws, int Hi, int Wi, int Hp, int Wp, int round_u8, StemNorm nrm) {
   const long long total = (long long)B * Hp * Wp;
@@ -124,20 +130,7 @@ __global__ void resize_frames_kernel(const unsigned char* __restrict__ src, floa
     const int y = (int)(r % Hd);
     r /= Hd;
     const int c = (int)(r % C), b = (int)(r / C);
-    float fy = ((float)y + 0.5f) * sy - 0.5f, fx = ((float)x + 0.5f) * sx - 0.5f;
-    int y0 = (int)floorf(fy), x0 = (int)floorf(fx);
-    float ly = fy - (float)y0, lx = fx - (float)x0;
-    int y1 = y0 + 1, x1 = x0 + 1;
-    if (y0 < 0) { y0 = 0; y1 = 0; ly = 0.f; }
-    if (x0 < 0) { x0 = 0; x1 = 0; lx = 0.f; }
-    if (y1 >= Hs) { y1 = Hs - 1; if (y0 >= Hs) y0 = Hs - 1; }
-    if (x1 >= Ws) { x1 = Ws - 1; if (x0 >= Ws) x0 = Ws - 1; }
-    const unsigned char* im = src + (size_t)b * Hs * Ws * C;
-    const float v00 = im[((size_t)y0 * Ws + x0) * C + c], v01 = im[((size_t)y0 * Ws + x1) * C + c];
-    const float v10 = im[((size_t)y1 * Ws + x0) * C + c], v11 = im[((size_t)y1 * Ws + x1) * C + c];
-    float v = (1.f - ly) * ((1.f - lx) * v00 + lx * v01) + ly * ((1.f - lx) * v10 + lx * v11);
-    if (round_u8) v = fminf(fmaxf(rintf(v), 0.f), 255.f);
-    dst[t] = v;
+    dst[t] = resize_sample(src + (size_t)b * Hs * Ws * C, Hs, Ws, C, c, y, x, sy, sx, round_u8);
   }
 }
 
@@ -777,10 +770,12 @@ int launch_stem_im2col(const float* img, void* canvas, void* A, int B, int Ctot,
   stem_canvas_kernel<<<grid_for((long long)B * Hp * Wp, 256), 256, 0, st>>>(img, reinterpret_cast<__half*>(canvas), B, Ctot, c0, C, Hi, Wi,
                                                                               Hp, Wp, nrm);
   PE_LAUNCH_CHECK();
-  const long long total = (long long)B * Ho * Wo * 28;
-  stem_im2col_kernel<<<grid_for(total, 256), 256, 0, st>>>(reinterpret_cast<const __half*>(canvas), reinterpret_cast<__half*>(A), B, Ho, Wo,
-                                                            Hp, Wp);
-  PE_LAUNCH_CHECK();
+  if (A) {  // optional explicit im2col matrix (kept for the op-level GEMM tests; the engine reads the canvas through TMA)
+    const long long total = (long long)B * Ho * Wo * 28;
+    stem_im2col_kernel<<<grid_for(total, 256), 256, 0, st>>>(reinterpret_cast<const __half*>(canvas), reinterpret_cast<__half*>(A), B, Ho,
+                                                              Wo, Hp, Wp);
+    PE_LAUNCH_CHECK();
+  }
   return PE_OK;
 }
 
@@ -791,10 +786,12 @@ int launch_stem_im2col_u8(const unsigned char* frames, void* canvas, void* A, in
   stem_canvas_u8_kernel<<<grid_for((long long)B * Hp * Wp, 256), 256, 0, st>>>(frames, reinterpret_cast<__half*>(canvas), B, Ctot, c0, C, Hs,
                                                                                  Ws, Hi, Wi, Hp, Wp, round_u8, nrm);
   PE_LAUNCH_CHECK();
-  const long long total = (long long)B * Ho * Wo * 28;
-  stem_im2col_kernel<<<grid_for(total, 256), 256, 0, st>>>(reinterpret_cast<const __half*>(canvas), reinterpret_cast<__half*>(A), B, Ho, Wo,
-                                                            Hp, Wp);
-  PE_LAUNCH_CHECK();
+  if (A) {  // optional explicit im2col matrix (kept for the op-level GEMM tests; the engine reads the canvas through TMA)
+    const long long total = (long long)B * Ho * Wo * 28;
+    stem_im2col_kernel<<<grid_for(total, 256), 256, 0, st>>>(reinterpret_cast<const __half*>(canvas), reinterpret_cast<__half*>(A), B, Ho,
+                                                              Wo, Hp, Wp);
+    PE_LAUNCH_CHECK();
+  }
   return PE_OK;
 }
 

@@ -133,7 +133,6 @@ void build_plan(pe_detector* d) {
   const int B = c.max_batch;
   const int passes = c.middle_fusion ? 2 : 1;
   d->add_buf("stem_canvas", B, c.canvas_h + 6, c.canvas_w + 8, 4, 2);
-  d->add_buf("stem_cols", B, d->H[0], d->W[0], d->stem_kp, 2);
   d->add_buf("stem_out", B, d->H[0], d->W[0], 64, 2);
   d->add_buf("pool_out", B, d->H[1], d->W[1], 64, 2);
   d->add_buf("x0", B, d->H[1], d->W[1], 256, 2);
@@ -238,18 +237,27 @@ struct Runner {
     for (int i = 0; i < 8; ++i) { nrm.mean[i] = 0.f; nrm.std[i] = 1.f; }
     for (int i = 0; i < d->stem_c; ++i) { nrm.mean[i] = c.pixel_mean[c0 + i]; nrm.std[i] = c.pixel_std[c0 + i]; }
     if (frames)
-      check(launch_stem_im2col_u8(frames, buf("stem_canvas"), buf("stem_cols"), B, Ctot, c0, d->stem_c, src_h, src_w, img_h, img_w, c.canvas_h,
-                                  c.canvas_w, round_u8, nrm, st), 2);
+      check(launch_stem_im2col_u8(frames, buf("stem_canvas"), nullptr, B, Ctot, c0, d->stem_c, src_h, src_w, img_h, img_w, c.canvas_h,
+                                  c.canvas_w, round_u8, nrm, st));
     else
-      check(launch_stem_im2col(images, buf("stem_canvas"), buf("stem_cols"), B, Ctot, c0, d->stem_c, img_h, img_w, c.canvas_h, c.canvas_w, nrm, st), 2);
-    {  // 7x7/2 conv as a GEMM over the im2col matrix (fp16 operands keep the 0..255 pixel range exact enough)
-      if (status == PE_OK) {
-        const Param& p = d->params[d->find_param("backbone.bottom_up.stem.conv1")];
-        pe_conv_desc cd;
-        cd.N = B; cd.H = d->H[0]; cd.W = d->W[0]; cd.Cin = d->stem_kp; cd.Cout = 64; cd.KH = 1; cd.KW = 1; cd.stride = 1;
-        cd.relu = 1; cd.residual_mode = 0; cd.out_fp32 = 0; cd.in_fp16 = 1;
-        status = gemm(cd, buf("stem_cols"), wts + p.w_off, reinterpret_cast<const float*>(wts + p.b_off), nullptr, buf("stem_out"));
+      check(launch_stem_im2col(images, buf("stem_canvas"), nullptr, B, Ctot, c0, d->stem_c, img_h, img_w, c.canvas_h, c.canvas_w, nrm, st));
+    if (status == PE_OK) {  // 7x7/2 conv: tcgen05 GEMM whose A operand is TMA-read straight from the canvas (fp16 operands)
+      const Param& p = d->params[d->find_param("backbone.bottom_up.stem.conv1")];
+      cudaEvent_t e0 = nullptr, e1 = nullptr;
+      if (d->profiling) {
+        while ((int)d->ev.size() < d->ev_used + 2) {
+          cudaEvent_t e;
+          if (cudaEventCreate(&e) != cudaSuccess) { status = PE_ERR_CUDA; break; }
+          d->ev.push_back(e);
+        }
+        if (status == PE_OK) { e0 = d->ev[d->ev_used++]; e1 = d->ev[d->ev_used++]; cudaEventRecord(e0, st); }
       }
+      if (status == PE_OK)
+        status = conv_stem_launch(buf("stem_canvas"), wts + p.w_off, reinterpret_cast<const float*>(wts + p.b_off), buf("stem_out"), B,
+                                  c.canvas_h, c.canvas_w, st);
+      if (e1) cudaEventRecord(e1, st);
+      d->last_launches++;
+      d->last_gemm_launches++;
     }
     check(launch_maxpool(buf("stem_out"), buf("pool_out"), B, d->H[0], d->W[0], 64, st));
     const int* blocks = c.depth == 101 ? kStageBlocks101 : kStageBlocks50;

@@ -225,7 +225,9 @@ __global__ void __launch_bounds__(kBlockThreads) fuse_packed_kernel(const FuseAr
           sg = s2; lo = seg_lo[s2]; n = seg_n[s2]; base = seg_base[s2]; live = seg_live[s2]; my_img = seg_img[s2];
         }
       const bool act = sg >= 0;
-      const unsigned segmask = act ? (n == 32 ? kFullMask : (((1u << n) - 1u) << lo)) : (1u << lane);
+      // idle lanes share ONE member mask (distinct masks inside a warp collective are processed one after another)
+      const unsigned usedmask = used == 32 ? kFullMask : ((1u << used) - 1u);
+      const unsigned segmask = act ? (n == 32 ? kFullMask : (((1u << n) - 1u) << lo)) : ~usedmask;
       const int row = act ? base + (lane - lo) : 0;
       const float4 box = act ? __ldg(a.boxes + row) : make_float4(0.f, 0.f, 0.f, 0.f);
       const float score = act ? __ldg(a.scores + row) : 0.f;

@@ -59,3 +59,21 @@ def test_fused_frame_resize_equals_two_step_path():
     torch.cuda.synchronize()
     assert torch.equal(a.counts, b.counts) and int(a.counts.sum()) > 0
     assert torch.equal(a.boxes, b.boxes) and torch.equal(a.scores, b.scores) and torch.equal(a.classes, b.classes)
+
+
+def test_forward_is_deterministic():
+    """Same inputs twice -> identical bits (guards the producer/consumer pipelines of the conv kernel against races)."""
+    B, K = 4, 3
+    det = detector.Detector(weights.random_state_dict(50, 3, K, seed=32), depth=50, num_classes=K, max_batch=B, canvas=(256, 320))
+    g = torch.Generator().manual_seed(3)
+    x = (torch.rand(B, 3, 256, 320, generator=g) * 255).cuda()
+    outs = []
+    for _ in range(3):
+        o = det.forward_device(x, (256, 320), out=detector.DetectionBuffers(B, K, det.device))
+        torch.cuda.synchronize()
+        feats = [det.buffer("pout%d_0" % l)[0].clone() for l in (2, 5)]
+        outs.append((o.boxes.clone(), o.scores.clone(), o.counts.clone(), feats))
+    for o in outs[1:]:
+        assert torch.equal(o[2], outs[0][2]) and torch.equal(o[0], outs[0][0]) and torch.equal(o[1], outs[0][1])
+        for a, b in zip(o[3], outs[0][3]):
+            assert torch.equal(a, b)
