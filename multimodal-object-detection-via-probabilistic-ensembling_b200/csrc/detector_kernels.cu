@@ -476,19 +476,35 @@ __global__ void __launch_bounds__(1024) rpn_merge_kernel(const float4* __restric
 }
 
 // ---------------------------------------------------------------------------------------------- ROIAlign
-__global__ void __launch_bounds__(256) roi_align_kernel(const RoiLevels fl, const float4* __restrict__ props, const int* __restrict__ prop_count,
+// One block per ROI, warp ph handles bin row ph (7 bins), lanes cover the channels with 128-bit loads.  The
+// per-sample geometry (ROIAlign_cuda.cu:14-61 bilinear_interpolate) is separable: the x terms of all 7 x gw sample
+// columns are tabulated once per ROI in shared memory, the y terms once per warp in registers.
+constexpr int kRoiGmax = 8;
+
+struct AxisSample { int lo, hi; float frac; int valid; };
+
+__device__ __forceinline__ AxisSample axis_sample(float start, float bin, int p, int i, int g, int size) {
+  AxisSample a;
+  const float v0 = start + p * bin + (i + 0.5f) * bin / (float)g;
+  a.valid = !(v0 < -1.f || v0 > (float)size);
+  float v = fmaxf(v0, 0.f);
+  int lo = (int)v, hi;
+  if (lo >= size - 1) { hi = lo = size - 1; v = (float)lo; } else hi = lo + 1;
+  a.lo = lo; a.hi = hi; a.frac = v - lo;
+  return a;
+}
+
+__global__ void __launch_bounds__(224) roi_align_kernel(const RoiLevels fl, const float4* __restrict__ props, const int* __restrict__ prop_count,
                                                         int B, int max_props, int C, __nv_bfloat16* __restrict__ out) {
-  const int lane = threadIdx.x & 31;
-  const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const long long total = (long long)B * max_props * 49;
-  if (warp >= total) return;
-  const int bin = (int)(warp % 49);
-  const long long roi = warp / 49;
+  __shared__ int s_lo[7 * kRoiGmax], s_hi[7 * kRoiGmax], s_ok[7 * kRoiGmax];
+  __shared__ float s_fr[7 * kRoiGmax];
+  const int lane = threadIdx.x & 31, ph = threadIdx.x >> 5;
+  const long long roi = blockIdx.x;
   const int b = (int)(roi / max_props), r = (int)(roi % max_props);
-  uint4* dst = reinterpret_cast<uint4*>(out + ((size_t)roi * 49 + bin) * C);
   const int cgroups = C >> 3;
+  uint4* dst_roi = reinterpret_cast<uint4*>(out + (size_t)roi * 49 * C);
   if (r >= prop_count[b]) {
-    for (int g = lane; g < cgroups; g += 32) dst[g] = make_uint4(0, 0, 0, 0);
+    for (int i = threadIdx.x; i < 49 * cgroups; i += blockDim.x) dst_roi[i] = make_uint4(0, 0, 0, 0);
     return;
   }
   const float4 box = __ldg(props + roi);
@@ -501,50 +517,70 @@ __global__ void __launch_bounds__(256) roi_align_kernel(const RoiLevels fl, cons
   const int H = fl.H[lvl], W = fl.W[lvl];
   const float scale = fl.scale[lvl];
   const __nv_bfloat16* feat = fl.feat[lvl] + (size_t)b * H * W * C;
-  const int ph = bin / 7, pw = bin - ph * 7;
   const float rsw = __fsub_rn(__fmul_rn(box.x, scale), 0.5f), rsh = __fsub_rn(__fmul_rn(box.y, scale), 0.5f);
   const float rew = __fsub_rn(__fmul_rn(box.z, scale), 0.5f), reh = __fsub_rn(__fmul_rn(box.w, scale), 0.5f);
   const float roi_w = __fsub_rn(rew, rsw), roi_h = __fsub_rn(reh, rsh);
   const float bin_h = __fdiv_rn(roi_h, 7.f), bin_w = __fdiv_rn(roi_w, 7.f);
   const int gh = (int)ceilf(__fdiv_rn(roi_h, 7.f)), gw = (int)ceilf(__fdiv_rn(roi_w, 7.f));
   const float count = (float)max(gh * gw, 1);
+  const bool xtab = gw <= kRoiGmax;
+  if (xtab && (int)threadIdx.x < 7 * gw) {
+    const AxisSample ax = axis_sample(rsw, bin_w, threadIdx.x / gw, threadIdx.x % gw, gw, W);
+    s_lo[threadIdx.x] = ax.lo; s_hi[threadIdx.x] = ax.hi; s_fr[threadIdx.x] = ax.frac; s_ok[threadIdx.x] = ax.valid;
+  }
+  __syncthreads();
+  // y terms of this warp's bin row: lane iy holds sample iy (gh <= 32), wider grids recompute on the fly
+  const bool ytab = gh <= 32;
+  AxisSample my_y = axis_sample(rsh, bin_h, ph, lane < gh ? lane : 0, gh > 0 ? gh : 1, H);
   for (int g = lane; g < cgroups; g += 32) {
-    float acc[8];
+    for (int pw = 0; pw < 7; ++pw) {
+      float acc[8];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) acc[j] = 0.f;
-    for (int iy = 0; iy < gh; ++iy) {
-      const float yy = rsh + ph * bin_h + (iy + 0.5f) * bin_h / (float)gh;
-      for (int ix = 0; ix < gw; ++ix) {
-        const float xx = rsw + pw * bin_w + (ix + 0.5f) * bin_w / (float)gw;
-        if (yy < -1.f || yy > (float)H || xx < -1.f || xx > (float)W) continue;
-        float y = fmaxf(yy, 0.f), x = fmaxf(xx, 0.f);
-        int yl = (int)y, xl = (int)x, yh, xh;
-        if (yl >= H - 1) { yh = yl = H - 1; y = (float)yl; } else yh = yl + 1;
-        if (xl >= W - 1) { xh = xl = W - 1; x = (float)xl; } else xh = xl + 1;
-        const float ly = y - yl, lx = x - xl, hy = 1.f - ly, hx = 1.f - lx;
-        const float w1 = hy * hx, w2 = hy * lx, w3 = ly * hx, w4 = ly * lx;
-        const uint4 v1 = __ldg(reinterpret_cast<const uint4*>(feat + ((size_t)yl * W + xl) * C) + g);
-        const uint4 v2 = __ldg(reinterpret_cast<const uint4*>(feat + ((size_t)yl * W + xh) * C) + g);
-        const uint4 v3 = __ldg(reinterpret_cast<const uint4*>(feat + ((size_t)yh * W + xl) * C) + g);
-        const uint4 v4 = __ldg(reinterpret_cast<const uint4*>(feat + ((size_t)yh * W + xh) * C) + g);
-        acc[0] += w1 * bflo(v1.x) + w2 * bflo(v2.x) + w3 * bflo(v3.x) + w4 * bflo(v4.x);
-        acc[1] += w1 * bfhi(v1.x) + w2 * bfhi(v2.x) + w3 * bfhi(v3.x) + w4 * bfhi(v4.x);
-        acc[2] += w1 * bflo(v1.y) + w2 * bflo(v2.y) + w3 * bflo(v3.y) + w4 * bflo(v4.y);
-        acc[3] += w1 * bfhi(v1.y) + w2 * bfhi(v2.y) + w3 * bfhi(v3.y) + w4 * bfhi(v4.y);
-        acc[4] += w1 * bflo(v1.z) + w2 * bflo(v2.z) + w3 * bflo(v3.z) + w4 * bflo(v4.z);
-        acc[5] += w1 * bfhi(v1.z) + w2 * bfhi(v2.z) + w3 * bfhi(v3.z) + w4 * bfhi(v4.z);
-        acc[6] += w1 * bflo(v1.w) + w2 * bflo(v2.w) + w3 * bflo(v3.w) + w4 * bflo(v4.w);
-        acc[7] += w1 * bfhi(v1.w) + w2 * bfhi(v2.w) + w3 * bfhi(v3.w) + w4 * bfhi(v4.w);
+      for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+      for (int iy = 0; iy < gh; ++iy) {
+        AxisSample ay;
+        if (ytab) {
+          ay.lo = __shfl_sync(kFullMask, my_y.lo, iy); ay.hi = __shfl_sync(kFullMask, my_y.hi, iy);
+          ay.frac = __shfl_sync(kFullMask, my_y.frac, iy); ay.valid = __shfl_sync(kFullMask, my_y.valid, iy);
+        } else {
+          ay = axis_sample(rsh, bin_h, ph, iy, gh, H);
+        }
+        if (!ay.valid) continue;
+        const float ly = ay.frac, hy = 1.f - ly;
+        const __nv_bfloat16* rowl = feat + (size_t)ay.lo * W * C;
+        const __nv_bfloat16* rowh = feat + (size_t)ay.hi * W * C;
+        for (int ix = 0; ix < gw; ++ix) {
+          int xl, xh, xok;
+          float lx;
+          if (xtab) { const int t = pw * gw + ix; xl = s_lo[t]; xh = s_hi[t]; lx = s_fr[t]; xok = s_ok[t]; }
+          else { const AxisSample ax = axis_sample(rsw, bin_w, pw, ix, gw, W); xl = ax.lo; xh = ax.hi; lx = ax.frac; xok = ax.valid; }
+          if (!xok) continue;
+          const float hx = 1.f - lx;
+          const float w1 = hy * hx, w2 = hy * lx, w3 = ly * hx, w4 = ly * lx;
+          const uint4 v1 = __ldg(reinterpret_cast<const uint4*>(rowl + (size_t)xl * C) + g);
+          const uint4 v2 = __ldg(reinterpret_cast<const uint4*>(rowl + (size_t)xh * C) + g);
+          const uint4 v3 = __ldg(reinterpret_cast<const uint4*>(rowh + (size_t)xl * C) + g);
+          const uint4 v4 = __ldg(reinterpret_cast<const uint4*>(rowh + (size_t)xh * C) + g);
+          acc[0] += w1 * bflo(v1.x) + w2 * bflo(v2.x) + w3 * bflo(v3.x) + w4 * bflo(v4.x);
+          acc[1] += w1 * bfhi(v1.x) + w2 * bfhi(v2.x) + w3 * bfhi(v3.x) + w4 * bfhi(v4.x);
+          acc[2] += w1 * bflo(v1.y) + w2 * bflo(v2.y) + w3 * bflo(v3.y) + w4 * bflo(v4.y);
+          acc[3] += w1 * bfhi(v1.y) + w2 * bfhi(v2.y) + w3 * bfhi(v3.y) + w4 * bfhi(v4.y);
+          acc[4] += w1 * bflo(v1.z) + w2 * bflo(v2.z) + w3 * bflo(v3.z) + w4 * bflo(v4.z);
+          acc[5] += w1 * bfhi(v1.z) + w2 * bfhi(v2.z) + w3 * bfhi(v3.z) + w4 * bfhi(v4.z);
+          acc[6] += w1 * bflo(v1.w) + w2 * bflo(v2.w) + w3 * bflo(v3.w) + w4 * bflo(v4.w);
+          acc[7] += w1 * bfhi(v1.w) + w2 * bfhi(v2.w) + w3 * bfhi(v3.w) + w4 * bfhi(v4.w);
+        }
       }
-    }
 #pragma unroll
-    for (int j = 0; j < 8; ++j) acc[j] /= count;
-    dst[g] = make_uint4(packbf(acc[0], acc[1]), packbf(acc[2], acc[3]), packbf(acc[4], acc[5]), packbf(acc[6], acc[7]));
+      for (int j = 0; j < 8; ++j) acc[j] /= count;
+      dst_roi[(size_t)(ph * 7 + pw) * cgroups + g] =
+          make_uint4(packbf(acc[0], acc[1]), packbf(acc[2], acc[3]), packbf(acc[4], acc[5]), packbf(acc[6], acc[7]));
+    }
   }
 }
 
 // ---------------------------------------------------------------------------------------------- head post-processing
-constexpr int kHeadThreads = 256;
+constexpr int kHeadThreads = 1024;  // up to 1000 ROIs per image: one row per thread, wide rank-by-counting
 constexpr int kMaxCand = 1024;  // score_thresh >= 0.5 admits at most one class per ROI, so <= 1000 candidates
 
 template <int K>
@@ -852,10 +888,9 @@ int launch_rpn_proposals(const RpnLevels& lv, int B, int pre_topk, int post_topk
 
 int launch_roi_align(const RoiLevels& fl, const float4* props, const int* prop_count, int B, int max_props, int C, void* out,
                      cudaStream_t st) {
-  if (C % 8) return PE_ERR_INVALID_ARGUMENT;
-  const long long warps = (long long)B * max_props * 49;
-  const long long blocks = (warps + 7) / 8;
-  roi_align_kernel<<<(unsigned)blocks, 256, 0, st>>>(fl, props, prop_count, B, max_props, C, reinterpret_cast<__nv_bfloat16*>(out));
+  if (C % 256) return PE_ERR_UNSUPPORTED;  // lanes cover the channels 8 at a time, whole warps per pass
+  roi_align_kernel<<<(unsigned)((long long)B * max_props), 224, 0, st>>>(fl, props, prop_count, B, max_props, C,
+                                                                         reinterpret_cast<__nv_bfloat16*>(out));
   PE_LAUNCH_CHECK();
   return PE_OK;
 }

@@ -245,7 +245,14 @@ __global__ void __launch_bounds__(kBlockThreads) fuse_packed_kernel(const FuseAr
       float area;
       if (kNms) {  // torchvision batched_nms coordinate trick: boxes + class * (max coordinate + 1), float32
         float mc = cluster ? fmaxf(fmaxf(box.x, box.y), fmaxf(box.z, box.w)) : -INFINITY;
-        mc = key_score(__reduce_max_sync(segmask, score_key(mc)));  // segment max through order-preserving keys
+        {  // segment max through order-preserving keys, full-warp collectives
+          const unsigned kk = score_key(mc);
+          unsigned best = 0;
+#pragma unroll
+          for (int s2 = 0; s2 < kWin; ++s2)
+            if (s2 < nseg) { const unsigned ms = __reduce_max_sync(kFullMask, sg == s2 ? kk : 0u); if (sg == s2) best = ms; }
+          mc = key_score(best);
+        }
         mbox = offset_box(box, __fmul_rn((float)cls, __fadd_rn(mc, 1.f)));
         area = nms_area(mbox);
       } else {
@@ -258,19 +265,28 @@ __global__ void __launch_bounds__(kBlockThreads) fuse_packed_kernel(const FuseAr
       unsigned my_cluster = 0;
       int my_pos = -1, nheads = 0;
       const unsigned skey = score_key(score);
+      // Full-warp collectives only (sub-warp member masks make the compiler emit a serialising loop per distinct
+      // mask): one redux per packed segment, ballots masked afterwards.
       while (true) {
         const unsigned key = removed ? 0u : skey;
-        const unsigned m = __reduce_max_sync(segmask, key);
-        if (!__any_sync(kFullMask, m != 0u)) break;
-        const unsigned cand = __ballot_sync(segmask, key == m && !removed);
-        const int hl = m ? (kNms ? __ffs(cand) - 1 : 31 - __clz(cand)) : lane;
+        unsigned m = 0;
+#pragma unroll
+        for (int s2 = 0; s2 < kWin; ++s2) {
+          if (s2 < nseg) {  // warp-uniform
+            const unsigned ms = __reduce_max_sync(kFullMask, sg == s2 ? key : 0u);
+            if (sg == s2) m = ms;
+          }
+        }
+        if (__ballot_sync(kFullMask, m != 0u) == 0u) break;
+        const unsigned cand = __ballot_sync(kFullMask, key == m && !removed) & segmask;
+        const int hl = (m && cand) ? (kNms ? __ffs(cand) - 1 : 31 - __clz(cand)) : lane;
         const float4 hb = shfl4(mbox, hl);
         const int hc = __shfl_sync(kFullMask, cls, hl);
         const float ha = __shfl_sync(kFullMask, area, hl);
         bool mt = false;
         if (!removed && lane != hl)
           mt = kNms ? match_nms(hb, ha, mbox, area, a.thr) : match_bayes(hb, hc, ha, mbox, cls, area, a.img_w, a.img_h, a.thr);
-        const unsigned mm = __ballot_sync(segmask, mt);
+        const unsigned mm = __ballot_sync(kFullMask, mt) & segmask;
         if (m != 0u) {
           if (lane == hl) { my_cluster = mm; my_pos = nheads; removed = true; }
           removed |= mt;
