@@ -584,10 +584,9 @@ int conv2d_launch(const pe_conv_desc& d, const void* x, const void* w, const flo
   pick_patch(a.Ho, a.Wo, d.residual_mode == 2 ? 64 : 128, &a.TH, &a.TW);  // mode 2 needs even TH, TW
   a.tiles_h = ceil_div(a.Ho, a.TH);
   a.tiles_w = ceil_div(a.Wo, a.TW);
-  int bn = d.Cout >= 256 ? 256 : (d.Cout >= 128 ? 128 : (d.Cout >= 64 ? 64 : (d.Cout > 16 ? 32 : 16)));
-  // small feature maps: a 128 x 256 tile with a long K loop keeps one SM busy for ~10 us while most SMs idle;
-  // narrower N tiles spread the same MMA work over more CTAs (the extra A re-reads come from L2)
-  while (bn > 64 && d.N * a.tiles_h * a.tiles_w * ceil_div(d.Cout, bn) < sm_count()) bn >>= 1;
+  // Widest N tile that fits: measured on B200, narrowing N to fill more SMs on small maps (res5, p5/p6) LOSES - those
+  // layers are bound by L2->SM operand traffic and every extra n-tile re-reads the A patch (profiles/README.md).
+  const int bn = d.Cout >= 256 ? 256 : (d.Cout >= 128 ? 128 : (d.Cout >= 64 ? 64 : (d.Cout > 16 ? 32 : 16)));
   a.tiles_n = ceil_div(d.Cout, bn);
   a.k_chunks = ceil_div(d.Cin, kBlockK);  // a ragged last chunk is zero-filled by TMA (A and W alike)
   a.relu = d.relu;

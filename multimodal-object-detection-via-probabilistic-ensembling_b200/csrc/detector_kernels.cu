@@ -393,8 +393,10 @@ __global__ void __launch_bounds__(kNmsThreads) nms_mask_kernel(const float4* __r
       const float4 bi = sb[i];
       const float ai = sa[i];
       const int j0 = w << 5;
-#pragma unroll 4
-      for (int t = 0; t < 32; ++t) {
+      const int rot = threadIdx.x & 31;  // neighbouring lanes own neighbouring words (512 B apart): rotate the column
+#pragma unroll 4                         // order so that a warp's shared-memory reads fall into distinct banks
+      for (int t0 = 0; t0 < 32; ++t0) {
+        const int t = (t0 + rot) & 31;
         const int j = j0 + t;
         if (j > i && j < n && iou_gt_fast(bi, ai, sb[j], sa[j], thr)) bits |= 1u << t;
       }
