@@ -188,7 +188,7 @@ def run_fusion(args):
         "clocks": clocks,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                      "frac": achieved / peaks["hbm_gbs"], "traffic": None, "peak_kind": peak_kind,
-                     "kernel": "fuse_warp_kernel<3>", "algorithmic_bytes_per_launch": alg},
+                     "kernel": "fuse_packed_kernel<3, probEn>", "algorithmic_bytes_per_launch": alg},
     }
     out["cpu_baseline"] = cpu_fusion_baseline(method, M, args.mean_dets, budget_s=args.cpu_seconds, procs=1)
     return out
