@@ -147,3 +147,48 @@ def test_end_to_end_detections_reasonable(small_case):
         close = (want["scores"][:, None] - inst.scores[None, :]).abs() < 0.15
         hit = ((iou > 0.7) & same & close).any(dim=1).float().mean()
         assert float(hit) >= 0.5, float(hit)
+
+
+@pytest.mark.parametrize("variant", ["early_fusion", "middle_fusion", "kaist_k1", "r101"])
+def test_detector_variants_features_close(variant):
+    """BASELINE.json configs 4-5: 4-channel early fusion, 6-channel middle fusion (shared backbone on both halves,
+    512-channel RPN / ROI heads), K = 1 (KAIST) and the R101 depth the FLIR demos use: backbone features and RPN
+    logits against the fp32 oracle (bf16 noise bound) + the engine's discrete stages against the oracle fed with the
+    ENGINE's own head outputs (exact)."""
+    mid = variant == "middle_fusion"
+    c = {"early_fusion": 4, "middle_fusion": 6}.get(variant, 3)
+    K = 1 if variant == "kaist_k1" else 3
+    depth = 101 if variant == "r101" else 50
+    mean = (103.530, 116.280, 123.675, 135.438, 135.438, 135.438)[:c]
+    sd = weights.random_state_dict(depth, 3 if mid else c, K, seed=40 + c + K, middle_fusion=mid)
+    cfg = D.DetCfg(depth=depth, in_channels=c, num_classes=K, pixel_mean=mean, pixel_std=(1.0,) * c, middle_fusion=mid)
+    g = torch.Generator().manual_seed(7)
+    imgs = [torch.rand(c, 160, 200, generator=g) * 255 for _ in range(2)]
+    res, inter = D.detector_forward(imgs, [(128, 160)] * 2, sd, cfg, return_intermediates=True)
+    det = detector.Detector(sd, depth=depth, num_classes=K, in_channels=c, middle_fusion=mid, pixel_mean=mean, pixel_std=(1.0,) * c,
+                            max_batch=2, canvas=(160, 224))
+    out = det.forward_device(torch.stack(imgs).cuda(), (128, 160))
+    torch.cuda.synchronize()
+    name = "p2" if mid else "pout2_0"
+    raw, dims, _ = det.buffer(name)
+    got = raw.view(torch.bfloat16).view(*dims).float().cpu().permute(0, 3, 1, 2)
+    assert rel_err(got, inter["features"]["p2"]) < (6e-2 if depth == 101 else 4e-2), rel_err(got, inter["features"]["p2"])
+    # exact check of the head post-processing on the engine's own head outputs
+    raw, dims, _ = det.buffer("head_out")
+    head = raw.view(torch.float32).view(dims[0], dims[3]).cpu()
+    raw, dims, _ = det.buffer("proposals")
+    props = raw.view(torch.float32).view(2, 1000, 4).cpu()
+    raw, _, _ = det.buffer("prop_count")
+    pcount = raw.view(torch.int32).cpu().tolist()
+    inst = out.to_instances([(128, 160)] * 2)
+    for n in range(2):
+        r = pcount[n]
+        h = head[n * 1000: n * 1000 + r]
+        lg, dl, vr = h[:, : K + 1], h[:, K + 1: K + 1 + 4 * K], torch.exp(h[:, K + 1 + 4 * K: K + 2 + 4 * K])
+        boxes = D.apply_deltas(dl, props[n, :r], (10.0, 10.0, 5.0, 5.0))
+        want = D.postprocess(D.fast_rcnn_inference_image(boxes, torch.softmax(lg, -1), lg, vr, (160, 200), cfg), (160, 200), 128, 160)
+        assert len(inst[n]) == len(want["scores"])
+        assert torch.equal(inst[n].pred_classes, want["pred_classes"])
+        if len(inst[n]):
+            assert float((inst[n].pred_boxes.tensor - want["pred_boxes"]).abs().max()) < 2e-3
+            assert float((inst[n].scores - want["scores"]).abs().max()) < 1e-5
