@@ -28,7 +28,6 @@ constexpr int kBlockM = 128;
 constexpr int kBlockK = 64;  // one 128-byte swizzle atom of bf16
 constexpr int kUmmaK = 16;
 constexpr int kThreads = 256;
-constexpr int kThreadsStaged = 384;  // staged epilogue: two groups of 4 epilogue warps, one per TMEM accumulator stage
 constexpr int kEpilogueWarp0 = 4;
 constexpr uint32_t kWatchdogPolls = 1u << 27;  // mbarrier polls before trapping (debug safety net)
 
@@ -190,7 +189,7 @@ __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
 // thread adds its accumulator row in place, and one elected thread TMA-stores the buffer (OOB rows/columns of
 // ragged tiles are clipped by the TMA unit).  Otherwise (fp32 / narrow outputs) rows are written directly.
 template <int BLOCK_N, bool kStaged>
-__global__ void __launch_bounds__(kStaged ? kThreadsStaged : kThreads, 1)
+__global__ void __launch_bounds__(kThreads, 1)
 conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                  const __grid_constant__ CUtensorMap map_out, const __grid_constant__ CUtensorMap map_res, const ConvArgs a) {
   using Cfg = TileCfg<BLOCK_N, kStaged>;
@@ -364,7 +363,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
     }
   } else if (warp >= kEpilogueWarp0) {
     // ================================ epilogue ================================
-    const int q = warp & 3;  // TMEM lane quarter this warp may access (warp id mod 4)
+    const int q = warp - kEpilogueWarp0;  // TMEM lane quarter owned by this warp
     const int row = q * 32 + lane;
     const int ph = row / a.TW, pw = row - ph * a.TW;
     int acc = 0;
@@ -374,18 +373,11 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
       const int rmode = a.residual_mode;  // 1: same-size residual tile, 2: coarser map (nearest 2x); both arrive by TMA
       const uint32_t R = (uint32_t)a.io_bufs;
       const int crow = (ph >> 1) * (a.TW >> 1) + (pw >> 1);  // this thread's pixel in the coarse (mode 2) tile
-      // Two epilogue groups (warps 4-7 and 8-11) alternate over this CTA's tiles: group e owns TMEM accumulator
-      // stage e, so while one group drains tile i the other already drains tile i+1 (two warps per scheduler
-      // hide each other's TMEM / shared-memory latencies).  Sub-tiles keep their global order g for the io warp.
-      const int group = (warp - kEpilogueWarp0) >> 2;
-      acc = group;
       uint32_t g = 0;  // running sub-tile counter: buffer g % R, barrier parity (g / R) & 1
-      int tile_seq = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++tile_seq) {
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
         const int n0 = (tile % a.tiles_n) * BLOCK_N;
         const int left = (a.Cout - n0) / 64;
         const int nsub = left < kSub ? left : kSub;
-        if ((tile_seq & 1) != group) { g += nsub; continue; }
         mbar_wait(&tmem_full[acc], acc_phase);
         tc_fence_after();
         for (int s2 = 0; s2 < nsub; ++s2, ++g) {
@@ -433,7 +425,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
           fence_proxy_async();            // make the generic-proxy row writes visible to the TMA store
           mbar_arrive(&io_written[p]);    // 128 arrivals release the buffer to the io warp
         }
-        acc_phase ^= 1;  // this group's accumulator stage is reused every second tile
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       }
     } else {
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
@@ -566,7 +558,7 @@ int launch_conv(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap&
   }
   const int tiles = a.N * a.tiles_h * a.tiles_w * a.tiles_n;
   const int grid = tiles < sm_count() ? tiles : sm_count();
-  conv_gemm_kernel<BLOCK_N, kStaged><<<grid, kStaged ? kThreadsStaged : kThreads, Cfg::kSmemBytes, st>>>(ma, mb, mo, mr, a);
+  conv_gemm_kernel<BLOCK_N, kStaged><<<grid, kThreads, Cfg::kSmemBytes, st>>>(ma, mb, mo, mr, a);
   PE_LAUNCH_CHECK();
   return PE_OK;
 }

@@ -496,10 +496,14 @@ __device__ __forceinline__ AxisSample axis_sample(float start, float bin, int p,
   return a;
 }
 
+// The bilinear samples of one bin overlap heavily (sample spacing <= 1 feature pixel), so the bin average is
+// evaluated in its separable form  sum_rows sum_cols Wy[row] * Wx[col] * f(row, col)  with per-pixel weights
+// Wy/Wx accumulated from the reference's per-sample terms: every touched feature pixel is loaded once per bin
+// instead of once per neighbouring sample (up to 4x fewer 128-bit loads).
 __global__ void __launch_bounds__(224) roi_align_kernel(const RoiLevels fl, const float4* __restrict__ props, const int* __restrict__ prop_count,
                                                         int B, int max_props, int C, __nv_bfloat16* __restrict__ out) {
-  __shared__ int s_lo[7 * kRoiGmax], s_hi[7 * kRoiGmax], s_ok[7 * kRoiGmax];
-  __shared__ float s_fr[7 * kRoiGmax];
+  __shared__ float s_wx[7][kRoiGmax + 2];
+  __shared__ int s_x0[7], s_nx[7];
   const int lane = threadIdx.x & 31, ph = threadIdx.x >> 5;
   const long long roi = blockIdx.x;
   const int b = (int)(roi / max_props), r = (int)(roi % max_props);
@@ -525,44 +529,85 @@ __global__ void __launch_bounds__(224) roi_align_kernel(const RoiLevels fl, cons
   const float bin_h = __fdiv_rn(roi_h, 7.f), bin_w = __fdiv_rn(roi_w, 7.f);
   const int gh = (int)ceilf(__fdiv_rn(roi_h, 7.f)), gw = (int)ceilf(__fdiv_rn(roi_w, 7.f));
   const float count = (float)max(gh * gw, 1);
-  const bool xtab = gw <= kRoiGmax;
-  if (xtab && (int)threadIdx.x < 7 * gw) {
-    const AxisSample ax = axis_sample(rsw, bin_w, threadIdx.x / gw, threadIdx.x % gw, gw, W);
-    s_lo[threadIdx.x] = ax.lo; s_hi[threadIdx.x] = ax.hi; s_fr[threadIdx.x] = ax.frac; s_ok[threadIdx.x] = ax.valid;
+  const bool separable = gw >= 1 && gh >= 1 && gw <= kRoiGmax && gh <= kRoiGmax;  // block-uniform
+
+  if (separable) {
+    // x weights of bin column pw: warp pw builds them (lane c <-> column x0 + c)
+    {
+      const int pw = ph;
+      const AxisSample first = axis_sample(rsw, bin_w, pw, 0, gw, W), last = axis_sample(rsw, bin_w, pw, gw - 1, gw, W);
+      const int x0 = first.lo, nx = last.hi - first.lo + 1;
+      float wx = 0.f;
+      for (int ix = 0; ix < gw; ++ix) {
+        const AxisSample ax = axis_sample(rsw, bin_w, pw, ix, gw, W);
+        if (!ax.valid) continue;
+        if (ax.lo == x0 + lane) wx += 1.f - ax.frac;
+        if (ax.hi == x0 + lane) wx += ax.frac;
+      }
+      if (lane < nx && lane < kRoiGmax + 2) s_wx[pw][lane] = wx;
+      if (lane == 0) { s_x0[pw] = x0; s_nx[pw] = nx < kRoiGmax + 2 ? nx : kRoiGmax + 2; }
+    }
+    // y weights of this warp's bin row (lane r <-> row y0 + r), kept in registers
+    const AxisSample yfirst = axis_sample(rsh, bin_h, ph, 0, gh, H), ylast = axis_sample(rsh, bin_h, ph, gh - 1, gh, H);
+    const int y0 = yfirst.lo;
+    int ny = ylast.hi - yfirst.lo + 1;
+    if (ny > kRoiGmax + 2) ny = kRoiGmax + 2;
+    float wy = 0.f;
+    for (int iy = 0; iy < gh; ++iy) {
+      const AxisSample ay = axis_sample(rsh, bin_h, ph, iy, gh, H);
+      if (!ay.valid) continue;
+      if (ay.lo == y0 + lane) wy += 1.f - ay.frac;
+      if (ay.hi == y0 + lane) wy += ay.frac;
+    }
+    __syncthreads();
+    for (int g = lane; g < cgroups; g += 32) {
+      for (int pw = 0; pw < 7; ++pw) {
+        const int x0 = s_x0[pw], nx = s_nx[pw];
+        float acc[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+        for (int rr = 0; rr < ny; ++rr) {
+          const float wyr = __shfl_sync(kFullMask, wy, rr);
+          if (wyr == 0.f) continue;
+          const __nv_bfloat16* rowp = feat + ((size_t)(y0 + rr) * W + x0) * C;
+          for (int cc = 0; cc < nx; ++cc) {
+            const float w = wyr * s_wx[pw][cc];
+            if (w == 0.f) continue;
+            const uint4 v = __ldg(reinterpret_cast<const uint4*>(rowp + (size_t)cc * C) + g);
+            acc[0] += w * bflo(v.x); acc[1] += w * bfhi(v.x); acc[2] += w * bflo(v.y); acc[3] += w * bfhi(v.y);
+            acc[4] += w * bflo(v.z); acc[5] += w * bfhi(v.z); acc[6] += w * bflo(v.w); acc[7] += w * bfhi(v.w);
+          }
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[j] /= count;
+        dst_roi[(size_t)(ph * 7 + pw) * cgroups + g] =
+            make_uint4(packbf(acc[0], acc[1]), packbf(acc[2], acc[3]), packbf(acc[4], acc[5]), packbf(acc[6], acc[7]));
+      }
+    }
+    return;
   }
-  __syncthreads();
-  // y terms of this warp's bin row: lane iy holds sample iy (gh <= 32), wider grids recompute on the fly
-  const bool ytab = gh <= 32;
-  AxisSample my_y = axis_sample(rsh, bin_h, ph, lane < gh ? lane : 0, gh > 0 ? gh : 1, H);
+
+  // general path (very large or degenerate ROIs): sample by sample, as the reference kernel does
   for (int g = lane; g < cgroups; g += 32) {
     for (int pw = 0; pw < 7; ++pw) {
       float acc[8];
 #pragma unroll
       for (int j = 0; j < 8; ++j) acc[j] = 0.f;
       for (int iy = 0; iy < gh; ++iy) {
-        AxisSample ay;
-        if (ytab) {
-          ay.lo = __shfl_sync(kFullMask, my_y.lo, iy); ay.hi = __shfl_sync(kFullMask, my_y.hi, iy);
-          ay.frac = __shfl_sync(kFullMask, my_y.frac, iy); ay.valid = __shfl_sync(kFullMask, my_y.valid, iy);
-        } else {
-          ay = axis_sample(rsh, bin_h, ph, iy, gh, H);
-        }
+        const AxisSample ay = axis_sample(rsh, bin_h, ph, iy, gh, H);
         if (!ay.valid) continue;
         const float ly = ay.frac, hy = 1.f - ly;
         const __nv_bfloat16* rowl = feat + (size_t)ay.lo * W * C;
         const __nv_bfloat16* rowh = feat + (size_t)ay.hi * W * C;
         for (int ix = 0; ix < gw; ++ix) {
-          int xl, xh, xok;
-          float lx;
-          if (xtab) { const int t = pw * gw + ix; xl = s_lo[t]; xh = s_hi[t]; lx = s_fr[t]; xok = s_ok[t]; }
-          else { const AxisSample ax = axis_sample(rsw, bin_w, pw, ix, gw, W); xl = ax.lo; xh = ax.hi; lx = ax.frac; xok = ax.valid; }
-          if (!xok) continue;
-          const float hx = 1.f - lx;
+          const AxisSample ax = axis_sample(rsw, bin_w, pw, ix, gw, W);
+          if (!ax.valid) continue;
+          const float lx = ax.frac, hx = 1.f - lx;
           const float w1 = hy * hx, w2 = hy * lx, w3 = ly * hx, w4 = ly * lx;
-          const uint4 v1 = __ldg(reinterpret_cast<const uint4*>(rowl + (size_t)xl * C) + g);
-          const uint4 v2 = __ldg(reinterpret_cast<const uint4*>(rowl + (size_t)xh * C) + g);
-          const uint4 v3 = __ldg(reinterpret_cast<const uint4*>(rowh + (size_t)xl * C) + g);
-          const uint4 v4 = __ldg(reinterpret_cast<const uint4*>(rowh + (size_t)xh * C) + g);
+          const uint4 v1 = __ldg(reinterpret_cast<const uint4*>(rowl + (size_t)ax.lo * C) + g);
+          const uint4 v2 = __ldg(reinterpret_cast<const uint4*>(rowl + (size_t)ax.hi * C) + g);
+          const uint4 v3 = __ldg(reinterpret_cast<const uint4*>(rowh + (size_t)ax.lo * C) + g);
+          const uint4 v4 = __ldg(reinterpret_cast<const uint4*>(rowh + (size_t)ax.hi * C) + g);
           acc[0] += w1 * bflo(v1.x) + w2 * bflo(v2.x) + w3 * bflo(v3.x) + w4 * bflo(v4.x);
           acc[1] += w1 * bfhi(v1.x) + w2 * bfhi(v2.x) + w3 * bfhi(v3.x) + w4 * bfhi(v4.x);
           acc[2] += w1 * bflo(v1.y) + w2 * bflo(v2.y) + w3 * bflo(v3.y) + w4 * bflo(v4.y);
