@@ -233,68 +233,131 @@ __device__ void find_kth_bin(const unsigned* hist, int nbins, unsigned kth, unsi
   __syncthreads();
 }
 
+constexpr int kTopkCandCap = 4096;  // elements of the threshold bin (+ everything above it) kept in shared memory
+constexpr size_t kTopkSmemBytes = 2048 * sizeof(unsigned) + (size_t)kTopkCandCap * 8 + (size_t)kTopkCap * 8;
+
 __global__ void __launch_bounds__(kTopkThreads) rpn_topk_kernel(const RpnLevels lv, int pre_topk, float img_h, float img_w,
                                                                 float4* __restrict__ cand_box, float* __restrict__ cand_score,
                                                                 unsigned char* __restrict__ cand_valid, int* __restrict__ cand_count) {
-  __shared__ unsigned hist[2048];
-  __shared__ unsigned long long sel[kTopkCap];
+  extern __shared__ __align__(16) unsigned char topk_smem[];
+  unsigned* hist = reinterpret_cast<unsigned*>(topk_smem);
+  unsigned long long* cand = reinterpret_cast<unsigned long long*>(hist + 2048);
+  unsigned long long* sel = cand + kTopkCandCap;
   __shared__ unsigned warp_tot[32];
   __shared__ unsigned res[2];
-  __shared__ unsigned sel_n, eq_run;
+  __shared__ unsigned sel_n, eq_run, cand_n;
   const int level = blockIdx.x, b = blockIdx.y, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   const int H = lv.H[level], W = lv.W[level], A = 3;
   const int n = H * W * A;
   const int k = pre_topk < n ? pre_topk : n;
   const float* base = lv.out[level] + (size_t)b * H * W * kRpnOutC;
   auto logit = [&](int e) { return __ldg(base + (size_t)(e / A) * kRpnOutC + (e % A)); };
+  auto pack = [](uint32_t key, int e) { return ((unsigned long long)key << 32) | (unsigned)(0xffffffffu - (unsigned)e); };
 
-  uint32_t prefix = 0, prefix_mask = 0;
-  unsigned kth = (unsigned)k;
-  const int shifts[3] = {21, 10, 0};
-  const int widths[3] = {11, 11, 10};
-  for (int pass = 0; pass < 3; ++pass) {
-    for (int i = tid; i < 2048; i += blockDim.x) hist[i] = 0;
-    __syncthreads();
-    const int sh = shifts[pass], nb = 1 << widths[pass];
+  // ---- pass 0 over global memory: histogram of the top 11 key bits -> bin of the k-th largest logit
+  for (int i = tid; i < 2048; i += blockDim.x) hist[i] = 0;
+  if (tid == 0) { sel_n = 0; eq_run = 0; cand_n = 0; }
+  __syncthreads();
+  for (int e = tid; e < n; e += blockDim.x) atomicAdd(&hist[sort_key(logit(e)) >> 21], 1u);
+  __syncthreads();
+  find_kth_bin(hist, 2048, (unsigned)k, res, warp_tot);
+  const unsigned bin0 = res[0], above0 = res[1];
+  const unsigned in_bin0 = hist[bin0];
+  __syncthreads();
+  uint32_t T;
+  unsigned need_eq, eq_total;
+  const bool small = above0 + in_bin0 <= (unsigned)kTopkCandCap;  // block-uniform
+  if (small) {
+    // ---- pass 1 over global memory: keep everything from the threshold bin upwards in shared memory
     for (int e = tid; e < n; e += blockDim.x) {
       const uint32_t key = sort_key(logit(e));
-      if ((key & prefix_mask) == prefix) atomicAdd(&hist[(key >> sh) & (nb - 1)], 1u);
+      if ((key >> 21) >= bin0) cand[atomicAdd(&cand_n, 1u)] = pack(key, e);
     }
     __syncthreads();
-    find_kth_bin(hist, nb, kth, res, warp_tot);
-    prefix |= res[0] << sh;
-    prefix_mask |= (uint32_t)(nb - 1) << sh;
-    kth -= res[1];
-    __syncthreads();
-  }
-  const uint32_t T = prefix;       // key of the kth largest element
-  const unsigned need_eq = kth;    // how many elements equal to T are selected (lowest index first)
-  const unsigned eq_total = hist[T & 1023u];
-  if (tid == 0) { sel_n = 0; eq_run = 0; }
-  __syncthreads();
-  if (eq_total == need_eq) {
-    for (int e = tid; e < n; e += blockDim.x) {
-      const uint32_t key = sort_key(logit(e));
-      if (key >= T) sel[atomicAdd(&sel_n, 1u)] = ((unsigned long long)key << 32) | (unsigned)(0xffffffffu - (unsigned)e);
+    const int nc = (int)cand_n;
+    uint32_t prefix = bin0 << 21, prefix_mask = 0x7ffu << 21;
+    unsigned kth = (unsigned)k - above0;
+    const int shifts[2] = {10, 0};
+    const int widths[2] = {11, 10};
+    for (int pass = 0; pass < 2; ++pass) {  // remaining radix passes run on the shared-memory list
+      for (int i = tid; i < 2048; i += blockDim.x) hist[i] = 0;
+      __syncthreads();
+      const int sh = shifts[pass], nb = 1 << widths[pass];
+      for (int i = tid; i < nc; i += blockDim.x) {
+        const uint32_t key = (uint32_t)(cand[i] >> 32);
+        if ((key & prefix_mask) == prefix) atomicAdd(&hist[(key >> sh) & (nb - 1)], 1u);
+      }
+      __syncthreads();
+      find_kth_bin(hist, nb, kth, res, warp_tot);
+      prefix |= res[0] << sh;
+      prefix_mask |= (uint32_t)(nb - 1) << sh;
+      kth -= res[1];
+      __syncthreads();
+    }
+    T = prefix;
+    need_eq = kth;
+    eq_total = hist[T & 1023u];
+    for (int i = tid; i < nc; i += blockDim.x) {
+      const unsigned long long c = cand[i];
+      const uint32_t key = (uint32_t)(c >> 32);
+      bool take = key > T;
+      if (key == T) {
+        if (eq_total == need_eq) take = true;
+        else {  // ties at the threshold: the need_eq lowest indices (= largest packed low words) win
+          unsigned ahead = 0;
+          for (int j = 0; j < nc; ++j) ahead += ((uint32_t)(cand[j] >> 32) == T) && (cand[j] > c);
+          take = ahead < need_eq;
+        }
+      }
+      if (take) sel[atomicAdd(&sel_n, 1u)] = c;
     }
   } else {
-    // ties at the threshold: take them in index order with a block-wide running count
-    for (int e0 = 0; e0 < n; e0 += blockDim.x) {
-      const int e = e0 + tid;
-      uint32_t key = 0;
-      bool gt = false, eq = false;
-      if (e < n) { key = sort_key(logit(e)); gt = key > T; eq = key == T; }
-      const unsigned bal = __ballot_sync(kFullMask, eq);
-      const unsigned before_lane = __popc(bal & ((1u << lane) - 1u));
-      if (lane == 0) warp_tot[wid] = __popc(bal);
+    // ---- many logits share the threshold bin: stay on global memory for the remaining passes
+    uint32_t prefix = bin0 << 21, prefix_mask = 0x7ffu << 21;
+    unsigned kth = (unsigned)k - above0;
+    const int shifts[2] = {10, 0};
+    const int widths[2] = {11, 10};
+    for (int pass = 0; pass < 2; ++pass) {
+      for (int i = tid; i < 2048; i += blockDim.x) hist[i] = 0;
       __syncthreads();
-      unsigned before = eq_run;
-      for (int w2 = 0; w2 < wid; ++w2) before += warp_tot[w2];
-      if (gt || (eq && before + before_lane < need_eq))
-        sel[atomicAdd(&sel_n, 1u)] = ((unsigned long long)key << 32) | (unsigned)(0xffffffffu - (unsigned)e);
+      const int sh = shifts[pass], nb = 1 << widths[pass];
+      for (int e = tid; e < n; e += blockDim.x) {
+        const uint32_t key = sort_key(logit(e));
+        if ((key & prefix_mask) == prefix) atomicAdd(&hist[(key >> sh) & (nb - 1)], 1u);
+      }
       __syncthreads();
-      if (tid == 0) { unsigned tot = 0; for (int w2 = 0; w2 < 32; ++w2) tot += warp_tot[w2]; eq_run += tot; }
+      find_kth_bin(hist, nb, kth, res, warp_tot);
+      prefix |= res[0] << sh;
+      prefix_mask |= (uint32_t)(nb - 1) << sh;
+      kth -= res[1];
       __syncthreads();
+    }
+    T = prefix;       // key of the kth largest element
+    need_eq = kth;    // how many elements equal to T are selected (lowest index first)
+    eq_total = hist[T & 1023u];
+    if (eq_total == need_eq) {
+      for (int e = tid; e < n; e += blockDim.x) {
+        const uint32_t key = sort_key(logit(e));
+        if (key >= T) sel[atomicAdd(&sel_n, 1u)] = pack(key, e);
+      }
+    } else {
+      // ties at the threshold: take them in index order with a block-wide running count
+      for (int e0 = 0; e0 < n; e0 += blockDim.x) {
+        const int e = e0 + tid;
+        uint32_t key = 0;
+        bool gt = false, eq = false;
+        if (e < n) { key = sort_key(logit(e)); gt = key > T; eq = key == T; }
+        const unsigned bal = __ballot_sync(kFullMask, eq);
+        const unsigned before_lane = __popc(bal & ((1u << lane) - 1u));
+        if (lane == 0) warp_tot[wid] = __popc(bal);
+        __syncthreads();
+        unsigned before = eq_run;
+        for (int w2 = 0; w2 < wid; ++w2) before += warp_tot[w2];
+        if (gt || (eq && before + before_lane < need_eq)) sel[atomicAdd(&sel_n, 1u)] = pack(key, e);
+        __syncthreads();
+        if (tid == 0) { unsigned tot = 0; for (int w2 = 0; w2 < 32; ++w2) tot += warp_tot[w2]; eq_run += tot; }
+        __syncthreads();
+      }
     }
   }
   __syncthreads();
@@ -916,7 +979,13 @@ int launch_concat_channels(const void* a, const void* b, void* y, long long pixe
 int launch_rpn_proposals(const RpnLevels& lv, int B, int pre_topk, int post_topk, float nms_thr, float img_h, float img_w,
                          const RpnScratch& s, int max_props, float4* props, int* prop_count, cudaStream_t st) {
   if (pre_topk > kTopkCap || pre_topk < 1) return PE_ERR_UNSUPPORTED;
-  rpn_topk_kernel<<<dim3(kRpnLevels, B), kTopkThreads, 0, st>>>(lv, pre_topk, img_h, img_w, s.cand_box, s.cand_score, s.cand_valid, s.cand_count);
+  static bool topk_attr = false;
+  if (!topk_attr) {
+    PE_CUDA_CHECK(cudaFuncSetAttribute(rpn_topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTopkSmemBytes));
+    topk_attr = true;
+  }
+  rpn_topk_kernel<<<dim3(kRpnLevels, B), kTopkThreads, kTopkSmemBytes, st>>>(lv, pre_topk, img_h, img_w, s.cand_box, s.cand_score, s.cand_valid,
+                                                                             s.cand_count);
   PE_LAUNCH_CHECK();
   const size_t smem = 1024 * 32 * sizeof(unsigned);
   static bool attr = false;
