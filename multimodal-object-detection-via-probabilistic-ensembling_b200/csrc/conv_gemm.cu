@@ -18,6 +18,7 @@
 //     NHWC stores).  Two TMEM accumulator stages overlap the epilogue of tile i with the mainloop of i+1.
 //   * persistent grid: min(#tiles, #SMs) CTAs, static round-robin tile schedule.
 #include <cuda.h>
+#include <stdlib.h>
 #include <cuda_bf16.h>
 #include "common.cuh"
 
@@ -27,6 +28,10 @@ namespace {
 constexpr int kBlockM = 128;
 constexpr int kBlockK = 64;  // one 128-byte swizzle atom of bf16
 constexpr int kUmmaK = 16;
+constexpr int kHaloTH = 16, kHaloTW = 8;                   // halo-mode patch: 16 rows of 8 pixels (one 8-row UMMA atom per patch row)
+constexpr int kHaloRows = (kHaloTH + 2) * (kHaloTW + 2);  // 180 pixels
+constexpr int kHaloBytes = 24 * 1024;                      // 180 * 128 B = 23040 B, rounded up so that every ring slot stays 1024 B aligned
+constexpr int kMaxBStages = 20;
 constexpr int kThreads = 256;
 constexpr int kEpilogueWarp0 = 4;
 constexpr uint32_t kWatchdogPolls = 1u << 27;  // mbarrier polls before trapping (debug safety net)
@@ -37,6 +42,8 @@ struct ConvArgs {
   int TH, TW, tiles_h, tiles_w, tiles_n;
   int k_chunks;  // ceil(Cin / 64)
   int relu, residual_mode, out_fp32, in_fp16;
+  int halo;             // 3x3: one (TH+2)x(TW+2) halo tile per K chunk in smem, the 9 taps are shifted UMMA descriptors
+  int a_stages, b_stages, b_resident;  // halo mode: A-halo ring / weight-tile ring depths; weights stay resident if they fit
   int stem_mode;        // 7x7/2 stem straight from the padded HWC4 canvas: 64-byte K chunks (8 px x 4 ch), 5-D TMA
   int stages, io_bufs;  // smem pipeline depth / number of 16 KB epilogue staging buffers (runtime split of the smem budget)
   int res_H, res_W;  // residual spatial size (mode 2: the coarser map)
@@ -113,6 +120,20 @@ __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
 
 // K-major, 128B-swizzled smem tile: rows of 128 B, 8-row groups 1024 B apart (cute UMMA::SmemDescriptor).
 // sw64: rows of 64 B, 8-row groups 512 B apart, SWIZZLE_64B (the stem's 32-element K chunks).
+// Halo-mode A operand: the 128 rows are 16 groups of 8 consecutive halo pixels (128 B apart); successive groups
+// start (TW+2)*128 = 1280 B apart and the window origin is only 128-byte aligned.  Measured on B200: the tensor
+// core applies the 128B swizzle to the ABSOLUTE shared-memory address bits (exactly what TMA wrote), so the
+// descriptor's base_offset field must stay 0 (setting it to the origin's row phase gives wrong results).
+__device__ __forceinline__ uint64_t umma_smem_desc_halo(uint32_t smem_addr, int use_base_offset) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)(((kHaloTW + 2) * 128) >> 4) << 32;      // stride byte offset between 8-row groups = 1280 B
+  d |= (uint64_t)1 << 46;
+  if (use_base_offset) d |= (uint64_t)((smem_addr >> 7) & 7) << 49;  // base offset
+  d |= (uint64_t)2 << 61;
+  return d;
+}
 __device__ __forceinline__ uint64_t umma_smem_desc(uint32_t smem_addr, bool sw64 = false) {
   uint64_t d = 0;
   d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);            // start address, bits [0,14)
@@ -172,7 +193,7 @@ struct TileCfg {
   static constexpr int kTmemCols = 2 * BLOCK_N < 32 ? 32 : 2 * BLOCK_N;
   // dynamic smem budget shared by the operand pipeline and (staged epilogue) the io buffers
   static constexpr int kBudget = kMaxStages * kStageBytes + (kStaged ? 2 * kIoBytes : 0);
-  static constexpr int kSmemBytes = kBudget + 1024 /*alignment slack*/ + 512 /*barriers*/;
+  static constexpr int kSmemBytes = kBudget + 1024 /*alignment slack*/ + 1024 /*barriers*/;
 };
 
 // ---------------------------------------------------------------------------------------------- epilogue helpers
@@ -196,7 +217,8 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
   extern __shared__ unsigned char smem_dyn[];
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~(uintptr_t)1023);
   const int n_stages = a.stages;
-  unsigned char* io_stage = smem + n_stages * Cfg::kStageBytes;
+  unsigned char* halo_b = smem + a.a_stages * kHaloBytes;  // halo mode: weight ring behind the A-halo ring
+  unsigned char* io_stage = a.halo ? halo_b + a.b_stages * Cfg::kBBytes : smem + n_stages * Cfg::kStageBytes;
   unsigned char* coarse_stage = io_stage + (kStaged ? a.io_bufs * kIoBytes : 0);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::kBudget);
   uint64_t* full_bar = bars;
@@ -205,7 +227,11 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
   uint64_t* tmem_empty = tmem_full + 2;
   uint64_t* io_ready = tmem_empty + 2;
   uint64_t* io_written = io_ready + kMaxIoBufs;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(io_written + kMaxIoBufs);
+  uint64_t* a_full = io_written + kMaxIoBufs;   // halo mode: A-halo ring
+  uint64_t* a_empty = a_full + 4;
+  uint64_t* b_full = a_empty + 4;               // halo mode: weight-tile ring
+  uint64_t* b_empty = b_full + kMaxBStages;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(b_empty + kMaxBStages);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int tiles_m = a.N * a.tiles_h * a.tiles_w;
@@ -233,6 +259,8 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
       mbar_init(&io_ready[s], 1);
       mbar_init(&io_written[s], 128);
     }
+    for (int s = 0; s < 4; ++s) { mbar_init(&a_full[s], 1); mbar_init(&a_empty[s], 1); }
+    for (int s = 0; s < kMaxBStages; ++s) { mbar_init(&b_full[s], 1); mbar_init(&b_empty[s], 1); }
     fence_barrier_init();
   }
   if (warp == 2) tmem_alloc<Cfg::kTmemCols>(tmem_slot);
@@ -244,12 +272,28 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
   if (warp == 0) {
     // ================================ TMA producer ================================
     if (lane == 0) {
-      int stage = 0;
-      uint32_t phase = 0;
+      int stage = 0, hstage = 0;
+      uint32_t phase = 0, hphase = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
         const int nt = tile % a.tiles_n, mt = tile / a.tiles_n;
         const int tw = mt % a.tiles_w, th = (mt / a.tiles_w) % a.tiles_h, img = mt / (a.tiles_w * a.tiles_h);
         const int h0 = th * a.TH - a.pad, w0 = tw * a.TW - a.pad, n0 = nt * BLOCK_N;
+        if (a.halo) {  // one halo tile per K chunk, then the 9 weight tiles of that chunk
+          for (int kc = 0; kc < a.k_chunks; ++kc) {
+            mbar_wait(&a_empty[hstage], hphase ^ 1);
+            mbar_expect_tx(&a_full[hstage], kHaloRows * 128);
+            tma_load_4d(&map_a, &a_full[hstage], smem + hstage * kHaloBytes, kc * kBlockK, w0, h0, img);
+            if (++hstage == a.a_stages) { hstage = 0; hphase ^= 1; }
+            if (a.b_resident && tile != (int)blockIdx.x) continue;  // weights were loaded with the first tile and stay
+            for (int tap = 0; tap < 9; ++tap) {
+              mbar_wait(&b_empty[stage], phase ^ 1);
+              mbar_expect_tx(&b_full[stage], Cfg::kBBytes);
+              tma_load_2d(&map_b, &b_full[stage], halo_b + stage * Cfg::kBBytes, tap * a.Cin + kc * kBlockK, n0);
+              if (++stage == a.b_stages) { stage = 0; phase ^= 1; }
+            }
+          }
+          continue;
+        }
         if (a.stem_mode) {  // 7 row taps, each one 64-byte chunk per pixel: A rows (2*ho + kh) of the canvas
           for (int kh = 0; kh < 7; ++kh) {
             mbar_wait(&empty_bar[stage], phase ^ 1);
@@ -279,14 +323,38 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
     // ================================ MMA issuer ================================
     if (lane == 0) {
       const uint32_t idesc = umma_instr_desc(kBlockM, BLOCK_N, a.in_fp16 != 0);
-      int stage = 0;
-      uint32_t phase = 0;
+      int stage = 0, hstage = 0;
+      uint32_t phase = 0, hphase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
         mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * BLOCK_N;
+        if (a.halo) {
+          for (int kc = 0; kc < a.k_chunks; ++kc) {
+            mbar_wait(&a_full[hstage], hphase);
+            tc_fence_after();
+            const uint32_t ha = smem_u32(smem + hstage * kHaloBytes);
+            for (int tap = 0; tap < 9; ++tap) {
+              if (!(a.b_resident && tile != (int)blockIdx.x)) mbar_wait(&b_full[stage], phase);
+              tc_fence_after();
+              const int kh = tap / 3, kw = tap - kh * 3;
+              const uint64_t da = umma_smem_desc_halo(ha + (uint32_t)((kh * (kHaloTW + 2) + kw) * 128), a.halo & 2);
+              const uint64_t db = umma_smem_desc(smem_u32(halo_b + stage * Cfg::kBBytes));
+#pragma unroll
+              for (int k = 0; k < kBlockK / kUmmaK; ++k)
+                umma_bf16(d_tmem, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (kc | tap | k) != 0);
+              if (!a.b_resident) umma_commit(&b_empty[stage]);
+              if (++stage == a.b_stages) { stage = 0; phase ^= 1; }
+            }
+            umma_commit(&a_empty[hstage]);
+            if (kc == a.k_chunks - 1) umma_commit(&tmem_full[acc]);
+            if (++hstage == a.a_stages) { hstage = 0; hphase ^= 1; }
+          }
+          if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+          continue;
+        }
         for (int it = 0; it < k_iters; ++it) {
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
@@ -572,7 +640,7 @@ int conv2d_launch(const pe_conv_desc& d, const void* x, const void* w, const flo
   if (d.stride != 1 && !(d.stride == 2 && d.KH == 1)) return PE_ERR_UNSUPPORTED;
   if (d.residual_mode < 0 || d.residual_mode > 2 || (d.residual_mode && !residual)) return PE_ERR_INVALID_ARGUMENT;
   if (!x || !w || !y) return PE_ERR_INVALID_ARGUMENT;
-  ConvArgs a;
+  ConvArgs a = {};
   a.N = d.N;
   a.Ho = d.stride == 2 ? (d.H - 1) / 2 + 1 : d.H;
   a.Wo = d.stride == 2 ? (d.W - 1) / 2 + 1 : d.W;
@@ -582,6 +650,15 @@ int conv2d_launch(const pe_conv_desc& d, const void* x, const void* w, const flo
   a.KW = d.KW;
   a.pad = d.KH / 2;
   pick_patch(a.Ho, a.Wo, d.residual_mode == 2 ? 64 : 128, &a.TH, &a.TW);  // mode 2 needs even TH, TW
+  // 3x3 convs on <= 256 channels are bound by the L2->SM fabric when every tap re-reads its A tile (9 x 16 KB per
+  // K chunk): halo mode loads one 18x10-pixel tile per chunk and feeds the 9 taps from it (PE_CONV_HALO=0 disables).
+  static const int halo_env = [] { const char* e = getenv("PE_CONV_HALO"); return e ? atoi(e) : 1; }();
+  // Measured (profiles/README.md): a win only where the whole 3x3 filter bank also stays resident in shared memory
+  // (res2: 64 -> 64 channels, 72 KB of weights; 80 -> 67 us per 8 frames); with streamed weights the fabric traffic is
+  // dominated by the weight tiles and the shorter operand queue costs more than the saved A re-reads.
+  const bool halo = halo_env && d.KH == 3 && d.stride == 1 && !d.out_fp32 && !d.residual_mode && d.Cin % 64 == 0 && d.Cout % 64 == 0 &&
+                    (halo_env > 1 || (d.Cin <= 64 && d.Cout <= 64));
+  if (halo) { a.TH = kHaloTH; a.TW = kHaloTW; }
   a.tiles_h = ceil_div(a.Ho, a.TH);
   a.tiles_w = ceil_div(a.Wo, a.TW);
   // Widest N tile that fits: measured on B200, narrowing N to fill more SMs on small maps (res5, p5/p6) LOSES - those
@@ -594,6 +671,9 @@ int conv2d_launch(const pe_conv_desc& d, const void* x, const void* w, const flo
   a.out_fp32 = d.out_fp32;
   a.in_fp16 = d.in_fp16;
   a.stem_mode = 0;
+  static const int halo_bo = [] { const char* e = getenv("PE_HALO_BASEOFF"); return e ? atoi(e) : 0; }();
+  a.halo = halo ? (halo_bo ? 3 : 1) : 0;
+  a.a_stages = a.b_stages = a.b_resident = 0;
   a.res_H = (a.Ho + 1) / 2;
   a.res_W = (a.Wo + 1) / 2;
   a.bias = bias;
@@ -605,7 +685,7 @@ int conv2d_launch(const pe_conv_desc& d, const void* x, const void* w, const flo
     const cuuint64_t s = (cuuint64_t)d.stride;
     cuuint64_t dims[4] = {(cuuint64_t)d.Cin, (cuuint64_t)a.Wo, (cuuint64_t)a.Ho, (cuuint64_t)d.N};
     cuuint64_t strides[3] = {s * d.Cin * 2, s * (cuuint64_t)d.W * d.Cin * 2, (cuuint64_t)d.H * d.W * d.Cin * 2};
-    cuuint32_t box[4] = {(cuuint32_t)kBlockK, (cuuint32_t)a.TW, (cuuint32_t)a.TH, 1};
+    cuuint32_t box[4] = {(cuuint32_t)kBlockK, (cuuint32_t)(halo ? a.TW + 2 : a.TW), (cuuint32_t)(halo ? a.TH + 2 : a.TH), 1};
     if (!make_map(&ma, x, 4, dims, strides, box)) return PE_ERR_CUDA;
   }
   {
@@ -655,6 +735,25 @@ int conv2d_launch(const pe_conv_desc& d, const void* x, const void* w, const flo
       if (io < 2) { io = 2; st_want = (budget - 2 * io_bytes) / stage_bytes; }
       a.stages = st_want;
       a.io_bufs = io;
+      if (halo) {
+        const int b_bytes = bn * kBlockK * 2;
+        const int all_b = 9 * a.k_chunks;
+        a.a_stages = 3;
+        a.io_bufs = 2;
+        int room = budget - a.a_stages * kHaloBytes - a.io_bufs * kIoBytes;
+        if (all_b <= kMaxBStages && all_b * b_bytes <= room && a.tiles_n == 1) {  // whole filter bank fits: load it once per CTA
+          a.b_resident = 1;
+          a.b_stages = all_b;
+          room -= all_b * b_bytes;
+          int more = room / kIoBytes;
+          if (more > 2) more = 2;
+          a.io_bufs += more;
+        } else {
+          a.b_stages = room / b_bytes;
+          if (a.b_stages > kMaxBStages) a.b_stages = kMaxBStages;
+          if (a.b_stages < 3) { a.a_stages = 2; a.b_stages = (budget - 2 * kHaloBytes - 2 * kIoBytes) / b_bytes; }
+        }
+      }
     }
   }
   if (staged) {
@@ -681,7 +780,7 @@ int conv2d_launch(const pe_conv_desc& d, const void* x, const void* w, const flo
 int conv_stem_launch(const void* canvas, const void* w, const float* bias, void* y, int B, int Hc, int Wc, cudaStream_t st) {
   if (!canvas || !w || !y || B < 1 || Hc % 32 || Wc % 32) return PE_ERR_INVALID_ARGUMENT;
   const int Hp = Hc + 6, Wp = Wc + 8;
-  ConvArgs a;
+  ConvArgs a = {};
   a.N = B; a.Ho = Hc / 2; a.Wo = Wc / 2; a.Cin = 224; a.Cout = 64;
   a.KH = 7; a.KW = 1; a.pad = 0;
   pick_patch(a.Ho, a.Wo, 128, &a.TH, &a.TW);
