@@ -32,6 +32,10 @@ constexpr int kHaloTH = 16, kHaloTW = 8;                   // halo-mode patch: 1
 constexpr int kHaloRows = (kHaloTH + 2) * (kHaloTW + 2);  // 180 pixels
 constexpr int kHaloBytes = 24 * 1024;                      // 180 * 128 B = 23040 B, rounded up so that every ring slot stays 1024 B aligned
 constexpr int kMaxBStages = 20;
+constexpr int kStemRowBytes = (2 * kBlockM + 6) * 8;      // canvas bytes feeding 128 neighbouring outputs of one filter row: 2096
+constexpr int kStemRowPitch = 2112;                         // smem pitch of those segments (16 B aligned)
+constexpr int kStemRowStages = 6;
+constexpr int kStemWBytes = 7 * 64 * 64;                   // resident stem filter bank: 7 rows x [64 x 32] fp16, 64B-swizzled
 constexpr int kThreads = 256;
 constexpr int kEpilogueWarp0 = 4;
 constexpr uint32_t kWatchdogPolls = 1u << 27;  // mbarrier polls before trapping (debug safety net)
@@ -44,7 +48,9 @@ struct ConvArgs {
   int relu, residual_mode, out_fp32, in_fp16;
   int halo;             // 3x3: one (TH+2)x(TW+2) halo tile per K chunk in smem, the 9 taps are shifted UMMA descriptors
   int a_stages, b_stages, b_resident;  // halo mode: A-halo ring / weight-tile ring depths; weights stay resident if they fit
-  int stem_mode;        // 7x7/2 stem straight from the padded HWC4 canvas: 64-byte K chunks (8 px x 4 ch), 5-D TMA
+  int stem_mode;        // 7x7/2 stem straight from the padded HWC4 canvas: 1 = 5-D TMA windows, 2 = row segments (see conv_stem_launch)
+  const unsigned char* canvas;  // stem_mode 2
+  int canvas_hp, canvas_wp;
   int stages, io_bufs;  // smem pipeline depth / number of 16 KB epilogue staging buffers (runtime split of the smem budget)
   int res_H, res_W;  // residual spatial size (mode 2: the coarser map)
   const float* bias;
@@ -98,6 +104,11 @@ __device__ __forceinline__ void tma_load_5d(const CUtensorMap* map, uint64_t* ba
       ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
       : "memory");
 }
+__device__ __forceinline__ void bulk_load_1d(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
 __device__ __forceinline__ void tma_load_2d(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, int c1) {
   asm volatile(
       "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
@@ -119,6 +130,18 @@ __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
 }
 
 // K-major, 128B-swizzled smem tile: rows of 128 B, 8-row groups 1024 B apart (cute UMMA::SmemDescriptor).
+// Un-swizzled K-major operand whose rows are only 16 B apart (stem row mode): a core matrix is 8 rows x 16 B =
+// 128 contiguous bytes, the next 16-byte K chunk of the same rows lies 16 B further (leading byte offset), the next
+// 8 rows 128 B further (stride byte offset).  Consecutive rows therefore OVERLAP in memory - exactly the overlap of
+// neighbouring 7x7/2 windows on one image row.
+__device__ __forceinline__ uint64_t umma_smem_desc_rows16(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
+  d |= (uint64_t)(16 >> 4) << 16;    // leading byte offset: K chunk to K chunk
+  d |= (uint64_t)(128 >> 4) << 32;   // stride byte offset: 8-row group to 8-row group
+  d |= (uint64_t)1 << 46;
+  return d;                          // layout type 0 = SWIZZLE_NONE
+}
 // sw64: rows of 64 B, 8-row groups 512 B apart, SWIZZLE_64B (the stem's 32-element K chunks).
 // Halo-mode A operand: the 128 rows are 16 groups of 8 consecutive halo pixels (128 B apart); successive groups
 // start (TW+2)*128 = 1280 B apart and the window origin is only 128-byte aligned.  Measured on B200: the tensor
@@ -218,7 +241,9 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~(uintptr_t)1023);
   const int n_stages = a.stages;
   unsigned char* halo_b = smem + a.a_stages * kHaloBytes;  // halo mode: weight ring behind the A-halo ring
-  unsigned char* io_stage = a.halo ? halo_b + a.b_stages * Cfg::kBBytes : smem + n_stages * Cfg::kStageBytes;
+  unsigned char* stem_w = smem + kStemRowStages * Cfg::kStageBytes;  // stem row mode: resident filter bank
+  unsigned char* io_stage = a.halo ? halo_b + a.b_stages * Cfg::kBBytes
+                                   : (a.stem_mode == 2 ? stem_w + kStemWBytes : smem + n_stages * Cfg::kStageBytes);
   unsigned char* coarse_stage = io_stage + (kStaged ? a.io_bufs * kIoBytes : 0);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::kBudget);
   uint64_t* full_bar = bars;
@@ -236,7 +261,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int tiles_m = a.N * a.tiles_h * a.tiles_w;
   const int num_tiles = tiles_m * a.tiles_n;
-  const int k_iters = a.stem_mode ? 7 : a.KH * a.KW * a.k_chunks;
+  const int k_iters = a.stem_mode == 1 ? 7 : a.KH * a.KW * a.k_chunks;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&map_a);
@@ -294,6 +319,21 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
           }
           continue;
         }
+        if (a.stem_mode == 2) {  // one stage per tile: the 7 canvas row segments under this run of 128 outputs
+          if (tile == (int)blockIdx.x) {
+            mbar_expect_tx(&b_full[0], kStemWBytes);
+            for (int kh = 0; kh < 7; ++kh) tma_load_2d(&map_b, &b_full[0], stem_w + kh * 4096, kh * 32, 0);
+          }
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          unsigned char* sa = smem + stage * Cfg::kStageBytes;
+          mbar_expect_tx(&full_bar[stage], 7 * kStemRowBytes);
+          const int ho = th * a.TH, wo0 = tw * a.TW;
+          for (int kh = 0; kh < 7; ++kh)
+            bulk_load_1d(sa + kh * kStemRowPitch,
+                         a.canvas + (((size_t)img * a.canvas_hp + 2 * ho + kh) * a.canvas_wp + 2 * wo0) * 8, kStemRowBytes, &full_bar[stage]);
+          if (++stage == n_stages) { stage = 0; phase ^= 1; }
+          continue;
+        }
         if (a.stem_mode) {  // 7 row taps, each one 64-byte chunk per pixel: A rows (2*ho + kh) of the canvas
           for (int kh = 0; kh < 7; ++kh) {
             mbar_wait(&empty_bar[stage], phase ^ 1);
@@ -331,6 +371,23 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
         mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * BLOCK_N;
+        if (a.stem_mode == 2) {
+          if (tile == (int)blockIdx.x) mbar_wait(&b_full[0], 0);
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + stage * Cfg::kStageBytes), sw = smem_u32(stem_w);
+          for (int kh = 0; kh < 7; ++kh) {
+#pragma unroll
+            for (int k = 0; k < 2; ++k)
+              umma_bf16(d_tmem, umma_smem_desc_rows16(sa + kh * kStemRowPitch + 32 * k), umma_smem_desc(sw + kh * 4096, true) + (uint64_t)(2 * k),
+                        idesc, (kh | k) != 0);
+          }
+          umma_commit(&empty_bar[stage]);
+          umma_commit(&tmem_full[acc]);
+          if (++stage == n_stages) { stage = 0; phase ^= 1; }
+          if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+          continue;
+        }
         if (a.halo) {
           for (int kc = 0; kc < a.k_chunks; ++kc) {
             mbar_wait(&a_full[hstage], hphase);
@@ -360,7 +417,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
           tc_fence_after();
           const uint32_t sa = smem_u32(smem + stage * Cfg::kStageBytes);
           const uint32_t sb = sa + Cfg::kABytes;
-          const bool sw64 = a.stem_mode != 0;
+          const bool sw64 = a.stem_mode == 1;
           const uint64_t da = umma_smem_desc(sa, sw64), db = umma_smem_desc(sb, sw64);
           const int n_mma = sw64 ? 2 : kBlockK / kUmmaK;
 #pragma unroll
@@ -783,15 +840,22 @@ int conv_stem_launch(const void* canvas, const void* w, const float* bias, void*
   ConvArgs a = {};
   a.N = B; a.Ho = Hc / 2; a.Wo = Wc / 2; a.Cin = 224; a.Cout = 64;
   a.KH = 7; a.KW = 1; a.pad = 0;
-  pick_patch(a.Ho, a.Wo, 128, &a.TH, &a.TW);
+  static const int stem_mode_env = [] { const char* e = getenv("PE_STEM_MODE"); return e ? atoi(e) : 2; }();
+  const int mode = stem_mode_env == 1 ? 1 : 2;
+  if (mode == 2) { a.TH = 1; a.TW = kBlockM; }  // a run of 128 outputs on one row: rows of the A operand are 16 B apart
+  else pick_patch(a.Ho, a.Wo, 128, &a.TH, &a.TW);
   a.tiles_h = ceil_div(a.Ho, a.TH);
   a.tiles_w = ceil_div(a.Wo, a.TW);
   a.tiles_n = 1;
   a.k_chunks = 1;
-  a.relu = 1; a.residual_mode = 0; a.out_fp32 = 0; a.in_fp16 = 1; a.stem_mode = 1;
+  a.relu = 1; a.residual_mode = 0; a.out_fp32 = 0; a.in_fp16 = 1; a.stem_mode = mode;
+  a.canvas = reinterpret_cast<const unsigned char*>(canvas);
+  a.canvas_hp = Hp;
+  a.canvas_wp = Wp;
   a.res_H = a.res_W = 0;
   a.bias = bias; a.residual = nullptr; a.out = y;
-  a.stages = 8; a.io_bufs = 2;
+  a.stages = mode == 2 ? kStemRowStages : 8;
+  a.io_bufs = 2;
   EncodeTiledFn fn = get_encode_fn();
   if (!fn) return PE_ERR_CUDA;
   cuuint32_t estr[5] = {1, 1, 1, 1, 1};
