@@ -77,3 +77,31 @@ def test_forward_is_deterministic():
         assert torch.equal(o[2], outs[0][2]) and torch.equal(o[0], outs[0][0]) and torch.equal(o[1], outs[0][1])
         for a, b in zip(o[3], outs[0][3]):
             assert torch.equal(a, b)
+
+
+def test_three_model_ensemble_pipeline():
+    """BASELINE.json configs[4]: thermal_only (3-ch) + early_fusion (4-ch) + middle_fusion (6-ch, shared backbone on both
+    halves, 512-channel heads) -> ProbEn over M = 3 models, one stream-parallel pass; fused output == oracle fusion of the
+    three detectors' own detections."""
+    B, K = 2, 3
+    specs = [("thermal_only", 3, False), ("early_fusion", 4, False), ("middle_fusion", 6, True)]
+    dets, frames = [], []
+    g = torch.Generator().manual_seed(5)
+    for i, (name, c, mid) in enumerate(specs):
+        cfg = detector.fusion_method_config(name)
+        sd = weights.random_state_dict(50, 3 if mid else c, K, seed=60 + i, middle_fusion=mid)
+        dets.append(detector.Detector(sd, depth=50, num_classes=K, max_batch=B, canvas=(160, 224), **cfg))
+        frames.append(torch.randint(0, 256, (B, 128, 160, c), dtype=torch.uint8, generator=g).cuda())
+    pipe = pipeline.ProbEnPipeline(dets, ("probEn", "v-avg"), frame_size=(128, 160))
+    out = pipe.forward_device(frames, net_hw=(160, 200))
+    torch.cuda.synchronize()
+    fused = pipeline.FusedOutput.split(out.flat, B, 3)
+    per_model = [d.to_instances([(128, 160)] * B) for d in pipe.dets]
+    assert all(sum(len(i) for i in pm) > 0 for pm in per_model)
+    for b in range(B):
+        infos = [{"bbox": pm[b].pred_boxes.tensor.double().tolist(), "score": pm[b].scores.double().tolist(),
+                  "class": pm[b].pred_classes.tolist(), "prob": pm[b].prob_score.double().tolist(),
+                  "vars": pm[b].vars.double().tolist()} for pm in per_model]
+        want = O.late_fusion_dispatch(("probEn", "v-avg"), infos, img_w=160, img_h=128)
+        got = None if fused[b] is None else tuple(t.numpy() for t in fused[b])
+        pc.assert_same_detections(got, want, 1e-4, "3-model ensemble img %d" % b)
