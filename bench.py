@@ -246,17 +246,44 @@ def run_pairs(args):
     method = (args.score_fusion, args.box_fusion)
     nh, nw = detector.resize_shortest_edge_shape(512, 640)
     canvas = ((nh + 31) // 32 * 32, (nw + 31) // 32 * 32)
-    dets = [detector.Detector(weights.random_state_dict(depth, 3, K, seed=11 + m), depth=depth, num_classes=K, max_batch=B,
-                              canvas=canvas, device=dev) for m in range(2)]
-    pipe = pipeline.ProbEnPipeline(dets, method, frame_size=(512, 640))
+    S = max(1, args.substreams)
+    if B % S:
+        raise SystemExit("--batch must be a multiple of --substreams")
+    Bs = B // S
+    dets0 = [detector.Detector(weights.random_state_dict(depth, 3, K, seed=11 + m), depth=depth, num_classes=K, max_batch=Bs,
+                               canvas=canvas, device=dev) for m in range(2)]
+    # S sub-batch pipelines (own streams / scratch, shared weights) publish into one flat result tensor
+    words = pipeline.FusedOutput.words_for(Bs, 2)
+    words_al = (words + 3) // 4 * 4
+    flat_all = torch.zeros(S * words_al, dtype=torch.int32, device=dev)
+    pipes, dets = [], []
+    for si in range(S):
+        ds = dets0 if si == 0 else [d.clone_shared_weights() for d in dets0]
+        dets += ds
+        pipes.append(pipeline.ProbEnPipeline(ds, method, frame_size=(512, 640), out_storage=flat_all[si * words_al: si * words_al + words]))
+    pipe = pipes[0]
+    side = [torch.cuda.Stream(device=dev) for _ in range(S)] if S > 1 else None
+    ev_in, ev_sub = torch.cuda.Event(), [torch.cuda.Event() for _ in range(S)]
     rgb, th = synth_frames(B, 777 + rank)
     host = [torch.from_numpy(rgb).pin_memory(), torch.from_numpy(th).pin_memory()]
     dev_u8 = [h.to(dev) for h in host]
-    host_out = torch.empty(pipe.out.words * (world if world > 1 else 1), dtype=torch.int32).pin_memory()
+    host_out = torch.empty(flat_all.numel() * (world if world > 1 else 1), dtype=torch.int32).pin_memory()
 
     def forward(frames):
-        out = pipe.forward_device(frames, net_hw=(nh, nw))  # uint8 frames; resize fused into the engine's input staging
-        return pipe.gather(out) if world > 1 else out.flat
+        # uint8 frames; resize fused into the engine's input staging
+        if S == 1:
+            pipe.forward_device(frames, net_hw=(nh, nw))
+        else:
+            main = torch.cuda.current_stream(dev)
+            ev_in.record(main)
+            for si in range(S):
+                with torch.cuda.stream(side[si]):
+                    side[si].wait_event(ev_in)
+                    pipes[si].forward_device([f[si * Bs:(si + 1) * Bs] for f in frames], net_hw=(nh, nw))
+                    ev_sub[si].record(side[si])
+            for si in range(S):
+                main.wait_event(ev_sub[si])
+        return pipeline.all_gather_flat(flat_all) if world > 1 else flat_all
 
     def step_device():
         forward(dev_u8)
@@ -327,28 +354,34 @@ def run_pairs(args):
     ms_e2e, _, _ = timed(step_e2e, args.steps, args.warmup)
     # instrumented pass: device time of the tensor-core GEMM launches inside one step.  The two detectors run
     # back to back here (single stream) so that every launch is timed alone on the GPU.
-    streams, pipe.streams = pipe.streams, None
+    saved_streams = [p_.streams for p_ in pipes]
+    for p_ in pipes:
+        p_.streams = None
+    def step_serial():
+        for si in range(S):
+            pipes[si].forward_device([f[si * Bs:(si + 1) * Bs] for f in dev_u8], net_hw=(nh, nw))
     for d in dets:
         d.set_profiling(True)
     for _ in range(2):
-        step_device()
+        step_serial()
         torch.cuda.synchronize()
         prof = [d.last_profile() for d in dets]
     for d in dets:
         d.set_profiling(False)
-    pipe.streams = streams
+    for p_, st_ in zip(pipes, saved_streams):
+        p_.streams = st_
     torch.cuda.synchronize()
     if rank != 0:
         return None
     conv_gf, head_gf = detector_gflop(depth, canvas[0], canvas[1], K)
     flop_step = 2 * B * (conv_gf + head_gf) * 1e9
     gemm_ms = sum(p[0] for p in prof)
-    launches = sum(p[2] for p in prof) + 2 + 2  # + pack x2, fuse x2 (the NCCL all-gather is not ours)
+    launches = sum(p[2] for p in prof) + 4 * S  # + pack x2, fuse x2 per sub-batch (the NCCL all-gather is not ours)
     peaks, peak_kind = measured_peaks()
     peak_tf = peaks.get("bf16_tflops_sustained", peaks["bf16_tflops"])
     achieved = flop_step / (gemm_ms * 1e-3) / 1e12
-    counts = [int(d_.counts[:B].sum().item()) for d_ in pipe.dets]
-    fused = int(pipe.out.counts[:B].sum().item())
+    counts = [sum(int(p_.dets[m].counts[:Bs].sum().item()) for p_ in pipes) for m in range(2)]
+    fused = sum(int(p_.out.counts[:Bs].sum().item()) for p_ in pipes)
     value = world * B * args.steps / (ms * 1e-3)
     out = {
         "metric": "RGB+thermal image-pairs/sec end-to-end (dual Faster R-CNN R%d-FPN -> ProbEn)" % depth,
@@ -359,7 +392,7 @@ def run_pairs(args):
         "config": {"workload": "FLIR RGB+thermal dual detector -> ProbEn (%s/%s), batch %d pairs/GPU, 512x640 frames resized to "
                                "%dx%d (canvas %dx%d), R%d-FPN x2, K=3, 1000 proposals, seeded random weights" %
                                (method[0], method[1], B, nh, nw, canvas[0], canvas[1], depth),
-                   "global_batch": B * world, "parallelism": "dp%d (pairs sharded, one NCCL all-gather of detections)" % world,
+                   "global_batch": B * world, "substreams": S, "parallelism": "dp%d (pairs sharded, one NCCL all-gather of detections)" % world,
                    "l2": "per-step activation working set (several GB) >> 126 MB L2; no explicit flush needed",
                    "detections_per_image": [c / B for c in counts], "fused_per_pair": fused / B},
         "e2e": {"value": world * B * args.steps / (ms_e2e * 1e-3), "unit": "pairs/s",
@@ -519,6 +552,7 @@ def main():
     ap.add_argument("--workload", default="pairs", choices=["pairs", "fusion"])
     ap.add_argument("--batch", type=int, default=16, help="image pairs per GPU per step (pairs workload)")
     ap.add_argument("--depth", type=int, default=50, choices=[50, 101])
+    ap.add_argument("--substreams", type=int, default=1, help="split the per-GPU pair batch into this many stream-parallel sub-batches")
     ap.add_argument("--images", type=int, default=1 << 20)
     ap.add_argument("--models", type=int, default=2)
     ap.add_argument("--mean-dets", type=float, default=7.5, dest="mean_dets")

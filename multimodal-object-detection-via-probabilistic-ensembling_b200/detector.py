@@ -151,6 +151,10 @@ class Detector:
         lib = _lib.load()
         self.lib = lib
         self.device = torch.device(device)
+        self._ctor = dict(depth=depth, num_classes=num_classes, in_channels=in_channels, middle_fusion=middle_fusion,
+                          pixel_mean=tuple(pixel_mean), pixel_std=tuple(pixel_std), score_thresh=score_thresh, nms_thresh=nms_thresh,
+                          rpn_nms_thresh=rpn_nms_thresh, pre_nms_topk=pre_nms_topk, post_nms_topk=post_nms_topk,
+                          detections_per_image=detections_per_image)
         self.num_classes, self.in_channels, self.max_batch = num_classes, in_channels, max_batch
         self.canvas = (int(canvas[0]), int(canvas[1]))
         cfg = _lib.DetectorConfig()
@@ -189,6 +193,18 @@ class Detector:
     def load_state_dict(self, sd):
         blob = pack_weights(sd, self.manifest, self.weight_bytes, self.num_classes)
         self.weights = blob.to(self.device)
+
+    def clone_shared_weights(self, max_batch=None):
+        """A second engine over the SAME weight blob (own scratch + outputs): lets sub-batches of one model run on
+        different streams."""
+        c = self._ctor
+        twin = Detector(None, depth=c["depth"], num_classes=c["num_classes"], in_channels=c["in_channels"], middle_fusion=c["middle_fusion"],
+                        pixel_mean=c["pixel_mean"], pixel_std=c["pixel_std"], max_batch=max_batch or self.max_batch, canvas=self.canvas,
+                        score_thresh=c["score_thresh"], nms_thresh=c["nms_thresh"], rpn_nms_thresh=c["rpn_nms_thresh"],
+                        pre_nms_topk=c["pre_nms_topk"], post_nms_topk=c["post_nms_topk"],
+                        detections_per_image=c["detections_per_image"], device=self.device)
+        twin.weights = self.weights
+        return twin
 
     def share_workspace(self, other):
         """Two detectors with the same plan (e.g. the RGB and the thermal model) can share scratch memory."""

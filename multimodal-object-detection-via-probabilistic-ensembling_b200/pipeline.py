@@ -18,13 +18,21 @@ from .fusion import _method_codes
 class FusedOutput:
     """Views into one flat int32/float32 buffer: [counts B | offsets B*M+1 | classes N | scores N | boxes 4N]."""
 
-    def __init__(self, B, M, device):
+    @staticmethod
+    def words_for(B, M):
+        N = B * M * MAX_DET
+        return B + (B * M + 1) + 2 * N + 4 * N + ((-(B + B * M + 1 + 2 * N)) % 4)
+
+    def __init__(self, B, M, device, storage=None):
+        """``storage``: optional int32 view (``words_for(B, M)`` words, 16-byte aligned) inside a larger buffer, so that
+        several sub-batch pipelines publish their results into ONE tensor (one all-gather)."""
         self.B, self.M = B, M
         self.N = N = B * M * MAX_DET
         self.words = B + (B * M + 1) + N + N + 4 * N
         pad = (-(B + B * M + 1 + 2 * N)) % 4  # keep boxes 16-byte aligned
         self.words += pad
-        self.flat = torch.zeros(self.words, dtype=torch.int32, device=device)
+        self.flat = torch.zeros(self.words, dtype=torch.int32, device=device) if storage is None else storage
+        assert self.flat.numel() == self.words and self.flat.data_ptr() % 16 == 0
         o = 0
         self.counts = self.flat[o:o + B]; o += B
         self.offsets = self.flat[o:o + B * M + 1]; o += B * M + 1
@@ -55,7 +63,7 @@ class FusedOutput:
 class ProbEnPipeline:
     """``detectors``: list of M ``Detector`` objects (same num_classes); model order = fusion order."""
 
-    def __init__(self, detectors, method=("probEn", "v-avg"), iou_thr=0.5, frame_size=(512, 640), concurrent=True):
+    def __init__(self, detectors, method=("probEn", "v-avg"), iou_thr=0.5, frame_size=(512, 640), concurrent=True, out_storage=None):
         self.lib = _lib.load()
         self.detectors = list(detectors)
         self.M = len(self.detectors)
@@ -86,7 +94,7 @@ class ProbEnPipeline:
         self.in_classes = torch.zeros(N, dtype=torch.int32, device=self.device)
         self.in_probs = torch.zeros((N, self.K), dtype=torch.float32, device=self.device)
         self.in_vars = torch.zeros(N, dtype=torch.float32, device=self.device)
-        self.out = FusedOutput(self.B, self.M, self.device)
+        self.out = FusedOutput(self.B, self.M, self.device, storage=out_storage)
         self.ws_bytes = int(self.lib.pe_fuse_workspace_bytes(self.B))
         self.fuse_ws = torch.empty(self.ws_bytes, dtype=torch.uint8, device=self.device)
 

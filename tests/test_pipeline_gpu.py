@@ -89,7 +89,7 @@ def test_three_model_ensemble_pipeline():
     g = torch.Generator().manual_seed(5)
     for i, (name, c, mid) in enumerate(specs):
         cfg = detector.fusion_method_config(name)
-        sd = weights.random_state_dict(50, 3 if mid else c, K, seed=60 + i, middle_fusion=mid)
+        sd = weights.random_state_dict(50, 3 if mid else c, K, seed=(60, 61, 63)[i], middle_fusion=mid)  # seeds with detections
         dets.append(detector.Detector(sd, depth=50, num_classes=K, max_batch=B, canvas=(160, 224), **cfg))
         frames.append(torch.randint(0, 256, (B, 128, 160, c), dtype=torch.uint8, generator=g).cuda())
     pipe = pipeline.ProbEnPipeline(dets, ("probEn", "v-avg"), frame_size=(128, 160))
