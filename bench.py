@@ -366,6 +366,7 @@ def run_pairs(args):
         step_serial()
         torch.cuda.synchronize()
         prof = [d.last_profile() for d in dets]
+        layers = [d.profile_launches() for d in dets]
     for d in dets:
         d.set_profiling(False)
     for p_, st_ in zip(pipes, saved_streams):
@@ -380,6 +381,30 @@ def run_pairs(args):
     peaks, peak_kind = measured_peaks()
     peak_tf = peaks.get("bf16_tflops_sustained", peaks["bf16_tflops"])
     achieved = flop_step / (gemm_ms * 1e-3) / 1e12
+    # per-launch roofline: every GEMM launch is bounded by max(flops / tensor peak, bytes / HBM peak); the sum of
+    # those bounds over the measured sum of launch times says how close the family runs to ITS roofline (many 1x1
+    # layers are HBM-bound, so the pure tensor fraction above cannot reach 1).
+    l_ms = np.concatenate([l[0] for l in layers]); l_fl = np.concatenate([l[1] for l in layers]); l_by = np.concatenate([l[2] for l in layers])
+    t_tensor = l_fl / (peak_tf * 1e12) * 1e3
+    t_hbm = l_by / (peaks["hbm_gbs"] * 1e9) * 1e3
+    bound_ms = np.maximum(t_tensor, t_hbm)
+    per_launch = {"frac": float(bound_ms.sum() / max(1e-9, l_ms.sum())), "bound_ms_per_step": float(bound_ms.sum()),
+                  "measured_ms_per_step": float(l_ms.sum()), "hbm_bound_launches": int((t_hbm > t_tensor).sum()),
+                  "tensor_bound_launches": int((t_hbm <= t_tensor).sum()),
+                  "hbm_bound_ms": float(l_ms[t_hbm > t_tensor].sum()), "tensor_bound_ms": float(l_ms[t_hbm <= t_tensor].sum()),
+                  "frac_hbm_bound": float(t_hbm[t_hbm > t_tensor].sum() / max(1e-9, l_ms[t_hbm > t_tensor].sum())),
+                  "frac_tensor_bound": float(t_tensor[t_hbm <= t_tensor].sum() / max(1e-9, l_ms[t_hbm <= t_tensor].sum())),
+                  "algorithmic_gb_per_step": float(l_by.sum() / 1e9)}
+    # DRAM traffic of the same launches from the committed ncu --set full capture (one detector forward at batch 8),
+    # scaled linearly to this step's 2 x B images; null when the capture is not in the tree
+    traffic, traffic_src = None, None
+    cap = os.path.join(ROOT, "profiles", "r01_conv_gemm_all_layers_b8_ncu_summary.csv")
+    if os.path.isfile(cap) and depth == 50:
+        import csv
+        rows = list(csv.DictReader(open(cap)))
+        mb = sum(float(r["dram_read[Mbyte]"]) + float(r["dram_write[Mbyte]"]) for r in rows)
+        traffic = mb * 1e6 * (2 * B / 8.0)
+        traffic_src = "profiles/r01_conv_gemm_all_layers_b8_ncu_summary.csv (74 GEMM launches, batch 8) x %.1f" % (2 * B / 8.0)
     counts = [sum(int(p_.dets[m].counts[:Bs].sum().item()) for p_ in pipes) for m in range(2)]
     fused = sum(int(p_.out.counts[:Bs].sum().item()) for p_ in pipes)
     value = world * B * args.steps / (ms * 1e-3)
@@ -400,11 +425,13 @@ def run_pairs(args):
         "gpu_launches": launches * args.steps,
         "clocks": clocks,
         "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf,
-                     "traffic": None, "peak_kind": peak_kind + " (sustained cuBLAS bf16)", "kernel": "conv_gemm_kernel<*> (tcgen05)",
+                     "traffic": traffic, "traffic_unit": "DRAM bytes per step over the GEMM launches", "traffic_source": traffic_src,
+                     "peak_kind": peak_kind + " (sustained cuBLAS bf16)", "kernel": "conv_gemm_kernel<*> (tcgen05)",
                      "algorithmic_gflop_per_step": flop_step / 1e9, "gemm_ms_per_step": gemm_ms,
                      "gemm_launches_per_step": sum(p[3] for p in prof),
                      "gemm_share_of_serial_step": gemm_ms / max(1e-9, sum(p[1] for p in prof)) if prof else None,
-                     "step_frac_of_peak": flop_step / (ms / args.steps * 1e-3) / 1e12 / peak_tf},
+                     "step_frac_of_peak": flop_step / (ms / args.steps * 1e-3) / 1e12 / peak_tf,
+                     "per_launch_roofline": per_launch},
     }
     out["cpu_baseline"] = cpu_pairs_baseline(depth, method, n_pairs=1)
     return out

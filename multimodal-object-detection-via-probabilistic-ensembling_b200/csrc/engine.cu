@@ -42,6 +42,7 @@ struct pe_detector {
   bool profiling = false;
   std::vector<cudaEvent_t> ev;
   int ev_used = 0;
+  std::vector<double> prof_flops, prof_bytes;  // algorithmic work of the GEMM launch behind each event pair
   int last_launches = 0, last_gemm_launches = 0;
   std::vector<pe::Param> params;
   std::vector<pe::Buf> bufs;
@@ -196,6 +197,15 @@ struct Runner {
       }
       e0 = d->ev[d->ev_used++];
       e1 = d->ev[d->ev_used++];
+      const int pad = (cd.KH - 1) / 2;
+      const double Ho = (cd.H + 2 * pad - cd.KH) / cd.stride + 1, Wo = (cd.W + 2 * pad - cd.KW) / cd.stride + 1;
+      const double taps = (double)cd.KH * cd.KW * cd.Cin, opix = (double)cd.N * Ho * Wo;
+      double bytes = (double)cd.N * cd.H * cd.W * cd.Cin * 2 / ((cd.KH == 1 && cd.stride == 2) ? 4.0 : 1.0) +
+                     taps * cd.Cout * 2 + cd.Cout * 4.0 + opix * cd.Cout * (cd.out_fp32 ? 4 : 2);
+      if (cd.residual_mode == 1) bytes += opix * cd.Cout * 2;
+      if (cd.residual_mode == 2) bytes += opix * cd.Cout * 2 / 4.0;
+      d->prof_flops.push_back(2.0 * opix * cd.Cout * taps);
+      d->prof_bytes.push_back(bytes);
       cudaEventRecord(e0, st);
     }
     const int s = conv2d_launch(cd, x, w, bias, res, y, st);
@@ -250,7 +260,14 @@ struct Runner {
           if (cudaEventCreate(&e) != cudaSuccess) { status = PE_ERR_CUDA; break; }
           d->ev.push_back(e);
         }
-        if (status == PE_OK) { e0 = d->ev[d->ev_used++]; e1 = d->ev[d->ev_used++]; cudaEventRecord(e0, st); }
+        if (status == PE_OK) {
+          e0 = d->ev[d->ev_used++];
+          e1 = d->ev[d->ev_used++];
+          const double opix = (double)B * (c.canvas_h / 2) * (c.canvas_w / 2);
+          d->prof_flops.push_back(2.0 * opix * 64 * 49 * d->stem_c);
+          d->prof_bytes.push_back((double)B * c.canvas_h * c.canvas_w * 8 + opix * 64 * 2 + 64.0 * kStemK * 2);
+          cudaEventRecord(e0, st);
+        }
       }
       if (status == PE_OK)
         status = conv_stem_launch(buf("stem_canvas"), wts + p.w_off, reinterpret_cast<const float*>(wts + p.b_off), buf("stem_out"), B,
@@ -437,6 +454,23 @@ extern "C" PE_API int pe_detector_last_profile(pe_detector* d, float* gemm_ms, f
   return PE_OK;
 }
 
+// Per-launch view of the same instrumentation: device time, algorithmic FLOPs and algorithmic bytes (each operand
+// once: input, weights, bias, residual, output) of GEMM launch i of the last forward.  Returns the launch count.
+extern "C" PE_API int pe_detector_profile_launches(pe_detector* d, float* ms, double* flops, double* bytes, int capacity) {
+  if (!d) return 0;
+  const int n = d->ev_used / 2;
+  if (!d->profiling || n == 0) return 0;
+  if (cudaEventSynchronize(d->ev[d->ev_used - 1]) != cudaSuccess) return 0;
+  for (int i = 0; i < n && i < capacity; ++i) {
+    float t = 0.f;
+    cudaEventElapsedTime(&t, d->ev[2 * i], d->ev[2 * i + 1]);
+    if (ms) ms[i] = t;
+    if (flops) flops[i] = i < (int)d->prof_flops.size() ? d->prof_flops[i] : 0.0;
+    if (bytes) bytes[i] = i < (int)d->prof_bytes.size() ? d->prof_bytes[i] : 0.0;
+  }
+  return n;
+}
+
 extern "C" PE_API int pe_resize_frames(const uint8_t* frames, float* out, int B, int C, int src_h, int src_w, int dst_h, int dst_w,
                                        int round_u8, void* stream) {
   if (!frames || !out || B < 1 || C < 1 || src_h < 1 || src_w < 1 || dst_h < 1 || dst_w < 1) return PE_ERR_INVALID_ARGUMENT;
@@ -476,6 +510,8 @@ extern "C" PE_API int pe_detector_forward(pe_detector* d, const void* weights, c
   if (img_h < 1 || img_w < 1 || img_h > d->cfg.canvas_h || img_w > d->cfg.canvas_w) return PE_ERR_INVALID_ARGUMENT;
   if (workspace_bytes < d->ws_bytes) return PE_ERR_WORKSPACE_TOO_SMALL;
   d->ev_used = 0;
+  d->prof_flops.clear();
+  d->prof_bytes.clear();
   d->last_launches = 0;
   d->last_gemm_launches = 0;
   pe::Runner r;
@@ -495,6 +531,8 @@ extern "C" PE_API int pe_detector_forward_frames(pe_detector* d, const void* wei
   if (img_h < 1 || img_w < 1 || img_h > d->cfg.canvas_h || img_w > d->cfg.canvas_w) return PE_ERR_INVALID_ARGUMENT;
   if (workspace_bytes < d->ws_bytes) return PE_ERR_WORKSPACE_TOO_SMALL;
   d->ev_used = 0;
+  d->prof_flops.clear();
+  d->prof_bytes.clear();
   d->last_launches = 0;
   d->last_gemm_launches = 0;
   pe::Runner r;

@@ -259,6 +259,15 @@ class Detector:
                    "pe_detector_last_profile")
         return g.value, s.value, n.value, ng.value
 
+    def profile_launches(self, capacity=512):
+        """Per GEMM launch of the last profiled forward: (ms, algorithmic flops, algorithmic bytes) numpy arrays."""
+        import numpy as np
+        ms = (ctypes.c_float * capacity)()
+        fl = (ctypes.c_double * capacity)()
+        by = (ctypes.c_double * capacity)()
+        n = min(capacity, self.lib.pe_detector_profile_launches(self.handle, ms, fl, by, capacity))
+        return np.array(ms[:n]), np.array(fl[:n]), np.array(by[:n])
+
     def forward(self, batched_inputs):
         """GeneralizedRCNN.forward-compatible entry (inference only): all images must share one size."""
         imgs = torch.stack([x["image"].to(torch.float32) for x in batched_inputs]).to(self.device)
