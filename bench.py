@@ -388,6 +388,12 @@ def run_pairs(args):
     t_tensor = l_fl / (peak_tf * 1e12) * 1e3
     t_hbm = l_by / (peaks["hbm_gbs"] * 1e9) * 1e3
     bound_ms = np.maximum(t_tensor, t_hbm)
+    if args.dump_launches:
+        with open(args.dump_launches, "w") as f:
+            f.write("idx,ms,gflop,mbytes,tensor_bound_ms,hbm_bound_ms,frac_of_bound,lost_ms\n")
+            for i in range(len(l_ms)):
+                f.write("%d,%.5f,%.3f,%.3f,%.5f,%.5f,%.3f,%.5f\n" % (i, l_ms[i], l_fl[i] / 1e9, l_by[i] / 1e6, t_tensor[i], t_hbm[i],
+                                                                  bound_ms[i] / max(1e-9, l_ms[i]), l_ms[i] - bound_ms[i]))
     per_launch = {"frac": float(bound_ms.sum() / max(1e-9, l_ms.sum())), "bound_ms_per_step": float(bound_ms.sum()),
                   "measured_ms_per_step": float(l_ms.sum()), "hbm_bound_launches": int((t_hbm > t_tensor).sum()),
                   "tensor_bound_launches": int((t_hbm <= t_tensor).sum()),
@@ -577,6 +583,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="pairs", choices=["pairs", "fusion"])
+    ap.add_argument("--dump_launches", default="", help="write the per-GEMM-launch roofline table of the instrumented pass to this CSV")
     ap.add_argument("--batch", type=int, default=16, help="image pairs per GPU per step (pairs workload)")
     ap.add_argument("--depth", type=int, default=50, choices=[50, 101])
     ap.add_argument("--substreams", type=int, default=1, help="split the per-GPU pair batch into this many stream-parallel sub-batches")

@@ -623,6 +623,61 @@ __global__ void __launch_bounds__(224) roi_align_kernel(const RoiLevels fl, cons
       if (ay.hi == y0 + lane) wy += ay.frac;
     }
     __syncthreads();
+    // Column sweep: walk the bin row's pixel columns once, reduce each column over the rows (t = sum_y Wy f), and add
+    // Wx * t to the bins that contain the column.  Adjacent bins share their border columns, so this loads ~20 % fewer
+    // pixels than bin-by-bin and does the row reduction once per column instead of once per (bin, column).  Needs every
+    // column to lie in at most two bins (block-uniform test; tiny ROIs take the bin-by-bin loop below).
+    bool sweep = true;
+#pragma unroll
+    for (int pw = 0; pw < 5; ++pw) sweep &= s_x0[pw + 2] > s_x0[pw] + s_nx[pw] - 1;
+#pragma unroll
+    for (int pw = 0; pw < 6; ++pw) sweep &= s_x0[pw + 1] >= s_x0[pw] && s_x0[pw + 1] + s_nx[pw + 1] >= s_x0[pw] + s_nx[pw];
+    if (sweep) {
+      const float inv_count = 1.f / count;
+      for (int g = lane; g < cgroups; g += 32) {
+        float cur[8], nxt[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { cur[j] = 0.f; nxt[j] = 0.f; }
+        int pw = 0;
+        const int xe = s_x0[6] + s_nx[6] - 1;
+        for (int x = s_x0[0]; x <= xe && pw < 7; ++x) {
+          float t[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) t[j] = 0.f;
+          const __nv_bfloat16* colp = feat + ((size_t)y0 * W + x) * C;
+          for (int rr = 0; rr < ny; ++rr) {
+            const float wyr = __shfl_sync(kFullMask, wy, rr);
+            if (wyr == 0.f) continue;
+            const uint4 v = __ldg(reinterpret_cast<const uint4*>(colp + (size_t)rr * W * C) + g);
+            t[0] += wyr * bflo(v.x); t[1] += wyr * bfhi(v.x); t[2] += wyr * bflo(v.y); t[3] += wyr * bfhi(v.y);
+            t[4] += wyr * bflo(v.z); t[5] += wyr * bfhi(v.z); t[6] += wyr * bflo(v.w); t[7] += wyr * bfhi(v.w);
+          }
+          const int c0 = x - s_x0[pw];
+          if (c0 >= 0 && c0 < s_nx[pw]) {
+            const float w = s_wx[pw][c0];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) cur[j] += w * t[j];
+          }
+          if (pw < 6) {
+            const int c1 = x - s_x0[pw + 1];
+            if (c1 >= 0 && c1 < s_nx[pw + 1]) {
+              const float w = s_wx[pw + 1][c1];
+#pragma unroll
+              for (int j = 0; j < 8; ++j) nxt[j] += w * t[j];
+            }
+          }
+          while (pw < 7 && x >= s_x0[pw] + s_nx[pw] - 1) {  // bin pw is complete (two bins may end on the same column)
+            dst_roi[(size_t)(ph * 7 + pw) * cgroups + g] =
+                make_uint4(packbf(cur[0] * inv_count, cur[1] * inv_count), packbf(cur[2] * inv_count, cur[3] * inv_count),
+                           packbf(cur[4] * inv_count, cur[5] * inv_count), packbf(cur[6] * inv_count, cur[7] * inv_count));
+#pragma unroll
+            for (int j = 0; j < 8; ++j) { cur[j] = nxt[j]; nxt[j] = 0.f; }
+            ++pw;
+          }
+        }
+      }
+      return;
+    }
     for (int g = lane; g < cgroups; g += 32) {
       for (int pw = 0; pw < 7; ++pw) {
         const int x0 = s_x0[pw], nx = s_nx[pw];
