@@ -174,66 +174,72 @@ constexpr int kWin = 4;
 
 // SCORE: PE_SCORE_* ; kNms: the ('max','argmax') torchvision-NMS path
 template <int K, int SCORE, bool kNms>
-__global__ void __launch_bounds__(kBlockThreads) fuse_packed_kernel(const FuseArgs a) {
+__global__ void __launch_bounds__(kBlockThreads, 4) fuse_packed_kernel(const FuseArgs a) {
+  __shared__ float4 s_boxes[kBlockThreads / 32][32];  // per warp: matching boxes of the pack
+  __shared__ float2 s_auxes[kBlockThreads / 32][32];  // per warp: (area, score key)
   const int lane = threadIdx.x & 31;
+  float4* const s_box = s_boxes[threadIdx.x >> 5];
+  float2* const s_aux = s_auxes[threadIdx.x >> 5];
   const int warps_total = (gridDim.x * blockDim.x) >> 5;
   const int win = a.M <= 7 ? kWin : 1;
   const int nwin = (a.B + win - 1) / win;
 
+  // fast-decision margin of the class-offset float32 boxes: |coordinate| <= cbound is checked per detection
+  const float cbound = (float)(K + 2) * fmaxf(fmaxf(a.img_w, a.img_h), 1.f);
+  const float ebound = 1.9073486328125e-6f * cbound;  // 2^-19 * cbound, see the pair loop
+  const float nthr = -a.thr;
+
   for (int wi = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; wi < nwin; wi += warps_total) {
     const int img0 = wi * win;
     const int nimg = min(win, a.B - img0);
-    // offsets of the window: lane L holds offs[img0*M + L]
+    // offsets of the window: lane L holds offs[img0*M + min(L, nimg*M)]
     const int no = nimg * a.M;
-    const int o = lane <= no ? __ldg(a.offs + (size_t)img0 * a.M + lane) : 0;
+    const int o = __ldg(a.offs + (size_t)img0 * a.M + min(lane, no));
     const int len = __shfl_down_sync(kFullMask, o, 1) - o;
     const unsigned nonempty = __ballot_sync(kFullMask, lane < no && len > 0);
+    {  // images that never enter a pack: empty, too large for a warp (block kernel's work list), over the cap
+      const int li = min(lane, nimg);
+      const int ni = __shfl_sync(kFullMask, o, min(li + 1, nimg) * a.M) - __shfl_sync(kFullMask, o, li * a.M);
+      if (lane < nimg) {
+        if (ni <= 0) a.out_counts[img0 + lane] = 0;
+        else if (ni > kMaxBlockDets) a.out_counts[img0 + lane] = -1;
+        else if (ni > 32) a.big_list[atomicAdd(a.big_count, 1)] = img0 + lane;
+      }
+    }
     int cur = 0;
     while (cur < nimg) {
-      // ---- greedy packing of images cur.. into the 32 lanes (warp-uniform scalar logic)
-      int seg_img[kWin], seg_lo[kWin], seg_n[kWin], seg_live[kWin], seg_base[kWin];
-      int nseg = 0, used = 0;
-      while (cur < nimg) {
-        const int base = __shfl_sync(kFullMask, o, cur * a.M);
-        const int n = __shfl_sync(kFullMask, o, (cur + 1) * a.M) - base;
-        if (n <= 0 || n > 32) {
-          if (lane == 0) {
-            if (n <= 0) a.out_counts[img0 + cur] = 0;
-            else if (n > kMaxBlockDets) a.out_counts[img0 + cur] = -1;
-            else a.big_list[atomicAdd(a.big_count, 1)] = img0 + cur;
-          }
-          ++cur;
-          continue;
-        }
-        if (used + n > 32) break;
-        seg_img[nseg] = img0 + cur;
-        seg_lo[nseg] = used;
-        seg_n[nseg] = n;
-        seg_base[nseg] = base;
-        seg_live[nseg] = __popc((nonempty >> (cur * a.M)) & ((1u << a.M) - 1u));
-        used += n;
-        ++nseg;
-        ++cur;
-        if (nseg == kWin) break;
-      }
-      if (nseg == 0) continue;
-      // ---- lane -> (segment, row)
-      int sg = -1, lo = 0, n = 0, base = 0, live = 0, my_img = 0;
-#pragma unroll
-      for (int s2 = 0; s2 < kWin; ++s2)
-        if (s2 < nseg && lane >= seg_lo[s2] && lane < seg_lo[s2] + seg_n[s2]) {
-          sg = s2; lo = seg_lo[s2]; n = seg_n[s2]; base = seg_base[s2]; live = seg_live[s2]; my_img = seg_img[s2];
-        }
-      const bool act = sg >= 0;
-      // idle lanes share ONE member mask (distinct masks inside a warp collective are processed one after another)
-      const unsigned usedmask = used == 32 ? kFullMask : ((1u << used) - 1u);
-      const unsigned segmask = act ? (n == 32 ? kFullMask : (((1u << n) - 1u) << lo)) : ~usedmask;
-      const int row = act ? base + (lane - lo) : 0;
+      // ---- greedy packing of images cur.. into the 32 lanes: cumulative detection counts t1..t4 (warp-uniform)
+      const int c0 = __shfl_sync(kFullMask, o, cur * a.M);
+      const int t1 = __shfl_sync(kFullMask, o, min(cur + 1, nimg) * a.M) - c0;
+      const int t2 = __shfl_sync(kFullMask, o, min(cur + 2, nimg) * a.M) - c0;
+      const int t3 = __shfl_sync(kFullMask, o, min(cur + 3, nimg) * a.M) - c0;
+      const int t4 = __shfl_sync(kFullMask, o, min(cur + 4, nimg) * a.M) - c0;
+      const int npk = min((t1 <= 32) + (t2 <= 32) + (t3 <= 32) + (t4 <= 32), nimg - cur);
+      if (npk == 0) { ++cur; continue; }  // more than 32 detections: handled above
+      const int used = npk == 1 ? t1 : (npk == 2 ? t2 : (npk == 3 ? t3 : t4));
+      // ---- lane -> (segment, row); idle lanes form one-lane segments of their own
+      const bool act = lane < used;
+      const int sg = (lane >= t1) + (lane >= t2) + (lane >= t3);
+      const int lo = !act ? lane : (sg == 0 ? 0 : (sg == 1 ? t1 : (sg == 2 ? t2 : t3)));
+      const int hi = !act ? lane + 1 : (sg == 0 ? t1 : (sg == 1 ? t2 : (sg == 2 ? t3 : t4)));
+      const int n = hi - lo;
+      const int base = c0 + lo;
+      const int my_img = img0 + cur + sg;
+      const int live = act ? __popc((nonempty >> ((cur + sg) * a.M)) & ((1u << a.M) - 1u)) : 0;
+      cur += npk;
+      if (used == 0) continue;
+      const unsigned segmask = (n == 32 ? kFullMask : ((1u << n) - 1u)) << lo;
+      const int row = act ? c0 + lane : 0;
+      const bool cluster = live >= 2;
       const float4 box = act ? __ldg(a.boxes + row) : make_float4(0.f, 0.f, 0.f, 0.f);
       const float score = act ? __ldg(a.scores + row) : 0.f;
       const int cls = act ? __ldg(a.classes + row) : 0;
-      const bool cluster = act && live >= 2;
-      if (act && live == 1) {  // single contributing model: pass-through in input order (demo_probEn.py:240-252)
+      // fusion-stage inputs are requested now so that their latency hides behind the pair loop
+      float pr[K];
+#pragma unroll
+      for (int k = 0; k < K; ++k) pr[k] = (cluster && !kNms) ? __ldg(a.probs + (size_t)row * K + k) : 0.25f;
+      const float var = (cluster && !kNms && a.box_mode == PE_BOX_VAVG) ? __ldg(a.vars + row) : 1.f;
+      if (live == 1) {  // single contributing model: pass-through in input order (demo_probEn.py:240-252)
         a.out_boxes[row] = box;
         a.out_scores[row] = score;
         a.out_classes[row] = cls;
@@ -241,7 +247,8 @@ __global__ void __launch_bounds__(kBlockThreads) fuse_packed_kernel(const FuseAr
       }
       if (!__any_sync(kFullMask, cluster)) continue;
 
-      float4 mbox = box;
+      // ---- stage the matching records of the pack in shared memory (one tile per warp)
+      float4 mbox;
       float area;
       if (kNms) {  // torchvision batched_nms coordinate trick: boxes + class * (max coordinate + 1), float32
         float mc = cluster ? fmaxf(fmaxf(box.x, box.y), fmaxf(box.z, box.w)) : -INFINITY;
@@ -250,50 +257,116 @@ __global__ void __launch_bounds__(kBlockThreads) fuse_packed_kernel(const FuseAr
           unsigned best = 0;
 #pragma unroll
           for (int s2 = 0; s2 < kWin; ++s2)
-            if (s2 < nseg) { const unsigned ms = __reduce_max_sync(kFullMask, sg == s2 ? kk : 0u); if (sg == s2) best = ms; }
+            if (s2 < npk) {
+              const unsigned ms = __reduce_max_sync(kFullMask, (act && sg == s2) ? kk : 0u);
+              if (sg == s2) best = ms;
+            }
           mc = key_score(best);
         }
         mbox = offset_box(box, __fmul_rn((float)cls, __fadd_rn(mc, 1.f)));
         area = nms_area(mbox);
       } else {
+        // class-offset boxes (demo_probEn.py:100-105) in float32 with the legacy +1 folded into x2, y2: only used
+        // for the fast decision, whose margin covers the rounding; borderline pairs re-evaluate the float64
+        // expression.  Detections outside the margin's coordinate bound, with non-positive area or non-finite
+        // fields get a NaN area, which sends every pair they take part in to the exact path.
+        const float fc = (float)cls;
+        mbox = make_float4(fmaf(fc, a.img_w, box.x), fmaf(fc, a.img_h, box.y), fmaf(fc, a.img_w, box.z) + 1.f,
+                           fmaf(fc, a.img_h, box.w) + 1.f);
         area = (box.z - box.x + 1.f) * (box.w - box.y + 1.f);
+        const float emax = fmaxf(fmaxf(fabsf(mbox.x), fabsf(mbox.y)), fmaxf(fabsf(mbox.z), fabsf(mbox.w)));
+        if (!(emax <= cbound) || !(area > 0.f)) area = __int_as_float(0x7fc00000);
+      }
+      const unsigned skey = score_key(score);
+      __syncwarp();  // the previous pack's readers are done with the tile
+      s_box[lane] = mbox;
+      s_aux[lane] = make_float2(area, __uint_as_float(skey));
+      __syncwarp();
+
+      // ---- all pairs of a segment, once each: in round r lane idx meets idx + r (mod n) and hands the verdict
+      //      back to it with one shuffle.  up = earlier-ranked lanes I match, higher = lanes ranked before me
+      //      (score desc; ties: higher lane first for the bayesian order, lower lane first for torchvision's
+      //      stable sort)
+      unsigned up = 0, higher = 0;
+      {
+        const int half = cluster ? (n >> 1) : 0;
+        const int rounds = __reduce_max_sync(kFullMask, half);
+        int pl = lane, ql = lane;
+        for (int r = 1; r <= rounds; ++r) {
+          pl = pl + 1 == hi ? lo : pl + 1;
+          ql = ql == lo ? hi - 1 : ql - 1;
+          const bool valid = r <= half;
+          const float4 pb = s_box[pl];
+          const float2 pa = s_aux[pl];
+          bool mt;
+          if (kNms) {
+            const float w = fmaxf(0.f, __fsub_rn(fminf(mbox.z, pb.z), fmaxf(mbox.x, pb.x)));
+            const float hh = fmaxf(0.f, __fsub_rn(fminf(mbox.w, pb.w), fmaxf(mbox.y, pb.y)));
+            const float inter = __fmul_rn(w, hh);
+            const float den = __fsub_rn(__fadd_rn(area, pa.x), inter);
+            const float d = fmaf(nthr, den, inter);
+            mt = d > 0.f;
+            if (!(fabsf(d) > 1e-5f * fabsf(den)) || !(den > 0.f)) mt = __fdiv_rn(inter, den) > a.thr;
+          } else {
+            // |error of w, hh| <= 2^-21 * cbound each (offset rounding + two float32 operations), so
+            // |error of inter - thr * uni| < ebound * (w + hh + 1) + 1e-5 * uni
+            const float w = fmaxf(fminf(mbox.z, pb.z) - fmaxf(mbox.x, pb.x), 0.f);
+            const float hh = fmaxf(fminf(mbox.w, pb.w) - fmaxf(mbox.y, pb.y), 0.f);
+            const float inter = w * hh;
+            const float uni = (area + pa.x) - inter;
+            const float d = fmaf(nthr, uni, inter);
+            const float tol = fmaf(ebound, w + hh, fmaf(1e-5f, uni, ebound));
+            mt = d > 0.f;
+            if (valid && !(fabsf(d) > tol))  // also taken when uni is NaN
+              mt = match_exact_f64(box, cls, __ldg(a.boxes + base + (pl - lo)), __ldg(a.classes + base + (pl - lo)),
+                                   a.img_w, a.img_h, a.thr);
+          }
+          const unsigned pk = __float_as_uint(pa.y);
+          const bool before = pk > skey || (pk == skey && (kNms ? pl < lane : pl > lane));
+          const unsigned res = mt ? (before ? 3u : 1u) : (before ? 2u : 0u);
+          const unsigned back = __shfl_sync(kFullMask, res, ql);
+          const unsigned pbit = valid ? 1u << pl : 0u, qbit = valid ? 1u << ql : 0u;
+          if (before) higher |= pbit;
+          if (res == 3u) up |= pbit;
+          if (!(back & 2u)) higher |= qbit;  // the partner ranks me after itself
+          if (back == 1u) up |= qbit;
+        }
       }
 
-      // ---- greedy clustering: per segment, head = max remaining score (ties: higher lane for the bayesian
-      //      order, lower lane for torchvision's stable sort)
-      bool removed = !cluster;
-      unsigned my_cluster = 0;
-      int my_pos = -1, nheads = 0;
-      const unsigned skey = score_key(score);
-      // Full-warp collectives only (sub-warp member masks make the compiler emit a serialising loop per distinct
-      // mask): one redux per packed segment, ballots masked afterwards.
+      // ---- greedy clustering as a fixed point over the pair bits: a detection is a cluster head iff every
+      //      earlier-ranked detection it matches was itself absorbed; absorbed iff it matches an earlier head.
+      //      Each round settles at least the earliest undecided detection of every segment.
+      const unsigned clmask = __ballot_sync(kFullMask, cluster);
+      bool is_head = cluster && up == 0u, is_rem = false;
+      unsigned heads = __ballot_sync(kFullMask, is_head);
       while (true) {
-        const unsigned key = removed ? 0u : skey;
-        unsigned m = 0;
-#pragma unroll
-        for (int s2 = 0; s2 < kWin; ++s2) {
-          if (s2 < nseg) {  // warp-uniform
-            const unsigned ms = __reduce_max_sync(kFullMask, sg == s2 ? key : 0u);
-            if (sg == s2) m = ms;
+        is_rem = (up & heads) != 0u;
+        const unsigned rem = __ballot_sync(kFullMask, is_rem);
+        is_head = cluster && (up & ~rem) == 0u;
+        heads = __ballot_sync(kFullMask, is_head);
+        if (((heads | rem) & clmask) == clmask) break;
+      }
+      // owner of an absorbed detection: the earliest-ranked head it matches
+      int owner = lane;
+      {
+        unsigned cand = is_rem ? (up & heads) : 0u;
+        if (cand) owner = __ffs(cand) - 1;
+        if (__any_sync(kFullMask, (cand & (cand - 1u)) != 0u)) {
+          const int myrank = __popc(higher);
+          int bestrank = 0x7fffffff;
+          while (__any_sync(kFullMask, cand != 0u)) {
+            const bool has = cand != 0u;
+            const int c = has ? __ffs(cand) - 1 : lane;
+            if (has) cand &= cand - 1u;
+            const int rc = __shfl_sync(kFullMask, myrank, c);
+            if (has && rc < bestrank) { bestrank = rc; owner = c; }
           }
         }
-        if (__ballot_sync(kFullMask, m != 0u) == 0u) break;
-        const unsigned cand = __ballot_sync(kFullMask, key == m && !removed) & segmask;
-        const int hl = (m && cand) ? (kNms ? __ffs(cand) - 1 : 31 - __clz(cand)) : lane;
-        const float4 hb = shfl4(mbox, hl);
-        const int hc = __shfl_sync(kFullMask, cls, hl);
-        const float ha = __shfl_sync(kFullMask, area, hl);
-        bool mt = false;
-        if (!removed && lane != hl)
-          mt = kNms ? match_nms(hb, ha, mbox, area, a.thr) : match_bayes(hb, hc, ha, mbox, cls, area, a.img_w, a.img_h, a.thr);
-        const unsigned mm = __ballot_sync(kFullMask, mt) & segmask;
-        if (m != 0u) {
-          if (lane == hl) { my_cluster = mm; my_pos = nheads; removed = true; }
-          removed |= mt;
-          ++nheads;
-        }
       }
-      if (cluster && lane == lo) a.out_counts[my_img] = nheads;
+      const unsigned same_owner = __match_any_sync(kFullMask, owner);
+      const unsigned my_cluster = is_head ? (same_owner & ~(1u << lane)) : 0u;
+      const int my_pos = is_head ? __popc(heads & higher) : -1;
+      if (cluster && lane == lo) a.out_counts[my_img] = __popc(heads & segmask);
 
       if (kNms) {  // survivors keep their own record (demo_probEn.py:66-69)
         if (my_pos >= 0) {
@@ -312,7 +385,7 @@ __global__ void __launch_bounds__(kBlockThreads) fuse_packed_kernel(const FuseAr
         bool bad = false;
 #pragma unroll
         for (int k = 0; k < K; ++k) {
-          const float p = cluster ? __ldg(a.probs + (size_t)row * K + k) : 0.25f;
+          const float p = pr[k];
           sp = __dadd_rn(sp, (double)p);
           lg[k] = __logf(p);
           bad |= p < 0.f;
@@ -323,7 +396,7 @@ __global__ void __launch_bounds__(kBlockThreads) fuse_packed_kernel(const FuseAr
         if (bad || bg < 0.0) lg[0] = __int_as_float(0x7fc00000);  // the reference's log(negative) -> NaN posterior
       }
       float wgt = 1.f;
-      if (a.box_mode == PE_BOX_VAVG) wgt = cluster ? __frcp_rn(__ldg(a.vars + row)) : 1.f;
+      if (a.box_mode == PE_BOX_VAVG) wgt = __frcp_rn(var);
       else if (a.box_mode == PE_BOX_SAVG) wgt = score;
 
       float S[K + 1];
