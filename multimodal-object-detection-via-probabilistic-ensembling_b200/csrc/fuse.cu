@@ -170,16 +170,90 @@ __device__ __forceinline__ float key_score(unsigned k) {
   return __uint_as_float((k & 0x80000000u) ? (k & 0x7fffffffu) : ~k);
 }
 
+// Pair loop of the packed kernel.  Every lane walks its segment's lanes in a circle (partner = next lane, wrapping
+// at the segment end), so after n/2 rounds each unordered pair has been evaluated by one of its two lanes; visits
+// beyond that (shorter segments keep turning while the longest one finishes) repeat consistent verdicts, and a
+// lane meeting itself only sets its own bit, which is cleared at the end.  kExact = false: float32 decision with an
+// error margin, returns true if some decision was inside the margin.  kExact = true: the reference's arithmetic.
+struct PairCtx {
+  float4 mbox;
+  float area;
+  unsigned skey;
+  int lane, lo, hi, rounds;
+  float nthr, thr, ebound;
+  const float4* rec;
+};
+
+template <bool kNms, bool kExact>
+__device__ __forceinline__ bool pair_rounds(const PairCtx& c, const FuseArgs& a, float4 box, int cls, int row0,
+                                            unsigned& up_out, unsigned& higher_out) {
+  const unsigned mybit = 1u << c.lane, lobit = 1u << c.lo, topbit = 1u << (c.hi - 1);
+  const float4* const p_lo = c.rec + 2 * c.lo;
+  const float4* pp = c.rec + 2 * c.lane;
+  unsigned pbit = mybit, qbit = mybit, up = 0u, higher = 0u;
+  bool unsure = false;
+#pragma unroll 2
+  for (int r = 0; r < c.rounds; ++r) {
+    const bool pwrap = pbit == topbit, qwrap = qbit == lobit;
+    pbit = pwrap ? lobit : pbit << 1;
+    pp = pwrap ? p_lo : pp + 2;
+    qbit = qwrap ? topbit : qbit >> 1;
+    const float4 pb = pp[0];
+    const float4 pa = pp[1];
+    bool mt;
+    if (kNms) {
+      const float w = fmaxf(0.f, __fsub_rn(fminf(c.mbox.z, pb.z), fmaxf(c.mbox.x, pb.x)));
+      const float hh = fmaxf(0.f, __fsub_rn(fminf(c.mbox.w, pb.w), fmaxf(c.mbox.y, pb.y)));
+      const float inter = __fmul_rn(w, hh);
+      const float den = __fsub_rn(__fadd_rn(c.area, pa.x), inter);
+      if (kExact) {
+        mt = __fdiv_rn(inter, den) > c.thr;
+      } else {
+        const float d = fmaf(c.nthr, den, inter);
+        mt = d > 0.f;
+        unsure |= !(fabsf(d) > 1e-5f * den) || !(den > 0.f);  // also when den is NaN
+      }
+    } else if (kExact) {
+      const int prow = row0 + (__ffs(pbit) - 1);
+      mt = match_exact_f64(box, cls, __ldg(a.boxes + prow), __ldg(a.classes + prow), a.img_w, a.img_h, c.thr);
+    } else {
+      // |error of w, hh| <= 2^-21 * cbound each (offset rounding + two float32 operations), so
+      // |error of inter - thr * uni| < ebound * (w + hh + 1) + 1e-5 * uni
+      const float w = fmaxf(fminf(c.mbox.z, pb.z) - fmaxf(c.mbox.x, pb.x), 0.f);
+      const float hh = fmaxf(fminf(c.mbox.w, pb.w) - fmaxf(c.mbox.y, pb.y), 0.f);
+      const float inter = w * hh;
+      const float uni = (c.area + pa.x) - inter;
+      const float d = fmaf(c.nthr, uni, inter);
+      const float tol = fmaf(c.ebound, w + hh, fmaf(1e-5f, uni, c.ebound));
+      mt = d > 0.f;
+      unsure |= !(fabsf(d) > tol);  // also when an area is NaN (flagged detections)
+    }
+    const unsigned pk = __float_as_uint(pa.y);
+    // score desc; ties: higher lane first for the bayesian order, lower lane first for torchvision's stable sort
+    const bool before = pk > c.skey || (pk == c.skey && (kNms ? pbit < mybit : pbit > mybit));
+    const unsigned all_mt = __ballot_sync(kFullMask, mt);
+    const unsigned all_bf = __ballot_sync(kFullMask, before);
+    if (before) {
+      higher |= pbit;
+      if (mt) up |= pbit;
+    }
+    // the lane whose partner I am ranks me after itself iff its 'before' bit is clear
+    higher |= ~all_bf & qbit;
+    up |= all_mt & ~all_bf & qbit;
+  }
+  up_out = up & ~mybit;
+  higher_out = higher & ~mybit;
+  return unsure;
+}
+
 constexpr int kWin = 4;
 
 // SCORE: PE_SCORE_* ; kNms: the ('max','argmax') torchvision-NMS path
 template <int K, int SCORE, bool kNms>
 __global__ void __launch_bounds__(kBlockThreads, 4) fuse_packed_kernel(const FuseArgs a) {
-  __shared__ float4 s_boxes[kBlockThreads / 32][32];  // per warp: matching boxes of the pack
-  __shared__ float2 s_auxes[kBlockThreads / 32][32];  // per warp: (area, score key)
+  __shared__ float4 s_tile[kBlockThreads / 32][64];  // per warp and lane: matching box | (area, score key, -, -)
   const int lane = threadIdx.x & 31;
-  float4* const s_box = s_boxes[threadIdx.x >> 5];
-  float2* const s_aux = s_auxes[threadIdx.x >> 5];
+  float4* const s_rec = s_tile[threadIdx.x >> 5];
   const int warps_total = (gridDim.x * blockDim.x) >> 5;
   const int win = a.M <= 7 ? kWin : 1;
   const int nwin = (a.B + win - 1) / win;
@@ -279,58 +353,22 @@ __global__ void __launch_bounds__(kBlockThreads, 4) fuse_packed_kernel(const Fus
       }
       const unsigned skey = score_key(score);
       __syncwarp();  // the previous pack's readers are done with the tile
-      s_box[lane] = mbox;
-      s_aux[lane] = make_float2(area, __uint_as_float(skey));
+      s_rec[2 * lane] = mbox;
+      s_rec[2 * lane + 1] = make_float4(area, __uint_as_float(skey), 0.f, 0.f);
       __syncwarp();
 
-      // ---- all pairs of a segment, once each: in round r lane idx meets idx + r (mod n) and hands the verdict
-      //      back to it with one shuffle.  up = earlier-ranked lanes I match, higher = lanes ranked before me
-      //      (score desc; ties: higher lane first for the bayesian order, lower lane first for torchvision's
-      //      stable sort)
-      unsigned up = 0, higher = 0;
+      // ---- all pairs of a segment: in round r lane idx meets idx + r (mod n) and the verdicts travel back
+      //      through two ballots.  up = earlier-ranked lanes I match, higher = lanes ranked before me.
+      //      Borderline float32 decisions only raise a flag; a pack that saw one is redone with exact decisions.
+      unsigned up, higher;
       {
-        const int half = cluster ? (n >> 1) : 0;
-        const int rounds = __reduce_max_sync(kFullMask, half);
-        int pl = lane, ql = lane;
-        for (int r = 1; r <= rounds; ++r) {
-          pl = pl + 1 == hi ? lo : pl + 1;
-          ql = ql == lo ? hi - 1 : ql - 1;
-          const bool valid = r <= half;
-          const float4 pb = s_box[pl];
-          const float2 pa = s_aux[pl];
-          bool mt;
-          if (kNms) {
-            const float w = fmaxf(0.f, __fsub_rn(fminf(mbox.z, pb.z), fmaxf(mbox.x, pb.x)));
-            const float hh = fmaxf(0.f, __fsub_rn(fminf(mbox.w, pb.w), fmaxf(mbox.y, pb.y)));
-            const float inter = __fmul_rn(w, hh);
-            const float den = __fsub_rn(__fadd_rn(area, pa.x), inter);
-            const float d = fmaf(nthr, den, inter);
-            mt = d > 0.f;
-            if (!(fabsf(d) > 1e-5f * fabsf(den)) || !(den > 0.f)) mt = __fdiv_rn(inter, den) > a.thr;
-          } else {
-            // |error of w, hh| <= 2^-21 * cbound each (offset rounding + two float32 operations), so
-            // |error of inter - thr * uni| < ebound * (w + hh + 1) + 1e-5 * uni
-            const float w = fmaxf(fminf(mbox.z, pb.z) - fmaxf(mbox.x, pb.x), 0.f);
-            const float hh = fmaxf(fminf(mbox.w, pb.w) - fmaxf(mbox.y, pb.y), 0.f);
-            const float inter = w * hh;
-            const float uni = (area + pa.x) - inter;
-            const float d = fmaf(nthr, uni, inter);
-            const float tol = fmaf(ebound, w + hh, fmaf(1e-5f, uni, ebound));
-            mt = d > 0.f;
-            if (valid && !(fabsf(d) > tol))  // also taken when uni is NaN
-              mt = match_exact_f64(box, cls, __ldg(a.boxes + base + (pl - lo)), __ldg(a.classes + base + (pl - lo)),
-                                   a.img_w, a.img_h, a.thr);
-          }
-          const unsigned pk = __float_as_uint(pa.y);
-          const bool before = pk > skey || (pk == skey && (kNms ? pl < lane : pl > lane));
-          const unsigned res = mt ? (before ? 3u : 1u) : (before ? 2u : 0u);
-          const unsigned back = __shfl_sync(kFullMask, res, ql);
-          const unsigned pbit = valid ? 1u << pl : 0u, qbit = valid ? 1u << ql : 0u;
-          if (before) higher |= pbit;
-          if (res == 3u) up |= pbit;
-          if (!(back & 2u)) higher |= qbit;  // the partner ranks me after itself
-          if (back == 1u) up |= qbit;
-        }
+        const int rounds = __reduce_max_sync(kFullMask, cluster ? (n >> 1) : 0);
+        PairCtx c;
+        c.mbox = mbox; c.area = area; c.skey = skey; c.lane = lane; c.lo = lo; c.hi = hi; c.rounds = rounds;
+        c.nthr = nthr; c.thr = a.thr; c.ebound = ebound; c.rec = s_rec;
+        const bool unsure = pair_rounds<kNms, false>(c, a, box, cls, c0, up, higher);
+        if (__any_sync(kFullMask, unsure)) pair_rounds<kNms, true>(c, a, box, cls, c0, up, higher);
+        if (!cluster) up = 0u;
       }
 
       // ---- greedy clustering as a fixed point over the pair bits: a detection is a cluster head iff every
@@ -670,9 +708,9 @@ int launch_fuse(const FuseArgs& a, cudaStream_t st) {
   PE_CUDA_CHECK(cudaMemsetAsync(a.big_count, 0, sizeof(int), st));
   const int warps_per_block = kBlockThreads / 32;
   const int sms = sm_count();
-  // persistent-style grid: a multiple of the SM count, at most 8 resident blocks per SM worth of warps
+  // persistent grid: one wave of resident blocks (4 per SM at 64 registers), warps stride over the windows
   long long want = ceil_div<long long>(ceil_div<long long>(a.B, kWin), warps_per_block);
-  long long cap = (long long)sms * 8;
+  long long cap = (long long)sms * 4;
   int grid = (int)(want < cap ? (want > 0 ? want : 1) : cap);
   const bool nms = a.score_mode == PE_SCORE_MAX && a.box_mode == PE_BOX_ARGMAX;
   if (nms) fuse_packed_kernel<K, PE_SCORE_MAX, true><<<grid, kBlockThreads, 0, st>>>(a);
