@@ -160,7 +160,9 @@ class COCOBBoxEval:
         """The six numbers _derive_coco_results reports (x100), plus per-category AP."""
         res = {"AP": self._stat(), "AP50": self._stat(iou=.5), "AP75": self._stat(iou=.75),
                "APs": self._stat(area=1), "APm": self._stat(area=2), "APl": self._stat(area=3)}
-        res = {k: (v * 100 if v >= 0 else float("nan")) for k, v in res.items()}
+        # COCOeval reports -1 for an empty slice and _derive_coco_results multiplies it like any other value
+        # (FLIR_evaluation.py:274), so an empty area range reads -100; only the per-category AP becomes NaN (:296)
+        res = {k: v * 100 for k, v in res.items()}
         for ci, cat in enumerate(self.cat_ids):
             v = self._stat(cat=ci)
             res["AP-%s" % cat] = v * 100 if v >= 0 else float("nan")

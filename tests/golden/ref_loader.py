@@ -272,3 +272,42 @@ def load_reference_detector_modules():
             del sys.modules[k]
         sys.modules.update(saved)
     return _DET
+
+
+def load_reference_cocoeval():
+    """Returns (COCO, COCOeval) of the reference's vendored detectron2/pycocotools (coco.py, cocoeval.py loaded by
+    path).  Stubs: matplotlib (plotting only), and ``pycocotools._mask`` whose one function used by the bbox
+    protocol, ``iou``, is the published maskApi.c ``bbIou`` restated in numpy (the Cython extension is not built
+    in this image).  numpy >= 1.24 dropped the ``np.float`` alias cocoeval.py:379 uses; it is restored as float."""
+    import numpy as np
+    if not hasattr(np, "float"):
+        np.float = float
+
+    def bb_iou(dt, gt, iscrowd):
+        dt = np.asarray(dt, np.float64).reshape(-1, 4)
+        gt = np.asarray(gt, np.float64).reshape(-1, 4)
+        out = np.zeros((len(dt), len(gt)))
+        for g in range(len(gt)):
+            ga = gt[g, 2] * gt[g, 3]
+            for d in range(len(dt)):
+                da = dt[d, 2] * dt[d, 3]
+                w = min(dt[d, 2] + dt[d, 0], gt[g, 2] + gt[g, 0]) - max(dt[d, 0], gt[g, 0])
+                if w <= 0:
+                    continue
+                h = min(dt[d, 3] + dt[d, 1], gt[g, 3] + gt[g, 1]) - max(dt[d, 1], gt[g, 1])
+                if h <= 0:
+                    continue
+                i = w * h
+                out[d, g] = i / (da if iscrowd[g] else da + ga - i)
+        return out
+
+    for name in ("matplotlib", "matplotlib.pyplot", "matplotlib.collections", "matplotlib.patches"):
+        if name not in sys.modules:
+            _stub(name, PatchCollection=None, Polygon=None)
+    _stub("pycocotools")
+    _stub("pycocotools._mask", iou=bb_iou, merge=None, frPyObjects=None)  # masks are never touched for bbox
+    _stub("_ref_pycocotools")
+    _load("_ref_pycocotools.mask", "detectron2/pycocotools/mask.py")
+    coco = _load("_ref_pycocotools.coco", "detectron2/pycocotools/coco.py")
+    cocoeval = _load("_ref_pycocotools.cocoeval", "detectron2/pycocotools/cocoeval.py")
+    return coco.COCO, cocoeval.COCOeval
