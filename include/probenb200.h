@@ -192,6 +192,27 @@ PE_API int pe_head_postprocess(const float* head_out, int npad, const float* pro
                                float score_thresh, float nms_thresh, int detections_per_image,
                                const pe_detections* out, void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Operator seams of detectron2/layers, for callers written against the reference's ops.
+ *
+ * pe_batched_nms: detectron2/layers/nms.py:9-26 batched_nms -> torchvision.ops.boxes.batched_nms.  boxes [n,4]
+ *   xyxy float32 (16-byte aligned), scores [n], idxs [n] int64 category ids (NULL = plain torchvision.ops.nms).
+ *   mode 0 = torchvision's coordinate-offset trick (boxes + float(idx) * (max coordinate + 1) in float32, the
+ *   path the reference takes for <= 20000 box elements on CUDA), mode 1 = suppression inside a category only
+ *   (_batched_nms_vanilla, and the reference's own loop for >= 40000 boxes).  keep [n] int64 receives the kept
+ *   ORIGINAL indices in descending score order (ties: lower index first), *n_keep their number.
+ * pe_roi_align_forward: detectron2._C.roi_align_forward (layers/csrc/vision.cpp:89, ROIAlign/ROIAlign.h:54-84,
+ *   ROIAlign_cuda.cu:65-139).  input [N,C,H,W] float32, rois [num_rois,5] = (batch index, x1, y1, x2, y2),
+ *   out [num_rois, C, pooled_h, pooled_w] float32 (caller-allocated; the reference op allocates it itself).
+ */
+PE_API size_t pe_batched_nms_workspace_bytes(int n);
+PE_API int pe_batched_nms_max_boxes(void);
+PE_API int pe_batched_nms(const float* boxes, const float* scores, const int64_t* idxs, int n, float iou_thr, int mode,
+                          int64_t* keep, int32_t* n_keep, void* workspace, size_t workspace_bytes, void* stream);
+PE_API int pe_roi_align_forward(const float* input, int N, int C, int H, int W, const float* rois, int num_rois,
+                                float spatial_scale, int pooled_h, int pooled_w, int sampling_ratio, int aligned,
+                                float* out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -79,6 +79,14 @@ SIGNATURES.update({
                             [ctypes.POINTER(Detections), c_void_p]),
 })
 
+SIGNATURES.update({
+    "pe_batched_nms_workspace_bytes": (c_size_t, [c_int]),
+    "pe_batched_nms_max_boxes": (c_int, []),
+    "pe_batched_nms": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_float, c_int, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
+    "pe_roi_align_forward": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_int, c_float, c_int, c_int, c_int, c_int,
+                                     c_void_p, c_void_p]),
+})
+
 _lib = None
 
 
