@@ -33,7 +33,7 @@ __device__ __forceinline__ bool finite4(float4 b) { return isfinite(b.x) && isfi
 // One bilinear sample of DefaultPredictor's resize (half-pixel centres).  Written with explicit round-to-nearest
 // intrinsics so that every kernel that resizes (stand-alone or fused into the stem staging) produces the same bits.
 __device__ __forceinline__ float resize_sample(const unsigned char* __restrict__ im, int Hs, int Ws, int C, int c, int y, int x,
-                                               float sy, float sx, int round_u8) {
+                                               float sy, float sx) {
   const float fy = __fsub_rn(__fmul_rn(__fadd_rn((float)y, 0.5f), sy), 0.5f);
   const float fx = __fsub_rn(__fmul_rn(__fadd_rn((float)x, 0.5f), sx), 0.5f);
   int y0 = (int)floorf(fy), x0 = (int)floorf(fx);
@@ -49,8 +49,94 @@ __device__ __forceinline__ float resize_sample(const unsigned char* __restrict__
   const float top = __fadd_rn(__fmul_rn(hx, v00), __fmul_rn(lx, v01));
   const float bot = __fadd_rn(__fmul_rn(hx, v10), __fmul_rn(lx, v11));
   float v = __fadd_rn(__fmul_rn(hy, top), __fmul_rn(ly, bot));
-  if (round_u8) v = fminf(fmaxf(rintf(v), 0.f), 255.f);
   return v;
+}
+
+// Pillow's BILINEAR resize of 8-bit images, bit for bit (the path DefaultPredictor takes for 3-channel uint8 frames:
+// data/transforms/transform.py:92-96 -> Image.resize).  Pillow (libImaging/Resample.c, ImagingResample with the
+// bilinear filter: precompute_coeffs, normalize_coeffs_8bpc, ImagingResampleHorizontal_8bpc, ...Vertical_8bpc; the
+// reference environment pins Pillow 9.2) filters in two passes - rows first, then columns - with double-precision
+// triangle weights normalised to sum 1, converted to 22-bit fixed point, and a rounded uint8 intermediate image.
+// The weights of one output coordinate are recomputed here in double with the library's exact operation order.
+constexpr int kPilPrecisionBits = 32 - 8 - 2;
+
+template <int KMAX>
+struct PilTaps {
+  int lo, n;
+  int k[KMAX];
+};
+
+template <int KMAX>
+__device__ __forceinline__ PilTaps<KMAX> pil_taps(int xx, int in_size, int out_size) {
+  PilTaps<KMAX> t;
+  const double scale = (double)((float)in_size - 0.f) / (double)out_size;
+  const double filterscale = scale < 1.0 ? 1.0 : scale;
+  const double support = filterscale;  // bilinear support 1.0 * filterscale
+  const double center = __dadd_rn(0.0, __dmul_rn(__dadd_rn((double)xx, 0.5), scale));
+  const double ss = __ddiv_rn(1.0, filterscale);
+  int xmin = (int)__dadd_rn(__dsub_rn(center, support), 0.5);
+  if (xmin < 0) xmin = 0;
+  int xmax = (int)__dadd_rn(__dadd_rn(center, support), 0.5);
+  if (xmax > in_size) xmax = in_size;
+  xmax -= xmin;
+  if (xmax > KMAX) xmax = KMAX;  // cannot happen for scale <= (KMAX - 1) / 2, which the launcher checks
+  double w[KMAX];
+  double ww = 0.0;
+#pragma unroll
+  for (int x = 0; x < KMAX; ++x) {
+    double v = 0.0;
+    if (x < xmax) {
+      double a = __dmul_rn(__dadd_rn(__dsub_rn((double)(x + xmin), center), 0.5), ss);
+      if (a < 0.0) a = -a;
+      v = a < 1.0 ? __dsub_rn(1.0, a) : 0.0;
+      ww = __dadd_rn(ww, v);
+    }
+    w[x] = v;
+  }
+#pragma unroll
+  for (int x = 0; x < KMAX; ++x) {
+    double v = w[x];
+    if (x < xmax && ww != 0.0) v = __ddiv_rn(v, ww);
+    t.k[x] = x < xmax ? (int)__dadd_rn(0.5, __dmul_rn(v, (double)(1 << kPilPrecisionBits))) : 0;
+  }
+  t.lo = xmin;
+  t.n = xmax;
+  return t;
+}
+
+__device__ __forceinline__ int pil_clip8(int v) {
+  v >>= kPilPrecisionBits;
+  return v < 0 ? 0 : (v > 255 ? 255 : v);
+}
+
+// All C (<= 4) channels c0.. of one output pixel.
+template <int KMAX>
+__device__ __forceinline__ void pil_resize_pixel(const unsigned char* __restrict__ im, int Ws, int Ctot, int c0, int C,
+                                                 const PilTaps<KMAX>& ty, const PilTaps<KMAX>& tx, int out[4]) {
+  int acc[4];
+#pragma unroll
+  for (int c = 0; c < 4; ++c) acc[c] = 1 << (kPilPrecisionBits - 1);
+#pragma unroll
+  for (int j = 0; j < KMAX; ++j) {
+    if (j < ty.n) {
+      const unsigned char* rowp = im + ((size_t)(ty.lo + j) * Ws + tx.lo) * Ctot + c0;
+      int h[4];
+#pragma unroll
+      for (int c = 0; c < 4; ++c) h[c] = 1 << (kPilPrecisionBits - 1);
+#pragma unroll
+      for (int i = 0; i < KMAX; ++i) {
+        if (i < tx.n) {
+#pragma unroll
+          for (int c = 0; c < 4; ++c)
+            if (c < C) h[c] += (int)rowp[(size_t)i * Ctot + c] * tx.k[i];
+        }
+      }
+#pragma unroll
+      for (int c = 0; c < 4; ++c) acc[c] += pil_clip8(h[c]) * ty.k[j];
+    }
+  }
+#pragma unroll
+  for (int c = 0; c < 4; ++c) out[c] = pil_clip8(acc[c]);
 }
 
 // ---------------------------------------------------------------------------------------------- stem im2col
@@ -78,8 +164,9 @@ __global__ void stem_canvas_kernel(const float* __restrict__ img, __half* __rest
 
 // Stage 1': the same canvas straight from raw uint8 HWC frames: bilinear resize (resize_frames_kernel's arithmetic, i.e.
 // DefaultPredictor's ResizeShortestEdge) + normalisation fused, so the float32 network input never exists in HBM.
+template <int KMAX>  // KMAX > 0: Pillow-exact uint8 resize (round_u8), KMAX = 0: float32 bilinear
 __global__ void stem_canvas_u8_kernel(const unsigned char* __restrict__ frames, __half* __restrict__ canvas, int B, int Ctot, int c0,
-                                      int C, int Hs, int Ws, int Hi, int Wi, int Hp, int Wp, int round_u8, StemNorm nrm) {
+                                      int C, int Hs, int Ws, int Hi, int Wi, int Hp, int Wp, StemNorm nrm) {
   const long long total = (long long)B * Hp * Wp;
   const float sy = (float)Hs / (float)Hi, sx = (float)Ws / (float)Wi;
   for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
@@ -90,11 +177,23 @@ __global__ void stem_canvas_u8_kernel(const unsigned char* __restrict__ frames, 
     __align__(8) __half v[4];
     const bool inside = y >= 0 && y < Hi && x >= 0 && x < Wi;
     const unsigned char* im = frames + (size_t)b * Hs * Ws * Ctot;
+    if (KMAX > 0) {
+      int px[4] = {0, 0, 0, 0};
+      if (inside) {
+        constexpr int KM = KMAX > 0 ? KMAX : 1;
+        const PilTaps<KM> ty = pil_taps<KM>(y, Hs, Hi), tx = pil_taps<KM>(x, Ws, Wi);
+        pil_resize_pixel<KM>(im, Ws, Ctot, c0, C, ty, tx, px);
+      }
 #pragma unroll
-    for (int c = 0; c < 4; ++c) {
-      float val = 0.f;
-      if (c < C && inside) val = __fdiv_rn(resize_sample(im, Hs, Ws, Ctot, c0 + c, y, x, sy, sx, round_u8) - nrm.mean[c], nrm.std[c]);
-      v[c] = __float2half_rn(val);
+      for (int c = 0; c < 4; ++c)
+        v[c] = __float2half_rn((c < C && inside) ? __fdiv_rn((float)px[c] - nrm.mean[c], nrm.std[c]) : 0.f);
+    } else {
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        float val = 0.f;
+        if (c < C && inside) val = __fdiv_rn(resize_sample(im, Hs, Ws, Ctot, c0 + c, y, x, sy, sx) - nrm.mean[c], nrm.std[c]);
+        v[c] = __float2half_rn(val);
+      }
     }
     *reinterpret_cast<uint2*>(canvas + (size_t)t * 4) = *reinterpret_cast<const uint2*>(v);
   }
@@ -120,17 +219,35 @@ __global__ void stem_im2col_kernel(const __half* __restrict__ canvas, __half* __
 // DefaultPredictor's ResizeShortestEdge (engine/defaults.py:186-190, data/transforms/transform.py:81-99): bilinear with
 // half-pixel centres (cv2.INTER_LINEAR / PIL BILINEAR geometry), uint8 HWC frames -> float32 CHW network input.
 // round_u8 reproduces the uint8 output quantisation of the PIL path used for 3-channel uint8 images.
+template <int KMAX>
 __global__ void resize_frames_kernel(const unsigned char* __restrict__ src, float* __restrict__ dst, int B, int C, int Hs, int Ws,
-                                     int Hd, int Wd, int round_u8) {
-  const long long total = (long long)B * C * Hd * Wd;
+                                     int Hd, int Wd) {
   const float sy = (float)Hs / (float)Hd, sx = (float)Ws / (float)Wd;
+  if (KMAX > 0) {  // one thread per output pixel, channels in groups of 4
+    constexpr int KM = KMAX > 0 ? KMAX : 1;
+    const long long total = (long long)B * Hd * Wd;
+    for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
+      const int x = (int)(t % Wd);
+      const long long r = t / Wd;
+      const int y = (int)(r % Hd), b = (int)(r / Hd);
+      const PilTaps<KM> ty = pil_taps<KM>(y, Hs, Hd), tx = pil_taps<KM>(x, Ws, Wd);
+      for (int c0 = 0; c0 < C; c0 += 4) {
+        int px[4];
+        const int cn = min(4, C - c0);
+        pil_resize_pixel<KM>(src + (size_t)b * Hs * Ws * C, Ws, C, c0, cn, ty, tx, px);
+        for (int c = 0; c < cn; ++c) dst[(((size_t)b * C + c0 + c) * Hd + y) * Wd + x] = (float)px[c];
+      }
+    }
+    return;
+  }
+  const long long total = (long long)B * C * Hd * Wd;
   for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
     const int x = (int)(t % Wd);
     long long r = t / Wd;
     const int y = (int)(r % Hd);
     r /= Hd;
     const int c = (int)(r % C), b = (int)(r / C);
-    dst[t] = resize_sample(src + (size_t)b * Hs * Ws * C, Hs, Ws, C, c, y, x, sy, sx, round_u8);
+    dst[t] = resize_sample(src + (size_t)b * Hs * Ws * C, Hs, Ws, C, c, y, x, sy, sx);
   }
 }
 
@@ -980,12 +1097,23 @@ int launch_stem_im2col(const float* img, void* canvas, void* A, int B, int Ctot,
   return PE_OK;
 }
 
+// Taps per output coordinate of the Pillow-exact resize: 3 cover any upscale, 9 a downscale by up to 4x.
+static int pil_kmax(int Hs, int Ws, int Hd, int Wd) {
+  const double s = fmax((double)Hs / Hd, (double)Ws / Wd);
+  return s <= 1.0 ? 3 : (s <= 4.0 ? 9 : -1);
+}
+
 int launch_stem_im2col_u8(const unsigned char* frames, void* canvas, void* A, int B, int Ctot, int c0, int C, int Hs, int Ws, int Hi,
                           int Wi, int Hc, int Wc, int round_u8, const StemNorm& nrm, cudaStream_t st) {
   if (C > 4) return PE_ERR_UNSUPPORTED;
   const int Ho = Hc / 2, Wo = Wc / 2, Hp = Hc + 6, Wp = Wc + 8;
-  stem_canvas_u8_kernel<<<grid_for((long long)B * Hp * Wp, 256), 256, 0, st>>>(frames, reinterpret_cast<__half*>(canvas), B, Ctot, c0, C, Hs,
-                                                                                 Ws, Hi, Wi, Hp, Wp, round_u8, nrm);
+  const int kmax = round_u8 ? pil_kmax(Hs, Ws, Hi, Wi) : 0;
+  if (kmax < 0) return PE_ERR_UNSUPPORTED;
+  const int grid = grid_for((long long)B * Hp * Wp, 256);
+  __half* cv = reinterpret_cast<__half*>(canvas);
+  if (kmax == 0) stem_canvas_u8_kernel<0><<<grid, 256, 0, st>>>(frames, cv, B, Ctot, c0, C, Hs, Ws, Hi, Wi, Hp, Wp, nrm);
+  else if (kmax == 3) stem_canvas_u8_kernel<3><<<grid, 256, 0, st>>>(frames, cv, B, Ctot, c0, C, Hs, Ws, Hi, Wi, Hp, Wp, nrm);
+  else stem_canvas_u8_kernel<9><<<grid, 256, 0, st>>>(frames, cv, B, Ctot, c0, C, Hs, Ws, Hi, Wi, Hp, Wp, nrm);
   PE_LAUNCH_CHECK();
   if (A) {  // optional explicit im2col matrix (kept for the op-level GEMM tests; the engine reads the canvas through TMA)
     const long long total = (long long)B * Ho * Wo * 28;
@@ -998,8 +1126,13 @@ int launch_stem_im2col_u8(const unsigned char* frames, void* canvas, void* A, in
 
 int launch_resize_frames(const unsigned char* src, float* dst, int B, int C, int Hs, int Ws, int Hd, int Wd, int round_u8,
                          cudaStream_t st) {
-  const long long total = (long long)B * C * Hd * Wd;
-  resize_frames_kernel<<<grid_for(total, 256), 256, 0, st>>>(src, dst, B, C, Hs, Ws, Hd, Wd, round_u8);
+  const int kmax = round_u8 ? pil_kmax(Hs, Ws, Hd, Wd) : 0;
+  if (kmax < 0) return PE_ERR_UNSUPPORTED;
+  const long long total = (long long)B * (kmax ? 1 : C) * Hd * Wd;
+  const int grid = grid_for(total, 256);
+  if (kmax == 0) resize_frames_kernel<0><<<grid, 256, 0, st>>>(src, dst, B, C, Hs, Ws, Hd, Wd);
+  else if (kmax == 3) resize_frames_kernel<3><<<grid, 256, 0, st>>>(src, dst, B, C, Hs, Ws, Hd, Wd);
+  else resize_frames_kernel<9><<<grid, 256, 0, st>>>(src, dst, B, C, Hs, Ws, Hd, Wd);
   PE_LAUNCH_CHECK();
   return PE_OK;
 }

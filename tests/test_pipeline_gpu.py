@@ -13,13 +13,31 @@ pytestmark = pytest.mark.gpu
 
 
 def test_resize_matches_torch_bilinear():
+    """4-/6-channel frames: plain float32 bilinear with half-pixel centres (cv2.resize INTER_LINEAR geometry,
+    data/transforms/transform.py:82-90); tolerance 1e-3 grey levels."""
     g = torch.Generator().manual_seed(0)
-    u8 = torch.randint(0, 256, (2, 64, 80, 3), dtype=torch.uint8, generator=g)
+    u8 = torch.randint(0, 256, (2, 64, 80, 4), dtype=torch.uint8, generator=g)
     got = ops.resize_frames(u8.cuda(), (100, 125), round_u8=False).cpu()
     want = torch.nn.functional.interpolate(u8.permute(0, 3, 1, 2).float(), size=(100, 125), mode="bilinear", align_corners=False)
     assert float((got - want).abs().max()) < 1e-3
-    got8 = ops.resize_frames(u8.cuda(), (100, 125), round_u8=True).cpu()
-    assert float((got8 - want.round().clamp(0, 255)).abs().max()) <= 1.0  # rounding ties may differ by one level
+
+
+@pytest.mark.parametrize("src,dst,C", [((64, 80), (100, 125), 3), ((512, 640), (800, 1000), 3), ((120, 90), (45, 77), 3),
+                                       ((50, 64), (13, 16), 3), ((37, 53), (91, 60), 1), ((40, 48), (64, 77), 6)])
+def test_resize_u8_is_pillow_exact(src, dst, C):
+    """3-channel uint8 frames go through PIL.Image.resize(BILINEAR) in the reference (transform.py:92-96): the kernel
+    must reproduce Pillow's fixed-point two-pass filter bit for bit (oracle/resize_oracle.py, pinned to Pillow)."""
+    from oracle import resize_oracle as R
+    rng = np.random.default_rng(src[0] + dst[1] + C)
+    img = rng.integers(0, 256, (2, src[0], src[1], C), dtype=np.uint8)
+    got = ops.resize_frames(torch.from_numpy(img).cuda(), dst, round_u8=True).cpu().numpy()
+    for b in range(2):
+        want = R.pil_bilinear_resize_u8(img[b], dst[0], dst[1]).transpose(2, 0, 1).astype(np.float32)
+        assert np.array_equal(got[b], want)
+    if C == 3:
+        from PIL import Image
+        pil = np.asarray(Image.fromarray(img[0]).resize((dst[1], dst[0]), Image.BILINEAR)).transpose(2, 0, 1)
+        assert np.array_equal(got[0], pil.astype(np.float32))
 
 
 def test_pipeline_fusion_equals_oracle_on_gpu_detections():
