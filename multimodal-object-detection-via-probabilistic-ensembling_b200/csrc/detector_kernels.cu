@@ -164,9 +164,25 @@ __global__ void stem_canvas_kernel(const float* __restrict__ img, __half* __rest
 
 // Stage 1': the same canvas straight from raw uint8 HWC frames: bilinear resize (resize_frames_kernel's arithmetic, i.e.
 // DefaultPredictor's ResizeShortestEdge) + normalisation fused, so the float32 network input never exists in HBM.
+// Upscales need at most 3 taps per axis: the engine tabulates them once per forward (row table [Hi] then column table
+// [Wi], int4 = first source index, three 22-bit weights) so that the per-pixel work is integer only.
+__global__ void pil_taps_table_kernel(int4* __restrict__ table, int Hs, int Ws, int Hi, int Wi) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= Hi + Wi) return;
+  const PilTaps<3> tp = t < Hi ? pil_taps<3>(t, Hs, Hi) : pil_taps<3>(t - Hi, Ws, Wi);
+  table[t] = make_int4(tp.lo | (tp.n << 24), tp.k[0], tp.k[1], tp.k[2]);
+}
+
+__device__ __forceinline__ PilTaps<3> pil_taps_from_table(int4 e) {
+  PilTaps<3> t;
+  t.lo = e.x & 0xffffff; t.n = e.x >> 24; t.k[0] = e.y; t.k[1] = e.z; t.k[2] = e.w;
+  return t;
+}
+
 template <int KMAX>  // KMAX > 0: Pillow-exact uint8 resize (round_u8), KMAX = 0: float32 bilinear
 __global__ void stem_canvas_u8_kernel(const unsigned char* __restrict__ frames, __half* __restrict__ canvas, int B, int Ctot, int c0,
-                                      int C, int Hs, int Ws, int Hi, int Wi, int Hp, int Wp, StemNorm nrm) {
+                                      int C, int Hs, int Ws, int Hi, int Wi, int Hp, int Wp, StemNorm nrm,
+                                      const int4* __restrict__ taps) {
   const long long total = (long long)B * Hp * Wp;
   const float sy = (float)Hs / (float)Hi, sx = (float)Ws / (float)Wi;
   for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
@@ -181,8 +197,13 @@ __global__ void stem_canvas_u8_kernel(const unsigned char* __restrict__ frames, 
       int px[4] = {0, 0, 0, 0};
       if (inside) {
         constexpr int KM = KMAX > 0 ? KMAX : 1;
-        const PilTaps<KM> ty = pil_taps<KM>(y, Hs, Hi), tx = pil_taps<KM>(x, Ws, Wi);
-        pil_resize_pixel<KM>(im, Ws, Ctot, c0, C, ty, tx, px);
+        if (KMAX == 3 && taps) {
+          const PilTaps<3> ty = pil_taps_from_table(__ldg(taps + y)), tx = pil_taps_from_table(__ldg(taps + Hi + x));
+          pil_resize_pixel<3>(im, Ws, Ctot, c0, C, ty, tx, px);
+        } else {
+          const PilTaps<KM> ty = pil_taps<KM>(y, Hs, Hi), tx = pil_taps<KM>(x, Ws, Wi);
+          pil_resize_pixel<KM>(im, Ws, Ctot, c0, C, ty, tx, px);
+        }
       }
 #pragma unroll
       for (int c = 0; c < 4; ++c)
@@ -680,13 +701,13 @@ __device__ __forceinline__ AxisSample axis_sample(float start, float bin, int p,
 // evaluated in its separable form  sum_rows sum_cols Wy[row] * Wx[col] * f(row, col)  with per-pixel weights
 // Wy/Wx accumulated from the reference's per-sample terms: every touched feature pixel is loaded once per bin
 // instead of once per neighbouring sample (up to 4x fewer 128-bit loads).
-__global__ void __launch_bounds__(224) roi_align_kernel(const RoiLevels fl, const float4* __restrict__ props, const int* __restrict__ prop_count,
+__global__ void __launch_bounds__(224, 3) roi_align_kernel(const RoiLevels fl, const float4* __restrict__ props, const int* __restrict__ prop_count,
                                                         int B, int max_props, int C, __nv_bfloat16* __restrict__ out) {
   __shared__ float s_wx[7][kRoiGmax + 2];
   __shared__ int s_x0[7], s_nx[7];
   const int lane = threadIdx.x & 31, ph = threadIdx.x >> 5;
-  const long long roi = blockIdx.x;
-  const int b = (int)(roi / max_props), r = (int)(roi % max_props);
+  const int b = blockIdx.y, r = blockIdx.x;  // grid (max_props, B)
+  const long long roi = (long long)b * max_props + r;
   const int cgroups = C >> 3;
   uint4* dst_roi = reinterpret_cast<uint4*>(out + (size_t)roi * 49 * C);
   if (r >= prop_count[b]) {
@@ -751,23 +772,52 @@ __global__ void __launch_bounds__(224) roi_align_kernel(const RoiLevels fl, cons
     for (int pw = 0; pw < 6; ++pw) sweep &= s_x0[pw + 1] >= s_x0[pw] && s_x0[pw + 1] + s_nx[pw + 1] >= s_x0[pw] + s_nx[pw];
     if (sweep) {
       const float inv_count = 1.f / count;
+      // row weights to registers once; with <= 4 rows (the usual case: ROIs span 7..14 pixels at their level) the rows of
+      // the NEXT column are requested before the current column is reduced, so 4..8 128-bit loads are in flight per lane
+      constexpr int kPre = 4;
+      float wyr[kPre];
+#pragma unroll
+      for (int rr = 0; rr < kPre; ++rr) wyr[rr] = rr < ny ? __shfl_sync(kFullMask, wy, rr) : 0.f;
+      const bool pipelined = ny <= kPre;
       for (int g = lane; g < cgroups; g += 32) {
         float cur[8], nxt[8];
 #pragma unroll
         for (int j = 0; j < 8; ++j) { cur[j] = 0.f; nxt[j] = 0.f; }
         int pw = 0;
         const int xe = s_x0[6] + s_nx[6] - 1;
+        const uint4* col0 = reinterpret_cast<const uint4*>(feat + (size_t)y0 * W * C) + g;
+        const size_t row_stride = (size_t)W * cgroups, col_stride = (size_t)cgroups;
+        uint4 pre[kPre];
+        auto fetch = [&](int x) {
+#pragma unroll
+          for (int rr = 0; rr < kPre; ++rr)
+            pre[rr] = (rr < ny && wyr[rr] != 0.f) ? __ldg(col0 + (size_t)rr * row_stride + (size_t)x * col_stride) : make_uint4(0, 0, 0, 0);
+        };
+        if (pipelined) fetch(s_x0[0]);
         for (int x = s_x0[0]; x <= xe && pw < 7; ++x) {
           float t[8];
 #pragma unroll
           for (int j = 0; j < 8; ++j) t[j] = 0.f;
-          const __nv_bfloat16* colp = feat + ((size_t)y0 * W + x) * C;
-          for (int rr = 0; rr < ny; ++rr) {
-            const float wyr = __shfl_sync(kFullMask, wy, rr);
-            if (wyr == 0.f) continue;
-            const uint4 v = __ldg(reinterpret_cast<const uint4*>(colp + (size_t)rr * W * C) + g);
-            t[0] += wyr * bflo(v.x); t[1] += wyr * bfhi(v.x); t[2] += wyr * bflo(v.y); t[3] += wyr * bfhi(v.y);
-            t[4] += wyr * bflo(v.z); t[5] += wyr * bfhi(v.z); t[6] += wyr * bflo(v.w); t[7] += wyr * bfhi(v.w);
+          if (pipelined) {
+            uint4 v[kPre];
+#pragma unroll
+            for (int rr = 0; rr < kPre; ++rr) v[rr] = pre[rr];
+            if (x < xe) fetch(x + 1);
+#pragma unroll
+            for (int rr = 0; rr < kPre; ++rr) {
+              const float w = wyr[rr];
+              t[0] += w * bflo(v[rr].x); t[1] += w * bfhi(v[rr].x); t[2] += w * bflo(v[rr].y); t[3] += w * bfhi(v[rr].y);
+              t[4] += w * bflo(v[rr].z); t[5] += w * bfhi(v[rr].z); t[6] += w * bflo(v[rr].w); t[7] += w * bfhi(v[rr].w);
+            }
+          } else {
+            const __nv_bfloat16* colp = feat + ((size_t)y0 * W + x) * C;
+            for (int rr = 0; rr < ny; ++rr) {
+              const float w = __shfl_sync(kFullMask, wy, rr);
+              if (w == 0.f) continue;
+              const uint4 v = __ldg(reinterpret_cast<const uint4*>(colp + (size_t)rr * W * C) + g);
+              t[0] += w * bflo(v.x); t[1] += w * bfhi(v.x); t[2] += w * bflo(v.y); t[3] += w * bfhi(v.y);
+              t[4] += w * bflo(v.z); t[5] += w * bfhi(v.z); t[6] += w * bflo(v.w); t[7] += w * bfhi(v.w);
+            }
           }
           const int c0 = x - s_x0[pw];
           if (c0 >= 0 && c0 < s_nx[pw]) {
@@ -795,28 +845,70 @@ __global__ void __launch_bounds__(224) roi_align_kernel(const RoiLevels fl, cons
       }
       return;
     }
-    for (int g = lane; g < cgroups; g += 32) {
-      for (int pw = 0; pw < 7; ++pw) {
-        const int x0 = s_x0[pw], nx = s_nx[pw];
-        float acc[8];
+    // Small ROIs (bins narrower than a pixel: a column may lie in up to all 7 bins of the row): same column sweep
+    // with one accumulator set per bin.  Each pixel of the bin row's window is still loaded exactly once.
+    {
+      const float inv_count = 1.f / count;
+      int bx0[7], bnx[7];
+      int xs = 0x7fffffff, xe = -1;
 #pragma unroll
-        for (int j = 0; j < 8; ++j) acc[j] = 0.f;
-        for (int rr = 0; rr < ny; ++rr) {
-          const float wyr = __shfl_sync(kFullMask, wy, rr);
-          if (wyr == 0.f) continue;
-          const __nv_bfloat16* rowp = feat + ((size_t)(y0 + rr) * W + x0) * C;
-          for (int cc = 0; cc < nx; ++cc) {
-            const float w = wyr * s_wx[pw][cc];
-            if (w == 0.f) continue;
-            const uint4 v = __ldg(reinterpret_cast<const uint4*>(rowp + (size_t)cc * C) + g);
-            acc[0] += w * bflo(v.x); acc[1] += w * bfhi(v.x); acc[2] += w * bflo(v.y); acc[3] += w * bfhi(v.y);
-            acc[4] += w * bflo(v.z); acc[5] += w * bfhi(v.z); acc[6] += w * bflo(v.w); acc[7] += w * bfhi(v.w);
+      for (int pw = 0; pw < 7; ++pw) {
+        bx0[pw] = s_x0[pw]; bnx[pw] = s_nx[pw];
+        xs = min(xs, bx0[pw]); xe = max(xe, bx0[pw] + bnx[pw] - 1);
+      }
+      constexpr int kPre7 = 3;
+      float wy7[kPre7];
+#pragma unroll
+      for (int rr = 0; rr < kPre7; ++rr) wy7[rr] = rr < ny ? __shfl_sync(kFullMask, wy, rr) : 0.f;
+      const bool few_rows = ny <= kPre7;
+      for (int g = lane; g < cgroups; g += 32) {
+        float acc[7][8];
+#pragma unroll
+        for (int pw = 0; pw < 7; ++pw)
+#pragma unroll
+          for (int j = 0; j < 8; ++j) acc[pw][j] = 0.f;
+        const uint4* col0 = reinterpret_cast<const uint4*>(feat + (size_t)y0 * W * C) + g;
+        const size_t row_stride = (size_t)W * cgroups;
+        for (int x = xs; x <= xe; ++x) {
+          float t[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) t[j] = 0.f;
+          const uint4* colp = col0 + (size_t)x * cgroups;
+          if (few_rows) {  // block-uniform: all rows of the column requested at once
+            uint4 v[kPre7];
+#pragma unroll
+            for (int rr = 0; rr < kPre7; ++rr)
+              v[rr] = (rr < ny && wy7[rr] != 0.f) ? __ldg(colp + (size_t)rr * row_stride) : make_uint4(0, 0, 0, 0);
+#pragma unroll
+            for (int rr = 0; rr < kPre7; ++rr) {
+              const float w = wy7[rr];
+              t[0] += w * bflo(v[rr].x); t[1] += w * bfhi(v[rr].x); t[2] += w * bflo(v[rr].y); t[3] += w * bfhi(v[rr].y);
+              t[4] += w * bflo(v[rr].z); t[5] += w * bfhi(v[rr].z); t[6] += w * bflo(v[rr].w); t[7] += w * bfhi(v[rr].w);
+            }
+          } else {
+            for (int rr = 0; rr < ny; ++rr) {
+              const float w = __shfl_sync(kFullMask, wy, rr);
+              if (w == 0.f) continue;
+              const uint4 v = __ldg(colp + (size_t)rr * row_stride);
+              t[0] += w * bflo(v.x); t[1] += w * bfhi(v.x); t[2] += w * bflo(v.y); t[3] += w * bfhi(v.y);
+              t[4] += w * bflo(v.z); t[5] += w * bfhi(v.z); t[6] += w * bflo(v.w); t[7] += w * bfhi(v.w);
+            }
+          }
+#pragma unroll
+          for (int pw = 0; pw < 7; ++pw) {
+            const int c = x - bx0[pw];
+            if (c >= 0 && c < bnx[pw]) {
+              const float w = s_wx[pw][c];
+#pragma unroll
+              for (int j = 0; j < 8; ++j) acc[pw][j] += w * t[j];
+            }
           }
         }
 #pragma unroll
-        for (int j = 0; j < 8; ++j) acc[j] /= count;
-        dst_roi[(size_t)(ph * 7 + pw) * cgroups + g] =
-            make_uint4(packbf(acc[0], acc[1]), packbf(acc[2], acc[3]), packbf(acc[4], acc[5]), packbf(acc[6], acc[7]));
+        for (int pw = 0; pw < 7; ++pw)
+          dst_roi[(size_t)(ph * 7 + pw) * cgroups + g] =
+              make_uint4(packbf(acc[pw][0] * inv_count, acc[pw][1] * inv_count), packbf(acc[pw][2] * inv_count, acc[pw][3] * inv_count),
+                         packbf(acc[pw][4] * inv_count, acc[pw][5] * inv_count), packbf(acc[pw][6] * inv_count, acc[pw][7] * inv_count));
       }
     }
     return;
@@ -1104,16 +1196,21 @@ static int pil_kmax(int Hs, int Ws, int Hd, int Wd) {
 }
 
 int launch_stem_im2col_u8(const unsigned char* frames, void* canvas, void* A, int B, int Ctot, int c0, int C, int Hs, int Ws, int Hi,
-                          int Wi, int Hc, int Wc, int round_u8, const StemNorm& nrm, cudaStream_t st) {
+                          int Wi, int Hc, int Wc, int round_u8, const StemNorm& nrm, cudaStream_t st, void* taps_ws) {
   if (C > 4) return PE_ERR_UNSUPPORTED;
   const int Ho = Hc / 2, Wo = Wc / 2, Hp = Hc + 6, Wp = Wc + 8;
   const int kmax = round_u8 ? pil_kmax(Hs, Ws, Hi, Wi) : 0;
   if (kmax < 0) return PE_ERR_UNSUPPORTED;
   const int grid = grid_for((long long)B * Hp * Wp, 256);
   __half* cv = reinterpret_cast<__half*>(canvas);
-  if (kmax == 0) stem_canvas_u8_kernel<0><<<grid, 256, 0, st>>>(frames, cv, B, Ctot, c0, C, Hs, Ws, Hi, Wi, Hp, Wp, nrm);
-  else if (kmax == 3) stem_canvas_u8_kernel<3><<<grid, 256, 0, st>>>(frames, cv, B, Ctot, c0, C, Hs, Ws, Hi, Wi, Hp, Wp, nrm);
-  else stem_canvas_u8_kernel<9><<<grid, 256, 0, st>>>(frames, cv, B, Ctot, c0, C, Hs, Ws, Hi, Wi, Hp, Wp, nrm);
+  int4* taps = kmax == 3 ? reinterpret_cast<int4*>(taps_ws) : nullptr;
+  if (taps) {
+    pil_taps_table_kernel<<<ceil_div(Hi + Wi, 256), 256, 0, st>>>(taps, Hs, Ws, Hi, Wi);
+    PE_LAUNCH_CHECK();
+  }
+  if (kmax == 0) stem_canvas_u8_kernel<0><<<grid, 256, 0, st>>>(frames, cv, B, Ctot, c0, C, Hs, Ws, Hi, Wi, Hp, Wp, nrm, nullptr);
+  else if (kmax == 3) stem_canvas_u8_kernel<3><<<grid, 256, 0, st>>>(frames, cv, B, Ctot, c0, C, Hs, Ws, Hi, Wi, Hp, Wp, nrm, taps);
+  else stem_canvas_u8_kernel<9><<<grid, 256, 0, st>>>(frames, cv, B, Ctot, c0, C, Hs, Ws, Hi, Wi, Hp, Wp, nrm, nullptr);
   PE_LAUNCH_CHECK();
   if (A) {  // optional explicit im2col matrix (kept for the op-level GEMM tests; the engine reads the canvas through TMA)
     const long long total = (long long)B * Ho * Wo * 28;
@@ -1193,7 +1290,7 @@ int launch_rpn_proposals(const RpnLevels& lv, int B, int pre_topk, int post_topk
 int launch_roi_align(const RoiLevels& fl, const float4* props, const int* prop_count, int B, int max_props, int C, void* out,
                      cudaStream_t st) {
   if (C % 256) return PE_ERR_UNSUPPORTED;  // lanes cover the channels 8 at a time, whole warps per pass
-  roi_align_kernel<<<(unsigned)((long long)B * max_props), 224, 0, st>>>(fl, props, prop_count, B, max_props, C,
+  roi_align_kernel<<<dim3((unsigned)max_props, (unsigned)B), 224, 0, st>>>(fl, props, prop_count, B, max_props, C,
                                                                          reinterpret_cast<__nv_bfloat16*>(out));
   PE_LAUNCH_CHECK();
   return PE_OK;

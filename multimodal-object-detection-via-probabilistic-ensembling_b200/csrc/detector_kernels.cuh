@@ -55,7 +55,7 @@ struct PackIn {
 int launch_stem_im2col(const float* img, void* canvas, void* A, int B, int Ctot, int c0, int C, int Hi, int Wi, int Hc, int Wc,
                        const StemNorm& nrm, cudaStream_t st);
 int launch_stem_im2col_u8(const unsigned char* frames, void* canvas, void* A, int B, int Ctot, int c0, int C, int Hs, int Ws, int Hi,
-                          int Wi, int Hc, int Wc, int round_u8, const StemNorm& nrm, cudaStream_t st);
+                          int Wi, int Hc, int Wc, int round_u8, const StemNorm& nrm, cudaStream_t st, void* taps_ws = nullptr);
 constexpr int kStemK = 224;  // 7 rows x (8 px x 4 ch): K of the stem GEMM (147 real taps, the rest meet zero weights)
 int launch_resize_frames(const unsigned char* src, float* dst, int B, int C, int Hs, int Ws, int Hd, int Wd, int round_u8,
                          cudaStream_t st);

@@ -134,6 +134,7 @@ void build_plan(pe_detector* d) {
   const int B = c.max_batch;
   const int passes = c.middle_fusion ? 2 : 1;
   d->add_buf("stem_canvas", B, c.canvas_h + 6, c.canvas_w + 8, 4, 2);
+  d->add_buf("pil_taps", 1, 1, c.canvas_h + c.canvas_w, 4, 4);  // Pillow resize tap tables (rows, then columns)
   d->add_buf("stem_out", B, d->H[0], d->W[0], 64, 2);
   d->add_buf("pool_out", B, d->H[1], d->W[1], 64, 2);
   d->add_buf("x0", B, d->H[1], d->W[1], 256, 2);
@@ -248,7 +249,7 @@ struct Runner {
     for (int i = 0; i < d->stem_c; ++i) { nrm.mean[i] = c.pixel_mean[c0 + i]; nrm.std[i] = c.pixel_std[c0 + i]; }
     if (frames)
       check(launch_stem_im2col_u8(frames, buf("stem_canvas"), nullptr, B, Ctot, c0, d->stem_c, src_h, src_w, img_h, img_w, c.canvas_h,
-                                  c.canvas_w, round_u8, nrm, st));
+                                  c.canvas_w, round_u8, nrm, st, buf("pil_taps")));
     else
       check(launch_stem_im2col(images, buf("stem_canvas"), nullptr, B, Ctot, c0, d->stem_c, img_h, img_w, c.canvas_h, c.canvas_w, nrm, st));
     if (status == PE_OK) {  // 7x7/2 conv: tcgen05 GEMM whose A operand is TMA-read straight from the canvas (fp16 operands)
