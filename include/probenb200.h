@@ -213,6 +213,28 @@ PE_API int pe_roi_align_forward(const float* input, int N, int C, int H, int W, 
                                 float spatial_scale, int pooled_h, int pooled_w, int sampling_ratio, int aligned,
                                 float* out, void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Input side (demo/FLIR/demo_FLIR_save_predictions.py:93-121: cv2.imread of the RGB / thermal JPEGs, cv2.resize of
+ * the RGB frame to the thermal size, 3-/4-/6-channel assembly).
+ *
+ * pe_jpeg_*: nvJPEG decode (libnvjpeg of the CUDA toolkit, loaded on first use; PE_ERR_UNSUPPORTED if absent) of n
+ *   JPEG byte strings held in HOST memory into frames [n, height, width, 3] interleaved BGR uint8 in DEVICE memory -
+ *   cv2.imread's layout; grey-scale JPEGs (FLIR thermal_8_bit) are replicated into the three channels.  Every image
+ *   must have the stated size.  The entropy decode runs on the calling host thread, the rest on `stream`.
+ * pe_resize_u8_cv: cv2.resize(src, (dst_w, dst_h)) for uint8, i.e. INTER_LINEAR with OpenCV's 11-bit fixed-point
+ *   weights, bit for bit.  Reads channels [src_c0, src_c0+channels) of src [B, src_h, src_w, src_channels] and writes
+ *   channels [dst_c0, dst_c0+channels) of dst [B, dst_h, dst_w, dst_channels]: with equal sizes it is a channel
+ *   copy, so two calls assemble the early-fusion BGRT or middle-fusion BGRTTT input (:104-121).
+ */
+typedef struct pe_jpeg_decoder pe_jpeg_decoder;
+PE_API int pe_jpeg_create(pe_jpeg_decoder** out);
+PE_API void pe_jpeg_destroy(pe_jpeg_decoder* d);
+PE_API int pe_jpeg_image_info(pe_jpeg_decoder* d, const uint8_t* data, size_t bytes, int* height, int* width, int* components);
+PE_API int pe_jpeg_decode_batch(pe_jpeg_decoder* d, const uint8_t* const* data, const size_t* bytes, int n, uint8_t* frames,
+                                int height, int width, void* stream);
+PE_API int pe_resize_u8_cv(const uint8_t* src, int src_channels, int src_c0, uint8_t* dst, int dst_channels, int dst_c0,
+                           int channels, int B, int src_h, int src_w, int dst_h, int dst_w, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -87,6 +87,14 @@ SIGNATURES.update({
                                      c_void_p, c_void_p]),
 })
 
+SIGNATURES.update({
+    "pe_jpeg_create": (c_int, [ctypes.POINTER(c_void_p)]),
+    "pe_jpeg_destroy": (None, [c_void_p]),
+    "pe_jpeg_image_info": (c_int, [c_void_p, c_void_p, c_size_t, ctypes.POINTER(c_int), ctypes.POINTER(c_int), ctypes.POINTER(c_int)]),
+    "pe_jpeg_decode_batch": (c_int, [c_void_p, ctypes.POINTER(c_void_p), ctypes.POINTER(c_size_t), c_int, c_void_p, c_int, c_int, c_void_p]),
+    "pe_resize_u8_cv": (c_int, [c_void_p, c_int, c_int, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p]),
+})
+
 _lib = None
 
 

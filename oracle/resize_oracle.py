@@ -85,3 +85,63 @@ def resize_shortest_edge_shape(h, w, short=800, max_size=1333):
         scale = max_size * 1.0 / max(newh, neww)
         newh, neww = newh * scale, neww * scale
     return int(newh + 0.5), int(neww + 0.5)
+
+
+# ---- cv2.resize(uint8, INTER_LINEAR) ---------------------------------------------------------------------------------
+# demo/FLIR/demo_FLIR_save_predictions.py:108,117 resizes the RGB frame to the thermal frame's size with
+# ``cv2.resize(rgb_img, (w, h), cv2.INTER_CUBIC)`` - the third positional argument of cv2.resize is ``dst``, so the
+# interpolation stays at its default, INTER_LINEAR.  Third-party arithmetic: OpenCV (reference pins 4.6.0, probEn.yml:140;
+# installed 4.13), modules/imgproc/src/resize.cpp, 8-bit linear path: 11-bit fixed-point weights from float32
+# fractions, horizontal pass in int, vertical pass with two truncating shifts.  Parity status: PINNED -
+# tests/test_oracle_resize.py checks this restatement bit for bit against the installed cv2 for down- and upscales
+# of 1-, 3- and 4-channel images.
+
+def _cv_coeffs(ssize, dsize, clamp_fraction):
+    scale = 1.0 / (float(dsize) / float(ssize))
+    i0 = np.zeros(dsize, np.int64)
+    i1 = np.zeros(dsize, np.int64)
+    w0 = np.zeros(dsize, np.int64)
+    w1 = np.zeros(dsize, np.int64)
+    for d in range(dsize):
+        f = np.float32((d + 0.5) * scale - 0.5)
+        s = int(np.floor(f))
+        f = np.float32(f - np.float32(s))
+        if clamp_fraction:  # columns: the fraction is zeroed at the borders
+            if s < 0:
+                f, s = np.float32(0), 0
+            if s >= ssize - 1:
+                f, s = np.float32(0), ssize - 1
+        i0[d] = min(max(s, 0), ssize - 1)
+        i1[d] = min(max(s + 1, 0), ssize - 1)
+        w0[d] = int(np.rint(np.float32(np.float32(1.0) - f) * np.float32(2048)))
+        w1[d] = int(np.rint(f * np.float32(2048)))
+    return i0, i1, w0, w1
+
+
+def cv2_linear_resize_u8(img, out_h, out_w):
+    """img: (H, W, C) uint8 -> (out_h, out_w, C) uint8, identical to ``cv2.resize(img, (out_w, out_h))``."""
+    img = np.asarray(img, np.uint8)
+    if img.ndim == 2:
+        img = img[:, :, None]
+    H, W, _ = img.shape
+    x0, x1, a0, a1 = _cv_coeffs(W, out_w, True)
+    y0, y1, b0, b1 = _cv_coeffs(H, out_h, False)
+    src = img.astype(np.int64)
+    rows = src[:, x0, :] * a0[None, :, None] + src[:, x1, :] * a1[None, :, None]
+    out = (((b0[:, None, None] * (rows[y0] >> 4)) >> 16) + ((b1[:, None, None] * (rows[y1] >> 4)) >> 16) + 2) >> 2
+    return np.clip(out, 0, 255).astype(np.uint8)
+
+
+def assemble_input(method, rgb, thermal):
+    """demo_FLIR_save_predictions.py:100-121: the array handed to the predictor (uint8 here; the reference stores the
+    4-/6-channel cases in float64 arrays holding the same integers)."""
+    if method == "thermal_only":
+        return thermal
+    rgb_r = cv2_linear_resize_u8(rgb, thermal.shape[0], thermal.shape[1])
+    if method in ("rgb_only", "RGB"):
+        return rgb_r if method == "rgb_only" else rgb
+    if method == "early_fusion":
+        return np.concatenate([rgb_r, thermal[:, :, :1]], axis=2)
+    if method == "middle_fusion":
+        return np.concatenate([rgb_r, thermal], axis=2)
+    raise ValueError(method)
