@@ -6,8 +6,14 @@
 
 Runs the B200 detector engine over the validation pairs and writes ``<outfolder>/val_<method>_predictions.json``
 with the keys of demo_FLIR_save_predictions.py:166-176 (image, boxes, scores, classes, image_id, class_logits,
-probs, vars; detections with class > 2 dropped, :148-164).  Differences from the reference, all on the input
-side (not yet on the GPU): frames are batched (``--batch``) instead of one by one.
+probs, vars; detections with class > 2 dropped, :148-164).  Rows follow ``data['images']`` like the reference's
+loop (:93-99); the ``image`` column repeats its quirk of listing ``os.listdir(RGB)`` names by position (:42,157).
+
+The input side runs on the GPU: the JPEG files are read as bytes, decoded by nvJPEG into HBM,
+the RGB frame is resized to the thermal frame's size with OpenCV's 8-bit bilinear arithmetic and the 3-/4-/6-channel
+input is assembled on the device (``probenb200.io``); DefaultPredictor's ResizeShortestEdge is fused into the
+detector's stem staging.  Extra flags (not in the reference): ``--batch N`` frames per launch, ``--depth {50,101}``,
+``--cpu_decode`` to read and assemble the frames with cv2 exactly as the reference does (decoder parity checks).
 """
 import json
 import os
@@ -51,7 +57,18 @@ def resize_like_predictor(img, short=800, max_size=1333):
     return cv2.resize(img, (nw, nh), interpolation=cv2.INTER_LINEAR)
 
 
-def save_predictions(args, batch=8, depth=101):
+def extra_flags(argv):
+    """Flags this CLI adds to the reference's (stripped before the reference parser sees the command line)."""
+    import argparse
+    ap = argparse.ArgumentParser(add_help=False)
+    ap.add_argument("--batch", type=int, default=8)
+    ap.add_argument("--depth", type=int, default=101, choices=[50, 101])
+    ap.add_argument("--cpu_decode", action="store_true")
+    return ap.parse_known_args(argv)
+
+
+def save_predictions(args, batch=8, depth=101, cpu_decode=False):
+    from probenb200 import io as pio
     val_folder = args.dataset_path
     val_json_path = val_folder + "/FLIR_thermal_RGBT_pairs_val.json"
     rgb_path, t_path = val_folder + "/RGB/", val_folder + "/thermal_8_bit/"
@@ -60,29 +77,39 @@ def save_predictions(args, batch=8, depth=101):
     print("model:", method)
     print("==========================")
     data = json.load(open(val_json_path, "r"))
-    name_to_id = {im["file_name"].split("/")[1].split(".")[0]: im["id"] for im in data["images"]}
-    files = [f for f in listdir(rgb_path) if isfile(join(rgb_path, f))]
+    stems = [im["file_name"].split("/")[1].split(".")[0] for im in data["images"]]
+    name_to_id = {st: im["id"] for st, im in zip(stems, data["images"])}
+    files_names = [f for f in listdir(rgb_path) if isfile(join(rgb_path, f))]
     if not os.path.exists(args.outfolder):
         os.mkdir(args.outfolder)
     mcfg = detector.fusion_method_config(method)
     sd = weights.load_checkpoint(args.model_path)
     print("model loaded:", args.model_path)
-    first = resize_like_predictor(load_frame(t_path, rgb_path, files[0], method))
-    canvas = ((first.shape[0] + 31) // 32 * 32, (first.shape[1] + 31) // 32 * 32)
+    decoder = None if cpu_decode else pio.JpegDecoder()
+
+    def load_batch(names):
+        """uint8 device frames [B, H, W, C] of the pairs `names` (file stems), C = 3 / 4 / 6."""
+        if cpu_decode:
+            return torch.from_numpy(np.stack([load_frame(t_path, rgb_path, n + ".jpg", method).astype(np.uint8) for n in names])).cuda()
+        return pio.load_pair_batch(decoder, [join(rgb_path, n + ".jpg") for n in names], [join(t_path, n + ".jpeg") for n in names],
+                                   method)
+
+    first = load_batch(stems[:1])
+    h0, w0 = int(first.shape[1]), int(first.shape[2])
+    net_hw = detector.resize_shortest_edge_shape(h0, w0)
+    canvas = ((net_hw[0] + 31) // 32 * 32, (net_hw[1] + 31) // 32 * 32)
     det = detector.Detector(sd, depth=depth, num_classes=80 if method == "rgb_only" else 3, max_batch=batch, canvas=canvas,
                             score_thresh=0.5, **mcfg)
     out = {k: [] for k in ("image", "boxes", "scores", "classes", "image_id", "class_logits", "probs", "vars")}
-    for i0 in range(0, len(files), batch):
-        names = files[i0:i0 + batch]
-        frames = [load_frame(t_path, rgb_path, n, method) for n in names]
-        h0, w0 = frames[0].shape[:2]
-        x = torch.stack([torch.from_numpy(resize_like_predictor(f).transpose(2, 0, 1).copy()) for f in frames])
-        res = det.forward_device(x.cuda(), (h0, w0)).to_instances([(h0, w0)] * len(names))
-        for n, inst in zip(names, res):
-            keep = inst.pred_classes <= 2
-            inst = inst[keep]
-            out["image"].append(n)
-            out["image_id"].append(name_to_id.get(n.split(".")[0], -1))
+    for i0 in range(0, len(stems), batch):
+        names = stems[i0:i0 + batch]
+        frames = load_batch(names)
+        # 3-channel uint8 frames take Pillow's resize in the reference, 4-/6-channel arrays cv2's float path
+        res = det.forward_frames_device(frames, net_hw, round_u8=frames.shape[3] == 3).to_instances([(h0, w0)] * len(names))
+        for j, (n, inst) in enumerate(zip(names, res)):
+            inst = inst[inst.pred_classes <= 2]
+            out["image"].append(files_names[i0 + j] if i0 + j < len(files_names) else n + ".jpg")
+            out["image_id"].append(name_to_id[n])
             out["boxes"].append(inst.pred_boxes.tensor.tolist())
             out["scores"].append(inst.scores.tolist())
             out["classes"].append(inst.pred_classes.tolist())
@@ -93,7 +120,9 @@ def save_predictions(args, batch=8, depth=101):
     with open(path, "w") as f:
         json.dump(out, f, indent=2)
     print("saved", path)
+    return path
 
 
 if __name__ == "__main__":
-    save_predictions(config_parser())
+    extra, rest = extra_flags(sys.argv[1:])
+    save_predictions(config_parser(rest), batch=extra.batch, depth=extra.depth, cpu_decode=extra.cpu_decode)

@@ -1,0 +1,104 @@
+"""The two drop-in CLIs end to end on a tiny synthetic FLIR-layout dataset (JPEG pairs + COCO annotations + random
+checkpoints): demo_FLIR_save_predictions.py (GPU decode and --cpu_decode) -> prediction JSONs in the reference's
+schema (demo_FLIR_save_predictions.py:166-176) -> demo_probEn.py (late fusion + COCO bbox evaluation)."""
+import importlib.util
+import json
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+from probenb200 import weights
+from probenb200.opt import config_parser
+
+cv2 = pytest.importorskip("cv2")
+pytestmark = pytest.mark.gpu
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _load_cli(name):
+    spec = importlib.util.spec_from_file_location("cli_" + name, os.path.join(ROOT, "demo", "FLIR", name + ".py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
+
+def _make_dataset(root, n=5):
+    rng = np.random.default_rng(0)
+    os.makedirs(os.path.join(root, "RGB"))
+    os.makedirs(os.path.join(root, "thermal_8_bit"))
+    images, anns = [], []
+    for i in range(n):
+        stem = "FLIR_%05d" % i
+        yy, xx = np.mgrid[0:128, 0:160].astype(np.float32)
+        th = 120 + 60 * np.sin(0.05 * xx + i) * np.cos(0.07 * yy) + rng.normal(0, 4, (128, 160))
+        th = np.clip(th, 0, 255).astype(np.uint8)
+        rgb = np.clip(cv2.resize(np.dstack([th, th // 2 + 40, 255 - th]), (260, 200)).astype(np.float32) + rng.normal(0, 3, (200, 260, 3)), 0, 255)
+        cv2.imwrite(os.path.join(root, "thermal_8_bit", stem + ".jpeg"), th)
+        cv2.imwrite(os.path.join(root, "RGB", stem + ".jpg"), rgb.astype(np.uint8))
+        images.append({"id": 1000 + i, "file_name": "thermal_8_bit/%s.jpeg" % stem, "height": 128, "width": 160})
+        for k in range(3):
+            x, y = rng.uniform(0, 100), rng.uniform(0, 80)
+            anns.append({"id": len(anns) + 1, "image_id": 1000 + i, "category_id": int(rng.integers(0, 3)),
+                         "bbox": [float(x), float(y), 40.0, 30.0], "area": 1200.0, "iscrowd": 0})
+    cats = [{"id": c, "name": n_} for c, n_ in enumerate(["person", "bicycle", "car"])]
+    json.dump({"images": images, "annotations": anns, "categories": cats}, open(os.path.join(root, "FLIR_thermal_RGBT_pairs_val.json"), "w"))
+
+
+@pytest.fixture(scope="module")
+def workdir(tmp_path_factory):
+    d = str(tmp_path_factory.mktemp("flir"))
+    _make_dataset(os.path.join(d, "val"))
+    return d
+
+
+SCHEMA = ("image", "boxes", "scores", "classes", "image_id", "class_logits", "probs", "vars")
+
+
+def test_save_predictions_then_proben(workdir):
+    save = _load_cli("demo_FLIR_save_predictions")
+    out = os.path.join(workdir, "out") + "/"
+    counts = {}
+    for m, (method, cin, mid) in enumerate([("thermal_only", 3, False), ("early_fusion", 4, False), ("middle_fusion", 3, True)]):
+        ck = os.path.join(workdir, method + ".pth")
+        torch.save({"model": weights.random_state_dict(50, cin, 3, seed=20 + m, middle_fusion=mid)}, ck)
+        args = config_parser(["--dataset_path", os.path.join(workdir, "val"), "--fusion_method", method, "--model_path", ck,
+                              "--outfolder", out])
+        path = save.save_predictions(args, batch=2, depth=50)
+        pred = json.load(open(path))
+        assert tuple(pred.keys()) == SCHEMA
+        assert pred["image_id"] == [1000 + i for i in range(5)] and len(pred["boxes"]) == 5
+        for i in range(5):
+            n = len(pred["boxes"][i])
+            assert len(pred["scores"][i]) == n and len(pred["probs"][i]) == n and len(pred["vars"][i]) == n
+            assert all(c <= 2 for c in pred["classes"][i])
+            assert all(len(p) == 3 for p in pred["probs"][i]) and all(len(l) == 4 for l in pred["class_logits"][i])
+        counts[method] = sum(len(b) for b in pred["boxes"])
+    assert sum(counts.values()) > 0, counts
+    proben = _load_cli("demo_probEn")
+    res = proben.main(["--dataset_path", os.path.join(workdir, "val"), "--prediction_path", out, "--score_fusion", "probEn",
+                       "--box_fusion", "v-avg", "--outfolder", out])
+    assert res is not None and set(("AP", "AP50", "AP75", "APs", "APm", "APl")) <= set(res)
+    fused = json.load(open(os.path.join(out, "probEn_probEn_v-avg_fused.json")))
+    assert all(set(d) == {"image_id", "category_id", "bbox", "score"} for d in fused)
+
+
+def test_gpu_decode_agrees_with_cpu_decode(workdir):
+    """Same checkpoint, same pairs: frames decoded by nvJPEG + device assembly vs cv2 (the reference's input code).
+    Grey-scale thermal JPEGs decode within +-2 grey levels, so the detections must be the same objects."""
+    save = _load_cli("demo_FLIR_save_predictions")
+    ck = os.path.join(workdir, "thermal_cmp.pth")
+    torch.save({"model": weights.random_state_dict(50, 3, 3, seed=20)}, ck)
+    preds = []
+    for cpu in (False, True):
+        out = os.path.join(workdir, "out_cpu" if cpu else "out_gpu") + "/"
+        args = config_parser(["--dataset_path", os.path.join(workdir, "val"), "--fusion_method", "thermal_only", "--model_path", ck,
+                              "--outfolder", out])
+        preds.append(json.load(open(save.save_predictions(args, batch=3, depth=50, cpu_decode=cpu))))
+    a, b = preds
+    assert a["image_id"] == b["image_id"]
+    na, nb = sum(len(x) for x in a["boxes"]), sum(len(x) for x in b["boxes"])
+    assert na > 0 and abs(na - nb) <= max(2, 0.1 * na), (na, nb)
