@@ -120,6 +120,9 @@ def save_predictions(args, batch=8, depth=101, cpu_decode=False):
     with open(path, "w") as f:
         json.dump(out, f, indent=2)
     print("saved", path)
+    # the same columns as a binary columnar file; demo_probEn.py prefers it when present
+    from probenb200 import detfile
+    detfile.DetFile.from_json_dict(out, K=3 if method != "rgb_only" else 80).save(path[:-5] + ".pedet")
     return path
 
 

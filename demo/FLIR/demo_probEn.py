@@ -45,6 +45,25 @@ def apply_late_fusion(det_list, method, img_w=640, img_h=512):
     return out
 
 
+def apply_late_fusion_columnar(cols, method, img_w=640, img_h=512):
+    """Same as ``apply_late_fusion`` from ``detfile.DetFile`` columns: one vectorised pack, one launch."""
+    import torch
+    from probenb200 import detfile
+    packed = detfile.pack_models(cols)
+    buf = fusion.fuse_packed(fusion.to_device(packed), method, img_w=float(img_w), img_h=float(img_h))
+    out = []
+    for r in fusion.unpack_results(packed, buf):
+        if r is None:
+            out.append(None)
+            continue
+        inst = Instances([img_h, img_w])
+        inst.pred_boxes = Boxes(r[0])
+        inst.scores = torch.from_numpy(r[1])
+        inst.pred_classes = torch.from_numpy(r[2])
+        out.append(inst)
+    return out
+
+
 def main(argv=None):
     args = config_parser(argv)
     pred = args.prediction_path
@@ -54,16 +73,34 @@ def main(argv=None):
         print("detection file %d:" % (i + 1), f)
     if not os.path.exists(args.outfolder):
         os.mkdir(args.outfolder)
-    dets = [json.load(open(f, "r")) for f in files if os.path.isfile(f)]
-    if len(dets) < 2:
-        raise FileNotFoundError("need at least two prediction files under %r" % pred)
     method = [args.score_fusion, args.box_fusion]
-    print("Method: ", method)
-    start = time.time()
-    results = apply_late_fusion(dets, method)
-    total = time.time() - start
+    # frame size for the class-offset tiles (the reference imreads every thermal JPEG for it, demo_probEn.py:269-271)
+    val_json = os.path.join(args.dataset_path or "", "FLIR_thermal_RGBT_pairs_val.json")
+    gt = json.load(open(val_json)) if args.dataset_path and os.path.isfile(val_json) else None
+    img_w, img_h = 640, 512
+    if gt and gt.get("images") and "width" in gt["images"][0]:
+        img_w, img_h = int(gt["images"][0]["width"]), int(gt["images"][0]["height"])
+    binaries = [f[:-5] + ".pedet" for f in files]
+    if all(os.path.isfile(f) for f in binaries):
+        # binary columnar files written next to the JSON by demo_FLIR_save_predictions.py: disk -> HBM without a
+        # per-detection Python step
+        from probenb200 import detfile
+        cols = [detfile.DetFile.load(f) for f in binaries]
+        print("Method: ", method)
+        start = time.time()
+        results = apply_late_fusion_columnar(cols, method, img_w, img_h)
+        total = time.time() - start
+        image_ids = [int(i) for i in cols[1].image_id]
+    else:
+        dets = [json.load(open(f, "r")) for f in files if os.path.isfile(f)]
+        if len(dets) < 2:
+            raise FileNotFoundError("need at least two prediction files under %r" % pred)
+        print("Method: ", method)
+        start = time.time()
+        results = apply_late_fusion(dets, method, img_w, img_h)
+        total = time.time() - start
+        image_ids = dets[1]["image_id"] if len(dets) > 1 else dets[0]["image_id"]
     print("Average time:", total / max(1, len(results)))
-    image_ids = dets[1]["image_id"] if len(dets) > 1 else dets[0]["image_id"]
     coco_dets = []
     for inst, iid in zip(results, image_ids):
         if inst is not None:
@@ -71,9 +108,7 @@ def main(argv=None):
                                                            inst.pred_classes.numpy(), iid)
     out_json = os.path.join(args.outfolder, "probEn_%s_%s_fused.json" % tuple(method))
     json.dump(coco_dets, open(out_json, "w"))
-    val_json = os.path.join(args.dataset_path or "", "FLIR_thermal_RGBT_pairs_val.json")
-    if args.dataset_path and os.path.isfile(val_json):
-        gt = json.load(open(val_json))
+    if gt is not None:
         ev = evaluation.COCOBBoxEval(gt["annotations"], coco_dets, image_ids=[im["id"] for im in gt["images"]])
         res = ev.evaluate()
         print("Evaluation results for bbox:")

@@ -84,6 +84,14 @@ def test_save_predictions_then_proben(workdir):
     assert res is not None and set(("AP", "AP50", "AP75", "APs", "APm", "APl")) <= set(res)
     fused = json.load(open(os.path.join(out, "probEn_probEn_v-avg_fused.json")))
     assert all(set(d) == {"image_id", "category_id", "bbox", "score"} for d in fused)
+    # that run read the binary columnar files written next to the JSONs; the JSON path must give the same result
+    for f in os.listdir(out):
+        if f.endswith(".pedet"):
+            os.remove(os.path.join(out, f))
+    res_json = proben.main(["--dataset_path", os.path.join(workdir, "val"), "--prediction_path", out, "--score_fusion", "probEn",
+                            "--box_fusion", "v-avg", "--outfolder", out])
+    assert res_json == pytest.approx(res, nan_ok=True)
+    assert json.load(open(os.path.join(out, "probEn_probEn_v-avg_fused.json"))) == fused
 
 
 def test_gpu_decode_agrees_with_cpu_decode(workdir):
@@ -102,3 +110,61 @@ def test_gpu_decode_agrees_with_cpu_decode(workdir):
     assert a["image_id"] == b["image_id"]
     na, nb = sum(len(x) for x in a["boxes"]), sum(len(x) for x in b["boxes"])
     assert na > 0 and abs(na - nb) <= max(2, 0.1 * na), (na, nb)
+
+
+def test_kaist_lamr_then_binary_proben(tmp_path):
+    """demo/KAIST: per-modality LAMR txt + variance npz (reference format, demo_LAMR_KAIST.py:127-145), then K = 1
+    ProbEn of two modalities; the fused txt must equal the oracle's fusion of the same files."""
+    from oracle import proben_oracle as O
+    root = str(tmp_path / "kaist")
+    rng = np.random.default_rng(3)
+    entries = []
+    for i in range(4):
+        e = "set06/V000/I%05d" % i
+        entries.append(e)
+        for sub in ("visible", "lwir"):
+            os.makedirs(os.path.join(root, "set06", "V000", sub), exist_ok=True)
+        yy, xx = np.mgrid[0:128, 0:160].astype(np.float32)
+        th = np.clip(110 + 70 * np.sin(0.06 * xx + i) * np.cos(0.05 * yy) + rng.normal(0, 4, (128, 160)), 0, 255).astype(np.uint8)
+        cv2.imwrite(os.path.join(root, "set06", "V000", "lwir", "I%05d.jpg" % i), th)
+        cv2.imwrite(os.path.join(root, "set06", "V000", "visible", "I%05d.jpg" % i), np.dstack([th, 255 - th, th // 2 + 30]))
+    split = os.path.join(root, "test-all-20.txt")
+    open(split, "w").write("\n".join(entries) + "\n")
+    spec = importlib.util.spec_from_file_location("cli_kaist", os.path.join(ROOT, "demo", "KAIST", "demo_LAMR_KAIST.py"))
+    kaist = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(kaist)
+    out = str(tmp_path / "pred") + "/"
+    for m, method in enumerate(["thermal_only", "rgb_only"]):
+        ck = str(tmp_path / (method + ".pth"))
+        torch.save({"model": weights.random_state_dict(50, 3, 1, seed=40 + m, head_gain=3.0)}, ck)
+        txt, npz = kaist.main(["--dataset_path", root, "--split_file", split, "--fusion_method", method, "--model_path", ck,
+                               "--outfolder", out, "--batch", "2"])
+        rows = [l.strip().split(",") for l in open(txt)]
+        assert all(len(r) == 6 and 1 <= int(r[0]) <= 4 for r in rows)
+        v = np.load(npz, allow_pickle=True)["vars"].item()
+        assert sorted(v.keys()) == [1, 2, 3, 4] and sum(len(x) for x in v.values()) == len(rows)
+    sys.path.insert(0, os.path.join(ROOT, "demo", "KAIST"))
+    spec = importlib.util.spec_from_file_location("cli_kaist_pe", os.path.join(ROOT, "demo", "KAIST", "demo_probEn_KAIST.py"))
+    pe = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(pe)
+    fused = pe.main(["--prediction_path", out, "--methods", "thermal_only", "rgb_only", "--img_w", "160", "--img_h", "128"])
+    got = np.loadtxt(fused, delimiter=",", ndmin=2) if os.path.getsize(fused) else np.zeros((0, 6))
+    files = [pe.read_modality(out, m, 4) for m in ("thermal_only", "rgb_only")]
+    want = []
+    for i in range(4):
+        infos = []
+        for f in files:
+            lo, hi = int(f.offsets[i]), int(f.offsets[i + 1])
+            infos.append({"bbox": f.boxes[lo:hi].astype(np.float64).tolist(), "score": f.scores[lo:hi].astype(np.float64).tolist(),
+                          "class": f.classes[lo:hi].tolist(), "prob": f.probs[lo:hi].astype(np.float64).tolist(),
+                          "vars": f.vars[lo:hi].astype(np.float64).tolist()})
+        r = O.late_fusion_dispatch(("probEn", "v-avg"), infos, img_w=160, img_h=128)
+        if r is None:
+            continue
+        b, s, c = (np.asarray(t, np.float64) for t in r)
+        for k in range(len(s)):
+            if int(c[k]) == 0:
+                want.append([i + 1, b[k][0], b[k][1], b[k][2] - b[k][0], b[k][3] - b[k][1], s[k]])
+    want = np.asarray(want, np.float64).reshape(-1, 6)
+    assert got.shape == want.shape and got.shape[0] > 0
+    np.testing.assert_allclose(got, want, rtol=1e-4, atol=1e-3)
