@@ -94,6 +94,18 @@ def test_save_predictions_then_proben(workdir):
     assert json.load(open(os.path.join(out, "probEn_probEn_v-avg_fused.json"))) == fused
 
 
+def test_single_model_map_cli(workdir):
+    """demo_mAP_FLIR.py: one detector over the validation pairs -> COCO bbox numbers."""
+    cli = _load_cli("demo_mAP_FLIR")
+    ck = os.path.join(workdir, "thermal_map.pth")
+    torch.save({"model": weights.random_state_dict(50, 3, 3, seed=20)}, ck)
+    out = os.path.join(workdir, "out_map") + "/"
+    res = cli.main(["--dataset_path", os.path.join(workdir, "val"), "--fusion_method", "thermal_only", "--model_path", ck,
+                    "--outfolder", out, "--batch", "2", "--depth", "50"])
+    assert set(("AP", "AP50", "AP75", "APs", "APm", "APl")) <= set(res)
+    assert json.load(open(os.path.join(out, "FLIR_thermal_only_mAP.json"))).keys() == res.keys()
+
+
 def test_gpu_decode_agrees_with_cpu_decode(workdir):
     """Same checkpoint, same pairs: frames decoded by nvJPEG + device assembly vs cv2 (the reference's input code).
     Grey-scale thermal JPEGs decode within +-2 grey levels, so the detections must be the same objects."""
