@@ -524,6 +524,13 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
           mbar_wait(&io_ready[p], (g / R) & 1u);  // buffer free and (residual layers) its residual sub-tile landed
           uint4* myrow = reinterpret_cast<uint4*>(io + row * 128);
           const uint4* crs = reinterpret_cast<const uint4*>(coarse_stage + p * kCoarseBytes + crow * 128);
+          // the eight residual chunks of this row are read up front: inside the loop every load would have to wait for
+          // the previous chunk's store (same buffer, the compiler cannot prove the swizzled slots distinct)
+          uint4 res[8];
+          if (rmode) {
+#pragma unroll
+            for (int c = 0; c < 8; ++c) res[c] = rmode == 1 ? myrow[c ^ (row & 7)] : crs[c ^ (crow & 7)];
+          }
 #pragma unroll
           for (int c = 0; c < 8; ++c) {
             float f[8];
@@ -537,7 +544,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
             }
             uint4* slot = myrow + (c ^ (row & 7));  // 128B swizzle: 16-byte chunk index XOR (row mod 8)
             if (rmode) {
-              const uint4 r = rmode == 1 ? *slot : crs[c ^ (crow & 7)];
+              const uint4 r = res[c];
               f[0] += bf16_lo(r.x); f[1] += bf16_hi(r.x); f[2] += bf16_lo(r.y); f[3] += bf16_hi(r.y);
               f[4] += bf16_lo(r.z); f[5] += bf16_hi(r.z); f[6] += bf16_lo(r.w); f[7] += bf16_hi(r.w);
             }
