@@ -38,3 +38,24 @@ def test_missing_library_is_loud(monkeypatch):
     monkeypatch.setattr(_lib, "LIB_PATH", "/nonexistent/libprobenb200.so")
     with pytest.raises(RuntimeError):
         _lib.load()
+
+
+def test_operator_dropins_refuse_cpu_tensors():
+    """No CPU path exists behind the detectron2.layers drop-ins or the input-side ops: CPU tensors raise RuntimeError
+    (the reference's ops dispatch on `input.is_cuda()`; here the other branch does not exist)."""
+    import pytest
+    import torch
+    from probenb200 import io as pio
+    from probenb200 import layers
+    with pytest.raises(RuntimeError):
+        layers.batched_nms(torch.zeros(3, 4), torch.zeros(3), torch.zeros(3, dtype=torch.int64), 0.5)
+    with pytest.raises(RuntimeError):
+        layers.ROIAlign((7, 7), 1.0, 0)(torch.zeros(1, 1, 8, 8), torch.zeros(1, 5))
+    with pytest.raises(RuntimeError):
+        pio.resize_u8(torch.zeros(1, 8, 8, 3, dtype=torch.uint8), (4, 4))
+    # shape errors are reported before any device work, like the reference's asserts
+    with pytest.raises((RuntimeError, AssertionError)):
+        layers.ROIAlign((7, 7), 1.0, 0)(torch.zeros(1, 1, 8, 8), torch.zeros(1, 4))
+    # empty inputs short-circuit without touching the GPU
+    assert layers.nms(torch.zeros(0, 4), torch.zeros(0), 0.5).shape == (0,)
+    assert layers.ROIAlign((7, 7), 1.0, 0)(torch.zeros(0, 3, 10, 10), torch.zeros(0, 5)).shape == (0, 3, 7, 7)
