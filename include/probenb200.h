@@ -220,7 +220,9 @@ PE_API int pe_roi_align_forward(const float* input, int N, int C, int H, int W, 
  * pe_jpeg_*: nvJPEG decode (libnvjpeg of the CUDA toolkit, loaded on first use; PE_ERR_UNSUPPORTED if absent) of n
  *   JPEG byte strings held in HOST memory into frames [n, height, width, 3] interleaved BGR uint8 in DEVICE memory -
  *   cv2.imread's layout; grey-scale JPEGs (FLIR thermal_8_bit) are replicated into the three channels.  Every image
- *   must have the stated size.  The entropy decode runs on the calling host thread, the rest on `stream`.
+ *   must have the stated size.  The entropy decode runs on the calling host thread, the rest on `stream`, which is
+ *   synchronised after every image (the decoder state's staging buffers are reused) - the only entry point that
+ *   blocks on its stream.
  * pe_resize_u8_cv: cv2.resize(src, (dst_w, dst_h)) for uint8, i.e. INTER_LINEAR with OpenCV's 11-bit fixed-point
  *   weights, bit for bit.  Reads channels [src_c0, src_c0+channels) of src [B, src_h, src_w, src_channels] and writes
  *   channels [dst_c0, dst_c0+channels) of dst [B, dst_h, dst_w, dst_channels]: with equal sizes it is a channel

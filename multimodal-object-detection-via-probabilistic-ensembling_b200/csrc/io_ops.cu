@@ -186,6 +186,11 @@ extern "C" PE_API int pe_jpeg_decode_batch(pe_jpeg_decoder* d, const uint8_t* co
     img.pitch[0] = (size_t)width * 3;
     // interleaved BGR, the layout cv2.imread returns; a grey-scale JPEG is replicated into the three channels
     if (api.Decode(d->handle, d->state, data[i], bytes[i], NVJPEG_OUTPUT_BGRI, &img, st) != NVJPEG_STATUS_SUCCESS) return PE_ERR_CUDA;
+    // One nvjpegJpegState owns the pinned staging buffers of the entropy-decoded coefficients; the next nvjpegDecode
+    // on the same state refills them on the host while the previous image's copies may still be in flight (seen as
+    // rare corrupt frames), so the state is drained after every image.  This is the one entry point of the library that
+    // synchronises its stream; the decode is host-synchronous (CPU Huffman stage) anyway.
+    PE_CUDA_CHECK(cudaStreamSynchronize(st));
   }
   return PE_OK;
 }
