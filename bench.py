@@ -439,7 +439,10 @@ def run_pairs(args):
                      "step_frac_of_peak": flop_step / (ms / args.steps * 1e-3) / 1e12 / peak_tf,
                      "per_launch_roofline": per_launch},
     }
-    out["cpu_baseline"] = cpu_pairs_baseline(depth, method, n_pairs=1)
+    if args.cpu_seconds > 0:
+        out["cpu_baseline"] = cpu_pairs_baseline(depth, method, n_pairs=1)
+    else:  # profiling runs (ncu replays): skip the ~20 s CPU leg
+        out["cpu_baseline"] = {"value": None, "unit": "pairs/s", "cores": 0, "kind": "port", "sample": "skipped (--cpu-seconds 0)"}
     return out
 
 
