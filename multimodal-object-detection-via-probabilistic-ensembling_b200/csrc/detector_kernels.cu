@@ -319,6 +319,11 @@ __global__ void resize_frames_kernel(const unsigned char* __restrict__ src, floa
 }
 
 // ---------------------------------------------------------------------------------------------- pooling
+__device__ __forceinline__ uint32_t bf16x2_max(uint32_t a, uint32_t b) {
+  const __nv_bfloat162 r = __hmax2(*reinterpret_cast<const __nv_bfloat162*>(&a), *reinterpret_cast<const __nv_bfloat162*>(&b));
+  return *reinterpret_cast<const uint32_t*>(&r);
+}
+
 __global__ void maxpool3x3s2_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ y, int B, int H, int W,
                                     int C, int Ho, int Wo) {
   const int cg = C >> 3;
@@ -329,21 +334,23 @@ __global__ void maxpool3x3s2_kernel(const __nv_bfloat16* __restrict__ x, __nv_bf
     const int wo = (int)(pix % Wo);
     pix /= Wo;
     const int ho = (int)(pix % Ho), b = (int)(pix / Ho);
-    float m[8];
-#pragma unroll
-    for (int j = 0; j < 8; ++j) m[j] = -INFINITY;
+    // max is exact in any precision: compare the packed bf16 pairs directly (HMNMX2.BF16) instead of unpacking to fp32
+    // (the kernel was instruction-bound: 400 instructions per thread, most of them unpack + fmaxf)
+    uint4 m = make_uint4(0xff80ff80u, 0xff80ff80u, 0xff80ff80u, 0xff80ff80u);  // -inf
+    const uint4* xb = reinterpret_cast<const uint4*>(x + (size_t)b * H * W * C) + g;
     for (int dy = 0; dy < 3; ++dy) {
       const int yy = 2 * ho - 1 + dy;
       if (yy < 0 || yy >= H) continue;
+      const uint4* xr = xb + (size_t)yy * W * cg;
+#pragma unroll
       for (int dx = 0; dx < 3; ++dx) {
         const int xx = 2 * wo - 1 + dx;
         if (xx < 0 || xx >= W) continue;
-        const uint4 r = __ldg(reinterpret_cast<const uint4*>(x + (((size_t)b * H + yy) * W + xx) * C) + g);
-        m[0] = fmaxf(m[0], bflo(r.x)); m[1] = fmaxf(m[1], bfhi(r.x)); m[2] = fmaxf(m[2], bflo(r.y)); m[3] = fmaxf(m[3], bfhi(r.y));
-        m[4] = fmaxf(m[4], bflo(r.z)); m[5] = fmaxf(m[5], bfhi(r.z)); m[6] = fmaxf(m[6], bflo(r.w)); m[7] = fmaxf(m[7], bfhi(r.w));
+        const uint4 r = __ldg(xr + (size_t)xx * cg);
+        m.x = bf16x2_max(m.x, r.x); m.y = bf16x2_max(m.y, r.y); m.z = bf16x2_max(m.z, r.z); m.w = bf16x2_max(m.w, r.w);
       }
     }
-    reinterpret_cast<uint4*>(y)[t] = make_uint4(packbf(m[0], m[1]), packbf(m[2], m[3]), packbf(m[4], m[5]), packbf(m[6], m[7]));
+    reinterpret_cast<uint4*>(y)[t] = m;
   }
 }
 
