@@ -13,7 +13,10 @@ The input side runs on the GPU: the JPEG files are read 
 the RGB frame is resized to the thermal frame's size with OpenCV's 8-bit bilinear arithmetic and the 3-/4-/6-channel
 input is assembled on the device (``probenb200.io``); DefaultPredictor's ResizeShortestEdge is fused into the
 detector's stem staging.  Extra flags (not in the reference): ``--batch N`` frames per launch, ``--depth {50,101}``,
-``--cpu_decode`` to read and assemble the frames with cv2 exactly as the reference does (decoder parity checks).
+``--cpu_decode`` to read and assemble the frames with cv2 exactly as the reference does - REQUIRED for bit-level decoder
+parity with the reference: nvJPEG and libjpeg-turbo differ by 1-2 grey levels.  ``rgb_only`` runs the 80-class COCO
+zoo model from ``trained_models/Detectron2_pretrained/model_final_f6e8b1.pkl`` like the reference (falling back to
+``--model_path`` when that file is absent); ``.pkl`` (model-zoo format) and ``.pth`` checkpoints are both accepted.
 """
 import json
 import os
@@ -30,6 +33,10 @@ import torch  # noqa: E402
 
 from probenb200 import detector, weights  # noqa: E402
 from probenb200.opt import config_parser  # noqa: E402
+
+
+# rgb_only: the COCO model-zoo R101-FPN 3x checkpoint, 80 classes (demo_FLIR_save_predictions.py:58-60)
+ZOO_RGB_MODEL = "trained_models/Detectron2_pretrained/model_final_f6e8b1.pkl"
 
 
 def load_frame(t_path, rgb_path, name, method):
@@ -83,8 +90,12 @@ def save_predictions(args, batch=8, depth=101, cpu_decode=False):
     if not os.path.exists(args.outfolder):
         os.mkdir(args.outfolder)
     mcfg = detector.fusion_method_config(method)
-    sd = weights.load_checkpoint(args.model_path)
-    print("model loaded:", args.model_path)
+    K = 80 if method == "rgb_only" else 3
+    model_path = args.model_path
+    if method == "rgb_only" and os.path.isfile(ZOO_RGB_MODEL):
+        model_path = ZOO_RGB_MODEL  # the reference ignores --model_path for rgb_only (:58-60)
+    sd = weights.load_checkpoint(model_path, num_classes=K)
+    print("model loaded:", model_path)
     decoder = None if cpu_decode else pio.JpegDecoder()
 
     def load_batch(names):
@@ -98,7 +109,7 @@ def save_predictions(args, batch=8, depth=101, cpu_decode=False):
     h0, w0 = int(first.shape[1]), int(first.shape[2])
     net_hw = detector.resize_shortest_edge_shape(h0, w0)
     canvas = ((net_hw[0] + 31) // 32 * 32, (net_hw[1] + 31) // 32 * 32)
-    det = detector.Detector(sd, depth=depth, num_classes=80 if method == "rgb_only" else 3, max_batch=batch, canvas=canvas,
+    det = detector.Detector(sd, depth=depth, num_classes=K, max_batch=batch, canvas=canvas,
                             score_thresh=0.5, **mcfg)
     out = {k: [] for k in ("image", "boxes", "scores", "classes", "image_id", "class_logits", "probs", "vars")}
     for i0 in range(0, len(stems), batch):
@@ -122,7 +133,7 @@ def save_predictions(args, batch=8, depth=101, cpu_decode=False):
     print("saved", path)
     # the same columns as a binary columnar file; demo_probEn.py prefers it when present
     from probenb200 import detfile
-    detfile.DetFile.from_json_dict(out, K=3 if method != "rgb_only" else 80).save(path[:-5] + ".pedet")
+    detfile.DetFile.from_json_dict(out, K=K).save(path[:-5] + ".pedet")
     return path
 
 

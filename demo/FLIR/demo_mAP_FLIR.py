@@ -43,6 +43,7 @@ def main(argv=None):
     dets = []
     for iid, boxes, scores, classes in zip(pred["image_id"], pred["boxes"], pred["scores"], pred["classes"]):
         dets += evaluation.instances_to_coco_json(boxes, scores, classes, iid)
+    evaluation.unmap_category_ids(dets, gt.get("categories"))  # FLIR_evaluation.py:163-175
     ev = evaluation.COCOBBoxEval(gt["annotations"], dets, image_ids=[im["id"] for im in gt["images"]])
     res = ev.evaluate()
     print("Evaluation results for bbox:")

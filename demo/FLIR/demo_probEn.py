@@ -8,8 +8,11 @@ Reads ``<prediction_path>val_{thermal_only,early_fusion,middle_fusion}_predictio
 demo_FLIR_save_predictions.py:166-176), fuses ALL images in one ``pe_fuse_batch`` launch on the GPU
 (the reference loops image by image in numpy, demo_probEn.py:204-292), and evaluates COCO bbox mAP against
 ``<dataset_path>/FLIR_thermal_RGBT_pairs_val.json`` when that file exists.  Extra: ``--save_fused FILE`` writes
-the fused detections as JSON.  Image height/width come from the annotation file (the reference imreads every
-thermal JPEG just to learn H, W - demo_probEn.py:269-271); 512 x 640 is assumed when no annotations are given.
+the fused detections as JSON.  The class-offset tile of the clustering is 640 x 512 whatever the frames' size, as in
+the reference (demo_probEn.py:100-103 hard-codes it); ``--tiles_from_annotations`` takes it from the first image of
+the annotation file instead (needed for frames larger than 640 x 512, where the reference's tiles overlap).  Binary
+``.pedet`` sidecars are read instead of the JSON only when they are at least as new as their JSON file (or with
+``--binary``); the source used is printed.
 """
 import json
 import os
@@ -64,8 +67,32 @@ def apply_late_fusion_columnar(cols, method, img_w=640, img_h=512):
     return out
 
 
+def extra_flags(argv):
+    """Flags this CLI adds to the reference's (stripped before the reference parser sees the command line)."""
+    import argparse
+    ap = argparse.ArgumentParser(add_help=False)
+    ap.add_argument("--tiles_from_annotations", action="store_true",
+                    help="class-offset tile = size of the first annotated image (reference: always 640 x 512)")
+    ap.add_argument("--binary", action="store_true", help="read the .pedet sidecars even when they are older than the JSON files")
+    ap.add_argument("--no_binary", action="store_true", help="always parse the JSON prediction files")
+    return ap.parse_known_args(argv)
+
+
+def _fresh_sidecars(files, binaries, force):
+    """A .pedet is used only if it exists and is not older than its JSON (the JSON is the reference's contract: a
+    regenerated JSON must never be shadowed by a stale sidecar)."""
+    for f, b in zip(files, binaries):
+        if not os.path.isfile(b):
+            return False
+        if not force and os.path.isfile(f) and os.path.getmtime(b) < os.path.getmtime(f):
+            print("stale sidecar %s (older than %s): reading the JSON files" % (b, f))
+            return False
+    return True
+
+
 def main(argv=None):
-    args = config_parser(argv)
+    extra, rest = extra_flags(sys.argv[1:] if argv is None else argv)
+    args = config_parser(rest)
     pred = args.prediction_path
     files = [pred + "val_thermal_only_predictions.json", pred + "val_early_fusion_predictions.json",
              pred + "val_middle_fusion_predictions.json"]
@@ -77,11 +104,12 @@ def main(argv=None):
     # frame size for the class-offset tiles (the reference imreads every thermal JPEG for it, demo_probEn.py:269-271)
     val_json = os.path.join(args.dataset_path or "", "FLIR_thermal_RGBT_pairs_val.json")
     gt = json.load(open(val_json)) if args.dataset_path and os.path.isfile(val_json) else None
-    img_w, img_h = 640, 512
-    if gt and gt.get("images") and "width" in gt["images"][0]:
+    img_w, img_h = 640, 512  # demo_probEn.py:100-103
+    if extra.tiles_from_annotations and gt and gt.get("images") and "width" in gt["images"][0]:
         img_w, img_h = int(gt["images"][0]["width"]), int(gt["images"][0]["height"])
     binaries = [f[:-5] + ".pedet" for f in files]
-    if all(os.path.isfile(f) for f in binaries):
+    if not extra.no_binary and _fresh_sidecars(files, binaries, extra.binary):
+        print("reading binary columnar detections:", ", ".join(os.path.basename(b) for b in binaries))
         # binary columnar files written next to the JSON by demo_FLIR_save_predictions.py: disk -> HBM without a
         # per-detection Python step
         from probenb200 import detfile
@@ -92,6 +120,7 @@ def main(argv=None):
         total = time.time() - start
         image_ids = [int(i) for i in cols[1].image_id]
     else:
+        print("reading JSON detections")
         dets = [json.load(open(f, "r")) for f in files if os.path.isfile(f)]
         if len(dets) < 2:
             raise FileNotFoundError("need at least two prediction files under %r" % pred)
@@ -106,6 +135,9 @@ def main(argv=None):
         if inst is not None:
             coco_dets += evaluation.instances_to_coco_json(inst.pred_boxes.tensor.numpy(), inst.scores.numpy(),
                                                            inst.pred_classes.numpy(), iid)
+    if gt is not None:
+        # FLIREvaluator un-maps the contiguous class index to the dataset's category id first (FLIR_evaluation.py:163-175)
+        evaluation.unmap_category_ids(coco_dets, gt.get("categories"))
     out_json = os.path.join(args.outfolder, "probEn_%s_%s_fused.json" % tuple(method))
     json.dump(coco_dets, open(out_json, "w"))
     if gt is not None:

@@ -36,8 +36,9 @@ constexpr int kStemRowBytes = (2 * kBlockM + 6) * 8;      // canvas bytes feedin
 constexpr int kStemRowPitch = 2112;                         // smem pitch of those segments (16 B aligned)
 constexpr int kStemRowStages = 6;
 constexpr int kStemWBytes = 7 * 64 * 64;                   // resident stem filter bank: 7 rows x [64 x 32] fp16, 64B-swizzled
-constexpr int kThreads = 256;
 constexpr int kEpilogueWarp0 = 4;
+constexpr int kEpilogueWarps = 8;   // two warps per TMEM lane quarter (one per scheduler pair): each owns half of the columns
+constexpr int kThreads = 32 * (kEpilogueWarp0 + kEpilogueWarps);
 constexpr uint32_t kWatchdogPolls = 1u << 27;  // mbarrier polls before trapping (debug safety net)
 
 struct ConvArgs {
@@ -124,7 +125,6 @@ __device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk
 template <int kPending>
 __device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(kPending) : "memory"); }
 __device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
-__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
 }
@@ -278,11 +278,11 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&tmem_full[s], 1);
-      mbar_init(&tmem_empty[s], 4);  // one arrive per epilogue warp
+      mbar_init(&tmem_empty[s], kEpilogueWarps);  // one arrive per epilogue warp
     }
     for (int s = 0; s < kMaxIoBufs; ++s) {
       mbar_init(&io_ready[s], 1);
-      mbar_init(&io_written[s], 128);
+      mbar_init(&io_written[s], 32 * kEpilogueWarps);
     }
     for (int s = 0; s < 4; ++s) { mbar_init(&a_full[s], 1); mbar_init(&a_empty[s], 1); }
     for (int s = 0; s < kMaxBStages; ++s) { mbar_init(&b_full[s], 1); mbar_init(&b_empty[s], 1); }
@@ -488,7 +488,11 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
     }
   } else if (warp >= kEpilogueWarp0) {
     // ================================ epilogue ================================
-    const int q = warp - kEpilogueWarp0;  // TMEM lane quarter owned by this warp
+    // warps 4-7 and 8-11: warp w may only touch TMEM lanes [32 * (w % 4), +32); the two warps of a lane quarter split
+    // the columns (half 0: channels 0-31 of every 64-channel sub-tile, half 1: channels 32-63), so each scheduler has two
+    // epilogue warps to interleave and the dependent TMEM -> bias -> residual -> ReLU -> smem chain of one hides the other's
+    const int q = (warp - kEpilogueWarp0) & 3;  // TMEM lane quarter owned by this warp
+    const int half = (warp - kEpilogueWarp0) >> 2;
     const int row = q * 32 + lane;
     const int ph = row / a.TW, pw = row - ph * a.TW;
     int acc = 0;
@@ -509,12 +513,10 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
           const uint32_t p = g % R;
           unsigned char* io = io_stage + p * kIoBytes;
           const int ch0 = n0 + s2 * 64;
-          uint32_t v[64];
-          const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BLOCK_N + s2 * 64);
+          uint32_t v[32];
+          const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BLOCK_N + s2 * 64 + half * 32);
           tmem_ld_32x32b_x16(taddr, v);
           tmem_ld_32x32b_x16(taddr + 16, v + 16);
-          tmem_ld_32x32b_x16(taddr + 32, v + 32);
-          tmem_ld_32x32b_x16(taddr + 48, v + 48);
           tmem_ld_wait();
           if (s2 == nsub - 1) {  // accumulator fully read: hand the TMEM stage back to the MMA warp
             tc_fence_before();
@@ -524,18 +526,19 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
           mbar_wait(&io_ready[p], (g / R) & 1u);  // buffer free and (residual layers) its residual sub-tile landed
           uint4* myrow = reinterpret_cast<uint4*>(io + row * 128);
           const uint4* crs = reinterpret_cast<const uint4*>(coarse_stage + p * kCoarseBytes + crow * 128);
-          // the eight residual chunks of this row are read up front: inside the loop every load would have to wait for
-          // the previous chunk's store (same buffer, the compiler cannot prove the swizzled slots distinct)
-          uint4 res[8];
+          // this warp's four residual chunks of the row are read up front: inside the loop every load would have to wait
+          // for the previous chunk's store (same buffer, the compiler cannot prove the swizzled slots distinct)
+          uint4 res[4];
           if (rmode) {
 #pragma unroll
-            for (int c = 0; c < 8; ++c) res[c] = rmode == 1 ? myrow[c ^ (row & 7)] : crs[c ^ (crow & 7)];
+            for (int j = 0; j < 4; ++j) res[j] = rmode == 1 ? myrow[(half * 4 + j) ^ (row & 7)] : crs[(half * 4 + j) ^ (crow & 7)];
           }
 #pragma unroll
-          for (int c = 0; c < 8; ++c) {
+          for (int j = 0; j < 4; ++j) {
+            const int c = half * 4 + j;
             float f[8];
 #pragma unroll
-            for (int i = 0; i < 8; ++i) f[i] = __uint_as_float(v[c * 8 + i]);
+            for (int i = 0; i < 8; ++i) f[i] = __uint_as_float(v[j * 8 + i]);
             if (a.bias) {
               const float4 b0 = __ldg(reinterpret_cast<const float4*>(a.bias + ch0 + c * 8));
               const float4 b1 = __ldg(reinterpret_cast<const float4*>(a.bias + ch0 + c * 8 + 4));
@@ -544,7 +547,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
             }
             uint4* slot = myrow + (c ^ (row & 7));  // 128B swizzle: 16-byte chunk index XOR (row mod 8)
             if (rmode) {
-              const uint4 r = res[c];
+              const uint4 r = res[j];
               f[0] += bf16_lo(r.x); f[1] += bf16_hi(r.x); f[2] += bf16_lo(r.y); f[3] += bf16_hi(r.y);
               f[4] += bf16_lo(r.z); f[5] += bf16_hi(r.z); f[6] += bf16_lo(r.w); f[7] += bf16_hi(r.w);
             }
@@ -555,7 +558,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
             *slot = make_uint4(pack_bf16(f[0], f[1]), pack_bf16(f[2], f[3]), pack_bf16(f[4], f[5]), pack_bf16(f[6], f[7]));
           }
           fence_proxy_async();            // make the generic-proxy row writes visible to the TMA store
-          mbar_arrive(&io_written[p]);    // 128 arrivals release the buffer to the io warp
+          mbar_arrive(&io_written[p]);    // 256 arrivals release the buffer to the io warp
         }
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       }
@@ -571,7 +574,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
         mbar_wait(&tmem_full[acc], acc_phase);
         tc_fence_after();
 #pragma unroll 1
-        for (int c0 = 0; c0 < BLOCK_N; c0 += 16) {
+        for (int c0 = half * 16; c0 < BLOCK_N; c0 += 32) {  // the two warps of a lane quarter take alternate 16-column chunks
           uint32_t v[16];
           tmem_ld_32x32b_x16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BLOCK_N + c0), v);
           tmem_ld_wait();

@@ -988,10 +988,15 @@ __global__ void __launch_bounds__(224, 3) roi_align_kernel(const RoiLevels fl, c
 constexpr int kHeadThreads = 1024;  // up to 1000 ROIs per image: one row per thread, wide rank-by-counting
 constexpr int kMaxCand = 1024;  // score_thresh >= 0.5 admits at most one class per ROI, so <= 1000 candidates
 
-template <int K>
+// KT = compile-time class count (1: KAIST, 3: FLIR); KT = 0: any class count given at run time (`k_rt`, e.g. the 80
+// COCO classes of the reference's rgb_only model, demo_FLIR_save_predictions.py:58-60).  The run-time variant admits
+// one candidate per ROI - the only possibility when score_thresh >= 0.5, which its launcher requires.
+template <int KT>
 __global__ void __launch_bounds__(kHeadThreads) head_post_kernel(const float* __restrict__ head /*[B*max_props][npad]*/, int npad,
                                                                  const float4* __restrict__ props, const int* __restrict__ prop_count,
-                                                                 int max_props, HeadParams hp, DetOut out) {
+                                                                 int max_props, HeadParams hp, DetOut out, int k_rt) {
+  constexpr int K = KT ? KT : 1;       // static array extents
+  const int Kn = KT ? KT : k_rt;       // class count
   __shared__ float4 c_box[kMaxCand];
   __shared__ float c_score[kMaxCand];
   __shared__ unsigned short c_row[kMaxCand], c_cls[kMaxCand], c_order[kMaxCand];
@@ -1013,7 +1018,43 @@ __global__ void __launch_bounds__(kHeadThreads) head_post_kernel(const float* __
     bool above[K];
 #pragma unroll
     for (int k2 = 0; k2 < K; ++k2) above[k2] = false;
-    if (r < R) {
+    if (KT == 0 && r < R) {
+      // run-time class count: softmax in the same operation order (max, exp(x - max), sum in class order, divide),
+      // then only the (unique) class above the threshold is decoded
+      const float* row = hb + (size_t)r * npad;
+      float mx = -INFINITY;
+      for (int k2 = 0; k2 <= Kn; ++k2) mx = fmaxf(mx, row[k2]);
+      float den = 0.f;
+      for (int k2 = 0; k2 <= Kn; ++k2) den += expf(row[k2] - mx);
+      bool fin = true;
+      int best = -1;
+      float bestp = 0.f;
+      for (int k2 = 0; k2 <= Kn; ++k2) {
+        const float pk = __fdiv_rn(expf(row[k2] - mx), den);
+        fin &= isfinite(pk);
+        if (k2 < Kn && pk > hp.score_thresh) { best = k2; bestp = pk; }
+      }
+      const float4 p = props[(size_t)b * max_props + r];
+      const float wdt = __fsub_rn(p.z, p.x), hgt = __fsub_rn(p.w, p.y);
+      const float cx = __fadd_rn(p.x, __fmul_rn(0.5f, wdt)), cy = __fadd_rn(p.y, __fmul_rn(0.5f, hgt));
+      for (int k2 = 0; k2 < Kn; ++k2) {  // fast_rcnn.py:100-103 drops the ROI if ANY class box is non-finite
+        const float* d = row + (Kn + 1) + 4 * k2;
+        const float dx = __fdiv_rn(d[0], 10.f), dy = __fdiv_rn(d[1], 10.f);
+        const float dw = fminf(__fdiv_rn(d[2], 5.f), kScaleClamp), dh = fminf(__fdiv_rn(d[3], 5.f), kScaleClamp);
+        const float pcx = __fadd_rn(__fmul_rn(dx, wdt), cx), pcy = __fadd_rn(__fmul_rn(dy, hgt), cy);
+        const float pw = __fmul_rn(expf(dw), wdt), ph = __fmul_rn(expf(dh), hgt);
+        float4 q = make_float4(__fsub_rn(pcx, __fmul_rn(0.5f, pw)), __fsub_rn(pcy, __fmul_rn(0.5f, ph)),
+                               __fadd_rn(pcx, __fmul_rn(0.5f, pw)), __fadd_rn(pcy, __fmul_rn(0.5f, ph)));
+        fin &= finite4(q);
+        if (k2 == best) {
+          q.x = fminf(fmaxf(q.x, 0.f), hp.img_w); q.z = fminf(fmaxf(q.z, 0.f), hp.img_w);
+          q.y = fminf(fmaxf(q.y, 0.f), hp.img_h); q.w = fminf(fmaxf(q.w, 0.f), hp.img_h);
+          bx[0] = q;
+        }
+      }
+      if (fin && best >= 0) { above[0] = true; nc = 1; pr[0] = bestp; pr[1] = __int_as_float(best); }
+    }
+    if (KT != 0 && r < R) {
       const float* row = hb + (size_t)r * npad;
       float mx = -INFINITY;
 #pragma unroll
@@ -1058,7 +1099,10 @@ __global__ void __launch_bounds__(kHeadThreads) head_post_kernel(const float* __
 #pragma unroll
       for (int k2 = 0; k2 < K; ++k2)
         if (above[k2]) {
-          if (pos < kMaxCand) { c_box[pos] = bx[k2]; c_score[pos] = pr[k2]; c_row[pos] = (unsigned short)r; c_cls[pos] = (unsigned short)k2; }
+          if (pos < kMaxCand) {
+            c_box[pos] = bx[k2]; c_score[pos] = pr[k2]; c_row[pos] = (unsigned short)r;
+            c_cls[pos] = (unsigned short)(KT ? k2 : __float_as_int(pr[1]));
+          }
           ++pos;
         }
     }
@@ -1138,13 +1182,13 @@ __global__ void __launch_bounds__(kHeadThreads) head_post_kernel(const float* __
         out.scores[ob] = c_score[ci];
         out.classes[ob] = (int)c_cls[ci];
         float mx = -INFINITY;
-        for (int k2 = 0; k2 <= K; ++k2) { out.logits[ob * (K + 1) + k2] = row[k2]; mx = fmaxf(mx, row[k2]); }
-        float den = 0.f, e[K + 1];
-        for (int k2 = 0; k2 <= K; ++k2) { e[k2] = expf(row[k2] - mx); den += e[k2]; }
-        for (int k2 = 0; k2 < K; ++k2) out.probs[ob * K + k2] = __fdiv_rn(e[k2], den);
+        for (int k2 = 0; k2 <= Kn; ++k2) { out.logits[ob * (Kn + 1) + k2] = row[k2]; mx = fmaxf(mx, row[k2]); }
+        float den = 0.f;
+        for (int k2 = 0; k2 <= Kn; ++k2) den += expf(row[k2] - mx);
+        for (int k2 = 0; k2 < Kn; ++k2) out.probs[ob * Kn + k2] = __fdiv_rn(expf(row[k2] - mx), den);
         // sic: the reference indexes the per-ROI variance with the candidate-list index (quirk 1)
         const int vrow = ci < R ? ci : R - 1;
-        out.vars[ob] = expf(hb[(size_t)vrow * npad + (K + 1) + 4 * K]);
+        out.vars[ob] = expf(hb[(size_t)vrow * npad + (Kn + 1) + 4 * Kn]);
         out.roi_index[ob] = r;
       }
       emitted += __popc(bal);
@@ -1330,8 +1374,10 @@ int launch_roi_align(const RoiLevels& fl, const float4* props, const int* prop_c
 int launch_head_post(const float* head, int npad, const float4* props, const int* prop_count, int B, int max_props, int K,
                      const HeadParams& hp, const DetOut& out, cudaStream_t st) {
   if (hp.max_det > kMaxDet) return PE_ERR_UNSUPPORTED;
-  if (K == 3) head_post_kernel<3><<<B, kHeadThreads, 0, st>>>(head, npad, props, prop_count, max_props, hp, out);
-  else if (K == 1) head_post_kernel<1><<<B, kHeadThreads, 0, st>>>(head, npad, props, prop_count, max_props, hp, out);
+  if (K == 3) head_post_kernel<3><<<B, kHeadThreads, 0, st>>>(head, npad, props, prop_count, max_props, hp, out, 3);
+  else if (K == 1) head_post_kernel<1><<<B, kHeadThreads, 0, st>>>(head, npad, props, prop_count, max_props, hp, out, 1);
+  else if (K >= 2 && K <= 1000 && hp.score_thresh >= 0.5f)  // e.g. the 80 COCO classes of the rgb_only zoo model
+    head_post_kernel<0><<<B, kHeadThreads, 0, st>>>(head, npad, props, prop_count, max_props, hp, out, K);
   else return PE_ERR_UNSUPPORTED;
   PE_LAUNCH_CHECK();
   return PE_OK;

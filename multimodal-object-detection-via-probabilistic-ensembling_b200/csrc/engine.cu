@@ -410,7 +410,10 @@ struct Runner {
 extern "C" PE_API int pe_detector_create(const pe_detector_config* cfg, pe_detector** out) {
   if (!cfg || !out) return PE_ERR_INVALID_ARGUMENT;
   if (cfg->depth != 50 && cfg->depth != 101) return PE_ERR_UNSUPPORTED;
-  if (cfg->num_classes != 1 && cfg->num_classes != 3) return PE_ERR_UNSUPPORTED;
+  // K = 1 (KAIST) and K = 3 (FLIR) have compile-time head kernels; any other class count up to 1000 (the 80 COCO classes
+  // of the reference's rgb_only zoo model) takes the run-time variant, which needs score_thresh >= 0.5 (one class per ROI)
+  if (cfg->num_classes < 1 || cfg->num_classes > 1000) return PE_ERR_UNSUPPORTED;
+  if (cfg->num_classes != 1 && cfg->num_classes != 3 && !(cfg->score_thresh >= 0.5f)) return PE_ERR_UNSUPPORTED;
   if (cfg->max_batch < 1 || cfg->canvas_h % 32 || cfg->canvas_w % 32 || cfg->canvas_h < 64 || cfg->canvas_w < 64) return PE_ERR_INVALID_ARGUMENT;
   if (cfg->middle_fusion ? cfg->in_channels != 6 : (cfg->in_channels < 1 || cfg->in_channels > 4)) return PE_ERR_INVALID_ARGUMENT;
   if (cfg->pre_nms_topk < 1 || cfg->pre_nms_topk > pe::kTopkSlots || cfg->post_nms_topk < 1 || cfg->post_nms_topk > pe::kMaxProps)

@@ -27,6 +27,29 @@ def instances_to_coco_json(boxes, scores, classes, image_id):
     return out
 
 
+def contiguous_to_dataset_ids(categories):
+    """Reverse of ``thing_dataset_id_to_contiguous_id``: ``load_coco_json`` maps the sorted dataset category ids to
+    0..C-1 (data/datasets/coco.py:87-88) and the evaluator un-maps every prediction before COCOeval
+    (FLIR_evaluation.py:163-175).  Returns the list ``dataset_id[contiguous]``; ``None`` when the annotation file
+    carries no category table (ids are then taken as they are)."""
+    if not categories:
+        return None
+    return sorted(int(c["id"]) for c in categories)
+
+
+def unmap_category_ids(detections, categories):
+    """FLIR_evaluation.py:163-175: contiguous class index -> dataset category id, in place; an index without a
+    category is an error exactly as in the reference (``assert category_id in reverse_id_mapping``)."""
+    ids = contiguous_to_dataset_ids(categories)
+    if ids is None:
+        return detections
+    for d in detections:
+        c = d["category_id"]
+        assert 0 <= c < len(ids), "A prediction has category_id={}, which is not available in the dataset.".format(c)
+        d["category_id"] = ids[c]
+    return detections
+
+
 def bbox_iou(dt, gt, iscrowd):
     """maskApi bbIou: dt (D,4) xywh, gt (G,4) xywh -> (D,G); crowd gt uses the detection area as union."""
     dt = np.asarray(dt, np.float64).reshape(-1, 4)

@@ -6,10 +6,11 @@
 ``random_state_dict`` makes seeded synthetic weights for tests / benchmarks (no checkpoints are available
 offline).  Plain detectron2 init overflows through the residual stack, so the last
 norm of each block is down-scaled and the heads are widened until the detector emits proposals and
-detections like a trained model does.  ``load_checkpoint`` reads a ``.pth`` the way
-detectron2/checkpoint/detection_checkpoint.py:26-45 does (bare state dict or {"model": ...}).
+detections like a trained model does.  ``load_checkpoint`` reads a ``.pth`` (bare state dict or {"model": ...}) or a
+Detectron2 model-zoo ``.pkl`` the way detectron2/checkpoint/detection_checkpoint.py:26-45 does.
 """
 import math
+import pickle
 
 import torch
 
@@ -78,8 +79,51 @@ def random_state_dict(depth=50, in_channels=3, num_classes=3, seed=0, middle_fus
     return sd
 
 
-def load_checkpoint(path):
-    obj = torch.load(path, map_location="cpu")
-    if isinstance(obj, dict) and "model" in obj and isinstance(obj["model"], dict):
-        obj = obj["model"]
-    return {k: (v if isinstance(v, torch.Tensor) else torch.as_tensor(v)) for k, v in obj.items()}
+class _NumpyOnlyUnpickler(pickle.Unpickler):
+    """Model-zoo ``.pkl`` files are plain dicts of numpy arrays and strings; nothing else is allowed to be constructed."""
+
+    _ALLOWED = {("numpy.core.multiarray", "_reconstruct"), ("numpy._core.multiarray", "_reconstruct"), ("numpy", "ndarray"),
+                ("numpy", "dtype"), ("numpy.core.multiarray", "scalar"), ("numpy._core.multiarray", "scalar"),
+                ("collections", "OrderedDict"), ("_codecs", "encode")}
+
+    def find_class(self, module, name):
+        if (module, name) not in self._ALLOWED:
+            raise pickle.UnpicklingError("refusing to unpickle %s.%s from a checkpoint" % (module, name))
+        return super().find_class(module, name)
+
+
+def _load_pkl(path):
+    """detectron2/checkpoint/detection_checkpoint.py:26-39: a ``.pkl`` in the Detectron2 model-zoo format is
+    ``{"model": {name: ndarray}, "__author__": ...}`` with the same parameter names as a ``.pth`` state dict.  Caffe2 /
+    Detectron1 files (no ``__author__``; names matched by heuristics, c2_model_loading.py) are outside the path."""
+    with open(path, "rb") as f:
+        data = _NumpyOnlyUnpickler(f, encoding="latin1").load()
+    if not (isinstance(data, dict) and "model" in data and "__author__" in data):
+        raise RuntimeError("%s is not a Detectron2 model-zoo .pkl (Caffe2 / Detectron1 checkpoints need name-matching "
+                           "heuristics that are not part of this path; convert them with the reference first)" % path)
+    return data["model"]
+
+
+def load_checkpoint(path, num_classes=None):
+    """``.pth`` (bare state dict or ``{"model": ...}``) or model-zoo ``.pkl`` -> {name: float tensor}
+    (detection_checkpoint.py:26-45).  ``.pth`` files are read with ``weights_only=True``: a checkpoint cannot run code.
+    A zoo model has no ``roi_heads.box_predictor.var_pred`` (the fork's variance head): the reference leaves that layer at
+    its unseeded random init (fast_rcnn.py:509-512), so its ``vars`` output for such a model is noise; here the layer is
+    zero-filled (variance 1) and a note is printed."""
+    if str(path).endswith(".pkl"):
+        obj = _load_pkl(path)
+    else:
+        obj = torch.load(path, map_location="cpu", weights_only=True)
+        if isinstance(obj, dict) and "model" in obj and isinstance(obj["model"], dict):
+            obj = obj["model"]
+    sd = {k: (v if isinstance(v, torch.Tensor) else torch.as_tensor(v)) for k, v in obj.items() if not isinstance(v, (str, bytes))}
+    q = "roi_heads.box_predictor.var_pred"
+    if q + ".weight" not in sd and "roi_heads.box_predictor.cls_score.weight" in sd:
+        print("checkpoint %s has no %s: variance head zero-filled (vars = 1)" % (path, q))
+        sd[q + ".weight"] = torch.zeros(1, sd["roi_heads.box_predictor.cls_score.weight"].shape[1])
+        sd[q + ".bias"] = torch.zeros(1)
+    if num_classes is not None and "roi_heads.box_predictor.cls_score.weight" in sd:
+        k = sd["roi_heads.box_predictor.cls_score.weight"].shape[0] - 1
+        if k != num_classes:
+            raise RuntimeError("checkpoint %s has %d classes, the model was configured for %d" % (path, k, num_classes))
+    return sd

@@ -42,9 +42,10 @@ def _make_dataset(root, n=5):
         images.append({"id": 1000 + i, "file_name": "thermal_8_bit/%s.jpeg" % stem, "height": 128, "width": 160})
         for k in range(3):
             x, y = rng.uniform(0, 100), rng.uniform(0, 80)
-            anns.append({"id": len(anns) + 1, "image_id": 1000 + i, "category_id": int(rng.integers(0, 3)),
+            anns.append({"id": len(anns) + 1, "image_id": 1000 + i, "category_id": int(rng.integers(1, 4)),
                          "bbox": [float(x), float(y), 40.0, 30.0], "area": 1200.0, "iscrowd": 0})
-    cats = [{"id": c, "name": n_} for c, n_ in enumerate(["person", "bicycle", "car"])]
+    # FLIR-style 1-based dataset category ids: the evaluator must un-map contiguous class indices (FLIR_evaluation.py:163-175)
+    cats = [{"id": c + 1, "name": n_} for c, n_ in enumerate(["person", "bicycle", "car"])]
     json.dump({"images": images, "annotations": anns, "categories": cats}, open(os.path.join(root, "FLIR_thermal_RGBT_pairs_val.json"), "w"))
 
 
@@ -84,6 +85,7 @@ def test_save_predictions_then_proben(workdir):
     assert res is not None and set(("AP", "AP50", "AP75", "APs", "APm", "APl")) <= set(res)
     fused = json.load(open(os.path.join(out, "probEn_probEn_v-avg_fused.json")))
     assert all(set(d) == {"image_id", "category_id", "bbox", "score"} for d in fused)
+    assert all(d["category_id"] in (1, 2, 3) for d in fused)  # dataset ids, not contiguous indices
     # that run read the binary columnar files written next to the JSONs; the JSON path must give the same result
     for f in os.listdir(out):
         if f.endswith(".pedet"):
@@ -92,6 +94,29 @@ def test_save_predictions_then_proben(workdir):
                             "--box_fusion", "v-avg", "--outfolder", out])
     assert res_json == pytest.approx(res, nan_ok=True)
     assert json.load(open(os.path.join(out, "probEn_probEn_v-avg_fused.json"))) == fused
+
+
+def test_rgb_only_with_model_zoo_pkl(workdir):
+    """The reference CLI's first branch (demo_FLIR_save_predictions.py:58-60): rgb_only = the 80-class COCO zoo model,
+    read from a Detectron2 model-zoo ``.pkl``; only classes <= 2 reach the JSON (:148-164), probs rows have 80 entries."""
+    import pickle
+    save = _load_cli("demo_FLIR_save_predictions")
+    sd = weights.random_state_dict(50, 3, 80, seed=27, head_gain=3.0)
+    # make the three FLIR-relevant COCO classes win often enough that rows survive the class <= 2 filter
+    sd["roi_heads.box_predictor.cls_score.bias"][:3] += 1.5
+    ck = os.path.join(workdir, "model_final_zoo.pkl")
+    pickle.dump({"model": {k: v.numpy() for k, v in sd.items() if "var_pred" not in k}, "__author__": "Detectron2 Model Zoo"}, open(ck, "wb"))
+    out = os.path.join(workdir, "out_rgb") + "/"
+    args = config_parser(["--dataset_path", os.path.join(workdir, "val"), "--fusion_method", "rgb_only", "--model_path", ck, "--outfolder", out])
+    pred = json.load(open(save.save_predictions(args, batch=2, depth=50)))
+    assert tuple(pred.keys()) == SCHEMA and len(pred["boxes"]) == 5
+    n = 0
+    for i in range(5):
+        assert all(c <= 2 for c in pred["classes"][i])
+        assert all(len(p) == 80 for p in pred["probs"][i]) and all(len(l) == 81 for l in pred["class_logits"][i])
+        assert all(v == [1.0] for v in pred["vars"][i])  # zoo models carry no variance head: zero-filled -> exp(0)
+        n += len(pred["boxes"][i])
+    assert n > 0
 
 
 def test_single_model_map_cli(workdir):

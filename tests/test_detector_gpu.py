@@ -149,7 +149,7 @@ def test_end_to_end_detections_reasonable(small_case):
         assert float(hit) >= 0.5, float(hit)
 
 
-@pytest.mark.parametrize("variant", ["early_fusion", "middle_fusion", "kaist_k1", "r101"])
+@pytest.mark.parametrize("variant", ["early_fusion", "middle_fusion", "kaist_k1", "r101", "coco_k80"])
 def test_detector_variants_features_close(variant):
     """BASELINE.json configs 4-5: 4-channel early fusion, 6-channel middle fusion (shared backbone on both halves,
     512-channel RPN / ROI heads), K = 1 (KAIST) and the R101 depth the FLIR demos use: backbone features and RPN
@@ -157,10 +157,10 @@ def test_detector_variants_features_close(variant):
     ENGINE's own head outputs (exact)."""
     mid = variant == "middle_fusion"
     c = {"early_fusion": 4, "middle_fusion": 6}.get(variant, 3)
-    K = 1 if variant == "kaist_k1" else 3
+    K = {"kaist_k1": 1, "coco_k80": 80}.get(variant, 3)  # K = 80: the rgb_only zoo model (demo_FLIR_save_predictions.py:58-60)
     depth = 101 if variant == "r101" else 50
     mean = (103.530, 116.280, 123.675, 135.438, 135.438, 135.438)[:c]
-    sd = weights.random_state_dict(depth, 3 if mid else c, K, seed=40 + c + K, middle_fusion=mid)
+    sd = weights.random_state_dict(depth, 3 if mid else c, K, seed=40 + c + K, middle_fusion=mid, head_gain=3.0 if K == 80 else 1.0)
     cfg = D.DetCfg(depth=depth, in_channels=c, num_classes=K, pixel_mean=mean, pixel_std=(1.0,) * c, middle_fusion=mid)
     g = torch.Generator().manual_seed(7)
     imgs = [torch.rand(c, 160, 200, generator=g) * 255 for _ in range(2)]

@@ -90,3 +90,42 @@ def test_resize_shape_rule():
     from probenb200.detector import resize_shortest_edge_shape
     assert resize_shortest_edge_shape(512, 640) == (800, 1000)
     assert resize_shortest_edge_shape(480, 1920) == (333, 1333)
+
+
+def test_category_ids_are_unmapped_like_flirevaluator():
+    """FLIR_evaluation.py:163-175 / coco.py:87-88: contiguous class index -> sorted dataset category ids (1-based in
+    FLIR-style files); without the un-mapping every class is off by one and AP collapses."""
+    anns = [dict(a, category_id=a["category_id"] + 1) for a in _gt()]
+    cats = [{"id": 3, "name": "car"}, {"id": 1, "name": "person"}, {"id": 2, "name": "bicycle"}]  # unsorted on purpose
+    assert evaluation.contiguous_to_dataset_ids(cats) == [1, 2, 3]
+    dets = []
+    for a in anns:
+        b = a["bbox"]
+        dets += evaluation.instances_to_coco_json([[b[0], b[1], b[0] + b[2], b[1] + b[3]]], [0.9], [a["category_id"] - 1], a["image_id"])
+    wrong = evaluation.COCOBBoxEval(anns, [dict(d) for d in dets]).evaluate()
+    assert wrong["AP"] < 50
+    evaluation.unmap_category_ids(dets, cats)
+    assert abs(evaluation.COCOBBoxEval(anns, dets).evaluate()["AP"] - 100) < 1e-9
+    with pytest.raises(AssertionError):
+        evaluation.unmap_category_ids([{"category_id": 3}], cats)
+    assert evaluation.unmap_category_ids([{"category_id": 2}], None) == [{"category_id": 2}]
+
+
+def test_stale_pedet_sidecar_is_not_used(tmp_path):
+    import importlib.util
+    import os
+    import time
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    spec = importlib.util.spec_from_file_location("cli_demo_probEn_host", os.path.join(root, "demo", "FLIR", "demo_probEn.py"))
+    cli = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(cli)
+    j, b = str(tmp_path / "a.json"), str(tmp_path / "a.pedet")
+    open(b, "w").write("x")
+    assert cli._fresh_sidecars([j], [b], False)            # no JSON beside it: the sidecar is the only source
+    open(j, "w").write("{}")
+    os.utime(b, (time.time() - 100, time.time() - 100))
+    assert not cli._fresh_sidecars([j], [b], False)        # JSON regenerated after the sidecar
+    assert cli._fresh_sidecars([j], [b], True)             # --binary forces it
+    os.utime(b, None)
+    assert cli._fresh_sidecars([j], [b], False)
+    assert not cli._fresh_sidecars([j], [str(tmp_path / "missing.pedet")], True)
