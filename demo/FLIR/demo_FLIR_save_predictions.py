@@ -74,8 +74,53 @@ def extra_flags(argv):
     return ap.parse_known_args(argv)
 
 
+def row_width(K):
+    return 1 + detector.MAX_DET * (4 + 1 + 1 + (K + 1) + K + 1)
+
+
+def detection_rows(buf, n):
+    """The first n images of a ``DetectionBuffers`` as one float32 row each: count | boxes | scores | classes | logits | probs | vars
+    (fixed stride, stays on the device: this is what the multi-GPU gather moves)."""
+    return torch.cat([buf.counts[:n, None].float(), buf.boxes[:n].reshape(n, -1), buf.scores[:n], buf.classes[:n].float(),
+                      buf.class_logits[:n].reshape(n, -1), buf.probs[:n].reshape(n, -1), buf.vars[:n]], 1)
+
+
+def rows_to_instances(rows, K, hw):
+    """Inverse of ``detection_rows`` on the host -> list of Instances with the fork's fields (fast_rcnn.py:133-145)."""
+    from probenb200.structures import Boxes, Instances
+    D = detector.MAX_DET
+    out = []
+    for r in rows:
+        n = int(r[0])
+        o = 1
+        inst = Instances(hw)
+        inst.pred_boxes = Boxes(r[o:o + 4 * D].view(D, 4)[:n].clone()); o += 4 * D
+        inst.scores = r[o:o + D][:n].clone(); o += D
+        inst.pred_classes = r[o:o + D][:n].to(torch.int64); o += D
+        inst.class_logits = r[o:o + D * (K + 1)].view(D, K + 1)[:n].clone(); o += D * (K + 1)
+        inst.prob_score = r[o:o + D * K].view(D, K)[:n].clone(); o += D * K
+        inst.vars = r[o:o + D][:n].clone().view(-1, 1)
+        out.append(inst)
+    return out
+
+
+def dist_setup():
+    """(rank, world) from the torchrun environment; initialises NCCL and selects cuda:LOCAL_RANK when world > 1."""
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if world <= 1:
+        return 0, 1
+    import torch.distributed as dist
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    if not dist.is_initialized():
+        dist.init_process_group("nccl", device_id=torch.device("cuda:%d" % local))
+    return dist.get_rank(), world
+
+
 def save_predictions(args, batch=8, depth=101, cpu_decode=False):
     from probenb200 import io as pio
+    from probenb200.pipeline import shard_range
+    rank, world = dist_setup()
     val_folder = args.dataset_path
     val_json_path = val_folder + "/FLIR_thermal_RGBT_pairs_val.json"
     rgb_path, t_path = val_folder + "/RGB/", val_folder + "/thermal_8_bit/"
@@ -97,6 +142,7 @@ def save_predictions(args, batch=8, depth=101, cpu_decode=False):
     sd = weights.load_checkpoint(model_path, num_classes=K)
     print("model loaded:", model_path)
     decoder = None if cpu_decode else pio.JpegDecoder()
+    shard = shard_range(len(stems), rank, world)
 
     def load_batch(names):
         """uint8 device frames [B, H, W, C] of the pairs `names` (file stems), C = 3 / 4 / 6."""
@@ -110,23 +156,36 @@ def save_predictions(args, batch=8, depth=101, cpu_decode=False):
     net_hw = detector.resize_shortest_edge_shape(h0, w0)
     canvas = ((net_hw[0] + 31) // 32 * 32, (net_hw[1] + 31) // 32 * 32)
     det = detector.Detector(sd, depth=depth, num_classes=K, max_batch=batch, canvas=canvas,
-                            score_thresh=0.5, **mcfg)
-    out = {k: [] for k in ("image", "boxes", "scores", "classes", "image_id", "class_logits", "probs", "vars")}
-    for i0 in range(0, len(stems), batch):
-        names = stems[i0:i0 + batch]
+                            score_thresh=0.5, device="cuda:%d" % torch.cuda.current_device(), **mcfg)
+    # multi-GPU: `torchrun --nproc-per-node N demo/FLIR/demo_FLIR_save_predictions.py ...` shards the pairs contiguously over
+    # the ranks (InferenceSampler's rule, data/samplers/distributed_sampler.py:190-193); every rank keeps its detections as
+    # fixed-stride device rows and rank 0 receives them through one padded NCCL all-gather (the reference pickles them through
+    # gloo, evaluation/FLIR_evaluation.py:125-131) and writes the JSON.  Single process: the shard is the whole set.
+    lo, hi = shard
+    rows = []
+    for i0 in range(lo, hi, batch):
+        names = stems[i0:min(i0 + batch, hi)]
         frames = load_batch(names)
         # 3-channel uint8 frames take Pillow's resize in the reference, 4-/6-channel arrays cv2's float path
-        res = det.forward_frames_device(frames, net_hw, round_u8=frames.shape[3] == 3).to_instances([(h0, w0)] * len(names))
-        for j, (n, inst) in enumerate(zip(names, res)):
-            inst = inst[inst.pred_classes <= 2]
-            out["image"].append(files_names[i0 + j] if i0 + j < len(files_names) else n + ".jpg")
-            out["image_id"].append(name_to_id[n])
-            out["boxes"].append(inst.pred_boxes.tensor.tolist())
-            out["scores"].append(inst.scores.tolist())
-            out["classes"].append(inst.pred_classes.tolist())
-            out["class_logits"].append(inst.class_logits.tolist())
-            out["probs"].append(inst.prob_score.tolist())
-            out["vars"].append(inst.vars.tolist())
+        buf = det.forward_frames_device(frames, net_hw, round_u8=frames.shape[3] == 3)
+        rows.append(detection_rows(buf, len(names)))
+    rows = torch.cat(rows) if rows else torch.zeros((0, row_width(K)), device="cuda")
+    if world > 1:
+        from probenb200 import pipeline
+        rows = torch.cat(pipeline.all_gather_ragged(rows))
+        if rank != 0:
+            return None
+    out = {k: [] for k in ("image", "boxes", "scores", "classes", "image_id", "class_logits", "probs", "vars")}
+    for i, (n, inst) in enumerate(zip(stems, rows_to_instances(rows.cpu(), K, (h0, w0)))):
+        inst = inst[inst.pred_classes <= 2]
+        out["image"].append(files_names[i] if i < len(files_names) else n + ".jpg")
+        out["image_id"].append(name_to_id[n])
+        out["boxes"].append(inst.pred_boxes.tensor.tolist())
+        out["scores"].append(inst.scores.tolist())
+        out["classes"].append(inst.pred_classes.tolist())
+        out["class_logits"].append(inst.class_logits.tolist())
+        out["probs"].append(inst.prob_score.tolist())
+        out["vars"].append(inst.vars.tolist())
     path = join(args.outfolder, "val_" + method + "_predictions.json")
     with open(path, "w") as f:
         json.dump(out, f, indent=2)
@@ -140,3 +199,7 @@ def save_predictions(args, batch=8, depth=101, cpu_decode=False):
 if __name__ == "__main__":
     extra, rest = extra_flags(sys.argv[1:])
     save_predictions(config_parser(rest), batch=extra.batch, depth=extra.depth, cpu_decode=extra.cpu_decode)
+    if int(os.environ.get("WORLD_SIZE", "1")) > 1:
+        import torch.distributed as dist
+        dist.barrier()
+        dist.destroy_process_group()

@@ -93,6 +93,12 @@ typedef struct pe_conv_desc {
 } pe_conv_desc;
 PE_API int pe_conv2d_fwd(const pe_conv_desc* desc, const void* x, const void* w, const float* bias,
                          const void* residual, void* y, void* stream);
+/* 1x1 conv over TWO inputs as one GEMM: y = act([x | x2] . w + bias), w = [Cout][Cin + cin2] bf16, x2 = [N, h2, w2, cin2] bf16
+ * read at `stride2` (1 | 2) so that it lands on x's H x W grid.  This is how the engine runs the first bottleneck block of a
+ * stage: out = relu(conv3(t) + shortcut(x)) (modeling/backbone/resnet.py:205-221) = relu([t | x] . [W3 | Wsc] + b3 + bsc): the
+ * projection-shortcut tensor is never written to HBM.  desc: KH = KW = 1, stride = 1, residual_mode = 0, Cin % 64 == 0. */
+PE_API int pe_conv1x1_dual_fwd(const pe_conv_desc* desc, const void* x, const void* x2, int cin2, int h2, int w2, int stride2,
+                               const void* w, const float* bias, void* y, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Detector engine: the inference path of detectron2/modeling/meta_arch/rcnn.py:219-267 (GeneralizedRCNN with
@@ -101,7 +107,8 @@ PE_API int pe_conv2d_fwd(const pe_conv_desc* desc, const void* x, const void* w,
  *   weights    one blob laid out per the manifest pe_detector_param_info() publishes (the host folds
  *              FrozenBatchNorm2d into conv weights/biases and repacks to [Cout][KH][KW][Cin] bf16; kinds:
  *              0 conv+BN, 1 conv+bias, 2 stem 7x7 as [64][Kpad] fp16, 3 RPN objectness|deltas rows,
- *              4 fc1 with (c,ph,pw)->(ph,pw,c) column permutation, 5 linear, 6 cls|bbox|var predictor rows);
+ *              4 fc1 with (c,ph,pw)->(ph,pw,c) column permutation, 5 linear, 6 cls|bbox|var predictor rows,
+ *              7 first-block conv3 with the block's projection shortcut appended along K, see pe_conv1x1_dual_fwd);
  *   workspace  pe_detector_workspace_bytes() of scratch; pe_detector_buffer_info() exposes named
  *              intermediates (p2..p6, rpn_out2..6, proposals, roi_feats, head_out, ...) for stage-wise parity tests;
  *   images     [B, in_channels, img_h, img_w] float32 (what GeneralizedRCNN.forward receives in

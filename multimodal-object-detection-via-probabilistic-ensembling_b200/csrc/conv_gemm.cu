@@ -45,7 +45,10 @@ struct ConvArgs {
   int N, Ho, Wo, Cin, Cout;
   int KH, KW, pad;
   int TH, TW, tiles_h, tiles_w, tiles_n;
+  uint32_t mul_tiles_n, mul_tiles_w, mul_tiles_h;  // fast_div multipliers of the tile decomposition
   int k_chunks;  // ceil(Cin / 64)
+  int k_chunks1; // dual-input 1x1 (bottleneck conv3 + projection shortcut as ONE GEMM over K = [t2 | x]): chunks [0, k_chunks1) come
+                 // from map_a, the rest from map_a2 (the block input, strided for stride-2 stages); == k_chunks otherwise
   int relu, residual_mode, out_fp32, in_fp16;
   int halo;             // 3x3: one (TH+2)x(TW+2) halo tile per K chunk in smem, the 9 taps are shifted UMMA descriptors
   int a_stages, b_stages, b_resident;  // halo mode: A-halo ring / weight-tile ring depths; weights stay resident if they fit
@@ -128,6 +131,18 @@ __device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bu
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
 }
+
+// One lane of a converged warp (the same lane every time).  The producer and MMA warps run their loops warp-uniformly and
+// predicate only the TMA / tcgen05 instructions with this: loop state then lives in uniform registers, and the issue path of
+// an MMA is a handful of instructions (with the whole role inside `if (lane == 0)` the compiler emitted an
+// ELECT / R2UR.BROADCAST sequence per operand and ~75 instructions per 4 MMAs, which made N <= 128 layers issue-bound).
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+  return pred != 0;
+}
+// n / d for n * d < 2^32 as one multiply-high (mul = ceil(2^32 / d); d == 1 is encoded as mul == 0)
+__device__ __forceinline__ uint32_t fast_div(uint32_t n, uint32_t mul) { return mul ? __umulhi(n, mul) : n; }
 
 // K-major, 128B-swizzled smem tile: rows of 128 B, 8-row groups 1024 B apart (cute UMMA::SmemDescriptor).
 // Un-swizzled K-major operand whose rows are only 16 B apart (stem row mode): a core matrix is 8 rows x 16 B =
@@ -235,7 +250,8 @@ __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
 template <int BLOCK_N, bool kStaged>
 __global__ void __launch_bounds__(kThreads, 1)
 conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
-                 const __grid_constant__ CUtensorMap map_out, const __grid_constant__ CUtensorMap map_res, const ConvArgs a) {
+                 const __grid_constant__ CUtensorMap map_out, const __grid_constant__ CUtensorMap map_res,
+                 const __grid_constant__ CUtensorMap map_a2, const ConvArgs a) {
   using Cfg = TileCfg<BLOCK_N, kStaged>;
   extern __shared__ unsigned char smem_dyn[];
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~(uintptr_t)1023);
@@ -266,6 +282,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&map_a);
     tma_prefetch_desc(&map_b);
+    if (a.k_chunks1 < a.k_chunks) tma_prefetch_desc(&map_a2);
     if (kStaged) {
       tma_prefetch_desc(&map_out);
       if (a.residual_mode) tma_prefetch_desc(&map_res);
@@ -294,131 +311,183 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
+  // tile -> (n tile, patch column, patch row, image) without integer division
+  auto decompose = [&](int tile, int& nt, int& tw, int& th, int& img) {
+    const uint32_t mt = fast_div((uint32_t)tile, a.mul_tiles_n);
+    nt = tile - (int)mt * a.tiles_n;
+    const uint32_t r = fast_div(mt, a.mul_tiles_w);
+    tw = (int)mt - (int)r * a.tiles_w;
+    img = (int)fast_div(r, a.mul_tiles_h);
+    th = (int)r - img * a.tiles_h;
+  };
+
   if (warp == 0) {
-    // ================================ TMA producer ================================
-    if (lane == 0) {
-      int stage = 0, hstage = 0;
-      uint32_t phase = 0, hphase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const int nt = tile % a.tiles_n, mt = tile / a.tiles_n;
-        const int tw = mt % a.tiles_w, th = (mt / a.tiles_w) % a.tiles_h, img = mt / (a.tiles_w * a.tiles_h);
-        const int h0 = th * a.TH - a.pad, w0 = tw * a.TW - a.pad, n0 = nt * BLOCK_N;
-        if (a.halo) {  // one halo tile per K chunk, then the 9 weight tiles of that chunk
-          for (int kc = 0; kc < a.k_chunks; ++kc) {
-            mbar_wait(&a_empty[hstage], hphase ^ 1);
+    // ================================ TMA producer (warp-uniform loops, one elected lane issues) ================================
+    const bool leader = elect_one();
+    int stage = 0, hstage = 0;
+    uint32_t phase = 0, hphase = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      int nt, tw, th, img;
+      decompose(tile, nt, tw, th, img);
+      const int h0 = th * a.TH - a.pad, w0 = tw * a.TW - a.pad, n0 = nt * BLOCK_N;
+      const bool first = tile == (int)blockIdx.x;
+      if (a.halo) {  // one halo tile per K chunk, then the 9 weight tiles of that chunk
+        for (int kc = 0; kc < a.k_chunks; ++kc) {
+          mbar_wait(&a_empty[hstage], hphase ^ 1);
+          if (leader) {
             mbar_expect_tx(&a_full[hstage], kHaloRows * 128);
             tma_load_4d(&map_a, &a_full[hstage], smem + hstage * kHaloBytes, kc * kBlockK, w0, h0, img);
-            if (++hstage == a.a_stages) { hstage = 0; hphase ^= 1; }
-            if (a.b_resident && tile != (int)blockIdx.x) continue;  // weights were loaded with the first tile and stay
-            for (int tap = 0; tap < 9; ++tap) {
-              mbar_wait(&b_empty[stage], phase ^ 1);
+          }
+          if (++hstage == a.a_stages) { hstage = 0; hphase ^= 1; }
+          if (a.b_resident && !first) continue;  // weights were loaded with the first tile and stay
+          for (int tap = 0; tap < 9; ++tap) {
+            mbar_wait(&b_empty[stage], phase ^ 1);
+            if (leader) {
               mbar_expect_tx(&b_full[stage], Cfg::kBBytes);
               tma_load_2d(&map_b, &b_full[stage], halo_b + stage * Cfg::kBBytes, tap * a.Cin + kc * kBlockK, n0);
-              if (++stage == a.b_stages) { stage = 0; phase ^= 1; }
             }
+            if (++stage == a.b_stages) { stage = 0; phase ^= 1; }
           }
-          continue;
         }
-        if (a.stem_mode == 2) {  // one stage per tile: the 7 canvas row segments under this run of 128 outputs
-          if (tile == (int)blockIdx.x) {
-            mbar_expect_tx(&b_full[0], kStemWBytes);
-            for (int kh = 0; kh < 7; ++kh) tma_load_2d(&map_b, &b_full[0], stem_w + kh * 4096, kh * 32, 0);
-          }
-          mbar_wait(&empty_bar[stage], phase ^ 1);
+        continue;
+      }
+      if (a.stem_mode == 2) {  // one stage per tile: the 7 canvas row segments under this run of 128 outputs
+        if (first && leader) {
+          mbar_expect_tx(&b_full[0], kStemWBytes);
+          for (int kh = 0; kh < 7; ++kh) tma_load_2d(&map_b, &b_full[0], stem_w + kh * 4096, kh * 32, 0);
+        }
+        mbar_wait(&empty_bar[stage], phase ^ 1);
+        if (leader) {
           unsigned char* sa = smem + stage * Cfg::kStageBytes;
           mbar_expect_tx(&full_bar[stage], 7 * kStemRowBytes);
-          const int ho = th * a.TH, wo0 = tw * a.TW;
-          for (int kh = 0; kh < 7; ++kh)
-            bulk_load_1d(sa + kh * kStemRowPitch,
-                         a.canvas + (((size_t)img * a.canvas_hp + 2 * ho + kh) * a.canvas_wp + 2 * wo0) * 8, kStemRowBytes, &full_bar[stage]);
-          if (++stage == n_stages) { stage = 0; phase ^= 1; }
-          continue;
+          const unsigned char* src = a.canvas + (((size_t)img * a.canvas_hp + 2 * (th * a.TH)) * a.canvas_wp + 2 * (tw * a.TW)) * 8;
+          const size_t row_pitch = (size_t)a.canvas_wp * 8;
+#pragma unroll
+          for (int kh = 0; kh < 7; ++kh) bulk_load_1d(sa + kh * kStemRowPitch, src + kh * row_pitch, kStemRowBytes, &full_bar[stage]);
         }
-        if (a.stem_mode) {  // 7 row taps, each one 64-byte chunk per pixel: A rows (2*ho + kh) of the canvas
-          for (int kh = 0; kh < 7; ++kh) {
-            mbar_wait(&empty_bar[stage], phase ^ 1);
+        if (++stage == n_stages) { stage = 0; phase ^= 1; }
+        continue;
+      }
+      if (a.stem_mode) {  // 7 row taps, each one 64-byte chunk per pixel: A rows (2*ho + kh) of the canvas
+        for (int kh = 0; kh < 7; ++kh) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          if (leader) {
             unsigned char* sa = smem + stage * Cfg::kStageBytes;
             unsigned char* sb = sa + Cfg::kABytes;
             mbar_expect_tx(&full_bar[stage], (kBlockM + BLOCK_N) * 64);
             tma_load_5d(&map_a, &full_bar[stage], sa, 0, w0, kh & 1, h0 + (kh >> 1), img);
             tma_load_2d(&map_b, &full_bar[stage], sb, kh * 32, n0);
-            if (++stage == n_stages) { stage = 0; phase ^= 1; }
           }
-          continue;
+          if (++stage == n_stages) { stage = 0; phase ^= 1; }
         }
-        for (int kh = 0; kh < a.KH; ++kh)
-          for (int kw = 0; kw < a.KW; ++kw)
-            for (int kc = 0; kc < a.k_chunks; ++kc) {
-              mbar_wait(&empty_bar[stage], phase ^ 1);
+        continue;
+      }
+      for (int kh = 0; kh < a.KH; ++kh)
+        for (int kw = 0; kw < a.KW; ++kw)
+          for (int kc = 0; kc < a.k_chunks; ++kc) {
+            mbar_wait(&empty_bar[stage], phase ^ 1);
+            if (leader) {
               unsigned char* sa = smem + stage * Cfg::kStageBytes;
               unsigned char* sb = sa + Cfg::kABytes;
               mbar_expect_tx(&full_bar[stage], Cfg::kStageBytes);
-              tma_load_4d(&map_a, &full_bar[stage], sa, kc * kBlockK, w0 + kw, h0 + kh, img);
+              if (kc < a.k_chunks1) tma_load_4d(&map_a, &full_bar[stage], sa, kc * kBlockK, w0 + kw, h0 + kh, img);
+              else tma_load_4d(&map_a2, &full_bar[stage], sa, (kc - a.k_chunks1) * kBlockK, w0, h0, img);
               tma_load_2d(&map_b, &full_bar[stage], sb, (kh * a.KW + kw) * a.Cin + kc * kBlockK, n0);
-              if (++stage == n_stages) { stage = 0; phase ^= 1; }
             }
-      }
+            if (++stage == n_stages) { stage = 0; phase ^= 1; }
+          }
     }
   } else if (warp == 1) {
-    // ================================ MMA issuer ================================
-    if (lane == 0) {
-      const uint32_t idesc = umma_instr_desc(kBlockM, BLOCK_N, a.in_fp16 != 0);
-      int stage = 0, hstage = 0;
-      uint32_t phase = 0, hphase = 0;
-      int acc = 0;
-      uint32_t acc_phase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+    // ================================ MMA issuer (warp-uniform loops, one elected lane issues) ================================
+    const bool leader = elect_one();
+    const uint32_t idesc = umma_instr_desc(kBlockM, BLOCK_N, a.in_fp16 != 0);
+    const uint32_t smem0 = smem_u32(smem);
+    int stage = 0, hstage = 0;
+    uint32_t phase = 0, hphase = 0;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      const bool first = tile == (int)blockIdx.x;
+      mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + acc * BLOCK_N;
+      if (a.stem_mode == 2) {
+        if (first) mbar_wait(&b_full[0], 0);
+        mbar_wait(&full_bar[stage], phase);
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + acc * BLOCK_N;
-        if (a.stem_mode == 2) {
-          if (tile == (int)blockIdx.x) mbar_wait(&b_full[0], 0);
-          mbar_wait(&full_bar[stage], phase);
-          tc_fence_after();
-          const uint32_t sa = smem_u32(smem + stage * Cfg::kStageBytes), sw = smem_u32(stem_w);
+        if (leader) {
+          const uint64_t da0 = umma_smem_desc_rows16(smem0 + stage * Cfg::kStageBytes);
+          const uint64_t db0 = umma_smem_desc(smem_u32(stem_w), true);
+#pragma unroll
           for (int kh = 0; kh < 7; ++kh) {
 #pragma unroll
             for (int k = 0; k < 2; ++k)
-              umma_bf16(d_tmem, umma_smem_desc_rows16(sa + kh * kStemRowPitch + 32 * k), umma_smem_desc(sw + kh * 4096, true) + (uint64_t)(2 * k),
+              umma_bf16(d_tmem, da0 + (uint64_t)((kh * kStemRowPitch + 32 * k) >> 4), db0 + (uint64_t)((kh * 4096) >> 4) + (uint64_t)(2 * k),
                         idesc, (kh | k) != 0);
           }
           umma_commit(&empty_bar[stage]);
           umma_commit(&tmem_full[acc]);
-          if (++stage == n_stages) { stage = 0; phase ^= 1; }
-          if (++acc == 2) { acc = 0; acc_phase ^= 1; }
-          continue;
         }
-        if (a.halo) {
-          for (int kc = 0; kc < a.k_chunks; ++kc) {
-            mbar_wait(&a_full[hstage], hphase);
-            tc_fence_after();
-            const uint32_t ha = smem_u32(smem + hstage * kHaloBytes);
-            for (int tap = 0; tap < 9; ++tap) {
-              if (!(a.b_resident && tile != (int)blockIdx.x)) mbar_wait(&b_full[stage], phase);
+        if (++stage == n_stages) { stage = 0; phase ^= 1; }
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+        continue;
+      }
+      if (a.halo) {
+        for (int kc = 0; kc < a.k_chunks; ++kc) {
+          mbar_wait(&a_full[hstage], hphase);
+          tc_fence_after();
+          const uint64_t da0 = umma_smem_desc_halo(smem0 + hstage * kHaloBytes, a.halo & 2);
+          if (a.b_resident) {
+            // the whole filter bank is resident (slot = kc * 9 + tap): 36 MMAs back to back, no barrier in between
+            if (first && kc == 0) {
+              for (int t = 0; t < a.b_stages; ++t) mbar_wait(&b_full[t], 0);
               tc_fence_after();
-              const int kh = tap / 3, kw = tap - kh * 3;
-              const uint64_t da = umma_smem_desc_halo(ha + (uint32_t)((kh * (kHaloTW + 2) + kw) * 128), a.halo & 2);
-              const uint64_t db = umma_smem_desc(smem_u32(halo_b + stage * Cfg::kBBytes));
+            }
+            if (leader) {
+              const uint64_t db0 = umma_smem_desc(smem_u32(halo_b + kc * 9 * Cfg::kBBytes));
 #pragma unroll
-              for (int k = 0; k < kBlockK / kUmmaK; ++k)
-                umma_bf16(d_tmem, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (kc | tap | k) != 0);
-              if (!a.b_resident) umma_commit(&b_empty[stage]);
+              for (int tap = 0; tap < 9; ++tap) {
+                const uint64_t da = da0 + (uint64_t)((((tap / 3) * (kHaloTW + 2) + (tap % 3)) * 128) >> 4);
+                const uint64_t db = db0 + (uint64_t)((tap * Cfg::kBBytes) >> 4);
+#pragma unroll
+                for (int k = 0; k < kBlockK / kUmmaK; ++k)
+                  umma_bf16(d_tmem, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (kc | tap | k) != 0);
+              }
+              umma_commit(&a_empty[hstage]);
+              if (kc == a.k_chunks - 1) umma_commit(&tmem_full[acc]);
+            }
+          } else {
+#pragma unroll
+            for (int tap = 0; tap < 9; ++tap) {
+              mbar_wait(&b_full[stage], phase);
+              tc_fence_after();
+              if (leader) {
+                const uint64_t da = da0 + (uint64_t)((((tap / 3) * (kHaloTW + 2) + (tap % 3)) * 128) >> 4);
+                const uint64_t db = umma_smem_desc(smem_u32(halo_b + stage * Cfg::kBBytes));
+#pragma unroll
+                for (int k = 0; k < kBlockK / kUmmaK; ++k)
+                  umma_bf16(d_tmem, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (kc | tap | k) != 0);
+                umma_commit(&b_empty[stage]);
+              }
               if (++stage == a.b_stages) { stage = 0; phase ^= 1; }
             }
-            umma_commit(&a_empty[hstage]);
-            if (kc == a.k_chunks - 1) umma_commit(&tmem_full[acc]);
-            if (++hstage == a.a_stages) { hstage = 0; hphase ^= 1; }
+            if (leader) {
+              umma_commit(&a_empty[hstage]);
+              if (kc == a.k_chunks - 1) umma_commit(&tmem_full[acc]);
+            }
           }
-          if (++acc == 2) { acc = 0; acc_phase ^= 1; }
-          continue;
+          if (++hstage == a.a_stages) { hstage = 0; hphase ^= 1; }
         }
-        for (int it = 0; it < k_iters; ++it) {
-          mbar_wait(&full_bar[stage], phase);
-          tc_fence_after();
-          const uint32_t sa = smem_u32(smem + stage * Cfg::kStageBytes);
-          const uint32_t sb = sa + Cfg::kABytes;
-          const bool sw64 = a.stem_mode == 1;
-          const uint64_t da = umma_smem_desc(sa, sw64), db = umma_smem_desc(sb, sw64);
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+        continue;
+      }
+      const bool sw64 = a.stem_mode == 1;
+      for (int it = 0; it < k_iters; ++it) {
+        mbar_wait(&full_bar[stage], phase);
+        tc_fence_after();
+        if (leader) {
+          const uint32_t sa = smem0 + stage * Cfg::kStageBytes;
+          const uint64_t da = umma_smem_desc(sa, sw64), db = umma_smem_desc(sa + Cfg::kABytes, sw64);
           const int n_mma = sw64 ? 2 : kBlockK / kUmmaK;
 #pragma unroll
           for (int k = 0; k < kBlockK / kUmmaK; ++k) {
@@ -427,65 +496,71 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
           }
           umma_commit(&empty_bar[stage]);  // frees the smem stage once these MMAs retire
           if (it == k_iters - 1) umma_commit(&tmem_full[acc]);
-          if (++stage == n_stages) { stage = 0; phase ^= 1; }
         }
-        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+        if (++stage == n_stages) { stage = 0; phase ^= 1; }
       }
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
   } else if (kStaged && warp == 3) {
     // ================================ io warp (staged epilogue) ================================
     // Owns the 16 KB staging buffers: hands them to the epilogue warps (io_ready: free, or - on residual layers -
     // filled with the TMA-loaded residual sub-tile, running up to io_bufs sub-tiles ahead) and TMA-stores them once
-    // all 128 epilogue threads have written their rows (io_written).  The epilogue warps never wait on a store.
-    if (lane == 0) {
-      constexpr int kSub = BLOCK_N / 64;
-      const int rmode = a.residual_mode;
-      const uint32_t R = (uint32_t)a.io_bufs;
-      const uint32_t res_bytes = rmode == 2 ? kCoarseBytes : kIoBytes;
-      auto tile_coords = [&](int tile, int& n0, int& w0, int& h0, int& img) {
-        const int nt = tile % a.tiles_n, mt = tile / a.tiles_n;
-        n0 = nt * BLOCK_N;
-        w0 = (mt % a.tiles_w) * a.TW;
-        h0 = ((mt / a.tiles_w) % a.tiles_h) * a.TH;
-        img = mt / (a.tiles_w * a.tiles_h);
-      };
-      auto sub_count = [&](int n0) { const int left = (a.Cout - n0) / 64; return left < kSub ? left : kSub; };
-      int rd_tile = blockIdx.x, rd_sub = 0;  // cursor of the next sub-tile to be made ready
-      uint32_t rd_g = 0;
-      auto make_ready = [&]() {
-        if (rd_tile >= num_tiles) return;
-        int n0, w0, h0, img;
-        tile_coords(rd_tile, n0, w0, h0, img);
-        const uint32_t pb = rd_g % R;
+    // all epilogue threads have written their rows (io_written).  The epilogue warps never wait on a store.
+    const bool leader = elect_one();
+    constexpr int kSub = BLOCK_N / 64;
+    const int rmode = a.residual_mode;
+    const int R = a.io_bufs;
+    const uint32_t res_bytes = rmode == 2 ? kCoarseBytes : kIoBytes;
+    auto sub_count = [&](int n0) { const int left = (a.Cout - n0) >> 6; return left < kSub ? left : kSub; };
+    int rd_tile = blockIdx.x, rd_sub = 0, rd_p = 0;  // cursor of the next sub-tile to be made ready, its buffer
+    int rd_n0 = 0, rd_w0 = 0, rd_h0 = 0, rd_img = 0;
+    auto rd_coords = [&]() {
+      int nt, tw, th;
+      decompose(rd_tile, nt, tw, th, rd_img);
+      rd_n0 = nt * BLOCK_N; rd_w0 = tw * a.TW; rd_h0 = th * a.TH;
+    };
+    if (rd_tile < num_tiles) rd_coords();
+    auto make_ready = [&]() {
+      if (rd_tile >= num_tiles) return;
+      if (leader) {
         if (rmode == 0) {
-          mbar_arrive(&io_ready[pb]);
+          mbar_arrive(&io_ready[rd_p]);
         } else {
-          mbar_expect_tx(&io_ready[pb], res_bytes);
-          if (rmode == 1) tma_load_4d(&map_res, &io_ready[pb], io_stage + pb * kIoBytes, n0 + rd_sub * 64, w0, h0, img);
-          else tma_load_4d(&map_res, &io_ready[pb], coarse_stage + pb * kCoarseBytes, n0 + rd_sub * 64, w0 >> 1, h0 >> 1, img);
-        }
-        ++rd_g;
-        if (++rd_sub == sub_count(n0)) { rd_sub = 0; rd_tile += gridDim.x; }
-      };
-      for (uint32_t i = 0; i < R; ++i) make_ready();
-      uint32_t g = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        int n0, w0, h0, img;
-        tile_coords(tile, n0, w0, h0, img);
-        const int nsub = sub_count(n0);
-        for (int s2 = 0; s2 < nsub; ++s2, ++g) {
-          const uint32_t p = g % R;
-          mbar_wait(&io_written[p], (g / R) & 1u);
-          tma_store_4d(&map_out, io_stage + p * kIoBytes, n0 + s2 * 64, w0, h0, img);
-          tma_store_commit();
-          if (g >= 1) {
-            tma_store_wait_read<1>();  // store g-1 has drained its buffer: recycle it for sub-tile g-1+R
-            make_ready();
-          }
+          mbar_expect_tx(&io_ready[rd_p], res_bytes);
+          if (rmode == 1) tma_load_4d(&map_res, &io_ready[rd_p], io_stage + rd_p * kIoBytes, rd_n0 + rd_sub * 64, rd_w0, rd_h0, rd_img);
+          else tma_load_4d(&map_res, &io_ready[rd_p], coarse_stage + rd_p * kCoarseBytes, rd_n0 + rd_sub * 64, rd_w0 >> 1, rd_h0 >> 1, rd_img);
         }
       }
-      tma_store_wait_all();
+      if (++rd_p == R) rd_p = 0;
+      if (++rd_sub == sub_count(rd_n0)) {
+        rd_sub = 0;
+        rd_tile += gridDim.x;
+        if (rd_tile < num_tiles) rd_coords();
+      }
+    };
+    for (int i = 0; i < R; ++i) make_ready();
+    int p = 0;
+    uint32_t par = 0;
+    bool any = false;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      int nt, tw, th, img;
+      decompose(tile, nt, tw, th, img);
+      const int n0 = nt * BLOCK_N, w0 = tw * a.TW, h0 = th * a.TH;
+      const int nsub = sub_count(n0);
+      for (int s2 = 0; s2 < nsub; ++s2) {
+        mbar_wait(&io_written[p], par);
+        if (leader) {
+          tma_store_4d(&map_out, io_stage + p * kIoBytes, n0 + s2 * 64, w0, h0, img);
+          tma_store_commit();
+          if (any) tma_store_wait_read<1>();  // the previous store has drained its buffer: recycle it for R sub-tiles ahead
+        }
+        __syncwarp();
+        if (any) make_ready();
+        any = true;
+        if (++p == R) { p = 0; par ^= 1; }
+      }
     }
+    if (leader) tma_store_wait_all();
   } else if (warp >= kEpilogueWarp0) {
     // ================================ epilogue ================================
     // warps 4-7 and 8-11: warp w may only touch TMEM lanes [32 * (w % 4), +32); the two warps of a lane quarter split
@@ -500,19 +575,28 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
     if constexpr (kStaged) {
       constexpr int kSub = BLOCK_N / 64;
       const int rmode = a.residual_mode;  // 1: same-size residual tile, 2: coarser map (nearest 2x); both arrive by TMA
-      const uint32_t R = (uint32_t)a.io_bufs;
+      const int R = a.io_bufs;
       const int crow = (ph >> 1) * (a.TW >> 1) + (pw >> 1);  // this thread's pixel in the coarse (mode 2) tile
-      uint32_t g = 0;  // running sub-tile counter: buffer g % R, barrier parity (g / R) & 1
+      const bool has_bias = a.bias != nullptr;
+      int p = 0;          // staging buffer of the running sub-tile
+      uint32_t par = 0;   // its barrier parity
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const int n0 = (tile % a.tiles_n) * BLOCK_N;
-        const int left = (a.Cout - n0) / 64;
+        const int n0 = (tile - (int)fast_div((uint32_t)tile, a.mul_tiles_n) * a.tiles_n) * BLOCK_N;
+        const int left = (a.Cout - n0) >> 6;
         const int nsub = left < kSub ? left : kSub;
-        mbar_wait(&tmem_full[acc], acc_phase);
-        tc_fence_after();
-        for (int s2 = 0; s2 < nsub; ++s2, ++g) {
-          const uint32_t p = g % R;
+        for (int s2 = 0; s2 < nsub; ++s2) {
           unsigned char* io = io_stage + p * kIoBytes;
-          const int ch0 = n0 + s2 * 64;
+          // this warp's 32 bias values are fetched before any wait, so their latency hides behind the barrier / TMEM loads
+          float4 bv[8];
+          if (has_bias) {
+            const float4* bp = reinterpret_cast<const float4*>(a.bias + n0 + s2 * 64 + half * 32);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) bv[j] = __ldg(bp + j);
+          }
+          if (s2 == 0) {
+            mbar_wait(&tmem_full[acc], acc_phase);
+            tc_fence_after();
+          }
           uint32_t v[32];
           const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BLOCK_N + s2 * 64 + half * 32);
           tmem_ld_32x32b_x16(taddr, v);
@@ -523,7 +607,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
             __syncwarp();
             if (lane == 0) mbar_arrive(&tmem_empty[acc]);
           }
-          mbar_wait(&io_ready[p], (g / R) & 1u);  // buffer free and (residual layers) its residual sub-tile landed
+          mbar_wait(&io_ready[p], par);  // buffer free and (residual layers) its residual sub-tile landed
           uint4* myrow = reinterpret_cast<uint4*>(io + row * 128);
           const uint4* crs = reinterpret_cast<const uint4*>(coarse_stage + p * kCoarseBytes + crow * 128);
           // this warp's four residual chunks of the row are read up front: inside the loop every load would have to wait
@@ -539,9 +623,8 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
             float f[8];
 #pragma unroll
             for (int i = 0; i < 8; ++i) f[i] = __uint_as_float(v[j * 8 + i]);
-            if (a.bias) {
-              const float4 b0 = __ldg(reinterpret_cast<const float4*>(a.bias + ch0 + c * 8));
-              const float4 b1 = __ldg(reinterpret_cast<const float4*>(a.bias + ch0 + c * 8 + 4));
+            if (has_bias) {
+              const float4 b0 = bv[2 * j], b1 = bv[2 * j + 1];
               f[0] += b0.x; f[1] += b0.y; f[2] += b0.z; f[3] += b0.w;
               f[4] += b1.x; f[5] += b1.y; f[6] += b1.z; f[7] += b1.w;
             }
@@ -559,13 +642,14 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
           }
           fence_proxy_async();            // make the generic-proxy row writes visible to the TMA store
           mbar_arrive(&io_written[p]);    // 256 arrivals release the buffer to the io warp
+          if (++p == R) { p = 0; par ^= 1; }
         }
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       }
     } else {
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const int nt = tile % a.tiles_n, mt = tile / a.tiles_n;
-        const int tw = mt % a.tiles_w, th = (mt / a.tiles_w) % a.tiles_h, img = mt / (a.tiles_w * a.tiles_h);
+        int nt, tw, th, img;
+        decompose(tile, nt, tw, th, img);
         const int h = th * a.TH + ph, w = tw * a.TW + pw, n0 = nt * BLOCK_N;
         const bool pix_ok = h < a.Ho && w < a.Wo;
         const size_t opix = ((size_t)img * a.Ho + h) * a.Wo + w;
@@ -681,10 +765,17 @@ void pick_patch(int Ho, int Wo, int max_tw, int* TH, int* TW) {
   *TW = bw;
 }
 
+uint32_t div_mul(int d) { return d <= 1 ? 0u : (uint32_t)(((1ull << 32) + (uint64_t)d - 1) / (uint64_t)d); }
+
 template <int BLOCK_N, bool kStaged>
-int launch_conv(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& mo, const CUtensorMap& mr, const ConvArgs& a,
-                cudaStream_t st) {
+int launch_conv(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& mo, const CUtensorMap& mr, const CUtensorMap& ma2,
+                const ConvArgs& a_in, cudaStream_t st) {
   using Cfg = TileCfg<BLOCK_N, kStaged>;
+  ConvArgs a = a_in;
+  a.mul_tiles_n = div_mul(a.tiles_n);
+  a.mul_tiles_w = div_mul(a.tiles_w);
+  a.mul_tiles_h = div_mul(a.tiles_h);
+  if ((long long)a.N * a.tiles_h * a.tiles_w * a.tiles_n * 2048 >= (1ll << 32)) return PE_ERR_UNSUPPORTED;  // fast_div range
   static bool attr_done = false;
   if (!attr_done) {
     PE_CUDA_CHECK(cudaFuncSetAttribute(conv_gemm_kernel<BLOCK_N, kStaged>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -693,7 +784,7 @@ int launch_conv(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap&
   }
   const int tiles = a.N * a.tiles_h * a.tiles_w * a.tiles_n;
   const int grid = tiles < sm_count() ? tiles : sm_count();
-  conv_gemm_kernel<BLOCK_N, kStaged><<<grid, kThreads, Cfg::kSmemBytes, st>>>(ma, mb, mo, mr, a);
+  conv_gemm_kernel<BLOCK_N, kStaged><<<grid, kThreads, Cfg::kSmemBytes, st>>>(ma, mb, mo, mr, ma2, a);
   PE_LAUNCH_CHECK();
   return PE_OK;
 }
@@ -701,7 +792,11 @@ int launch_conv(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap&
 }  // namespace
 
 int conv2d_launch(const pe_conv_desc& d, const void* x, const void* w, const float* bias, const void* residual, void* y,
-                  cudaStream_t st) {
+                  cudaStream_t st, const ConvSecondInput* x2) {
+  if (x2 && x2->x) {  // dual-input 1x1: y = act([x | x2(strided)] . w + bias), w = [Cout][Cin + Cin2]
+    if (d.KH != 1 || d.KW != 1 || d.stride != 1 || d.Cin % 64 || x2->Cin % 8 || (x2->stride != 1 && x2->stride != 2)) return PE_ERR_UNSUPPORTED;
+    if ((x2->H - 1) / x2->stride + 1 != d.H || (x2->W - 1) / x2->stride + 1 != d.W) return PE_ERR_INVALID_ARGUMENT;
+  }
   if (d.N < 1 || d.H < 1 || d.W < 1 || d.Cin < 8 || d.Cin % 8 || d.Cout < 8 || d.Cout % 8) return PE_ERR_INVALID_ARGUMENT;
   if (!((d.KH == 1 && d.KW == 1) || (d.KH == 3 && d.KW == 3))) return PE_ERR_UNSUPPORTED;
   if (d.stride != 1 && !(d.stride == 2 && d.KH == 1)) return PE_ERR_UNSUPPORTED;
@@ -733,6 +828,9 @@ int conv2d_launch(const pe_conv_desc& d, const void* x, const void* w, const flo
   const int bn = d.Cout >= 256 ? 256 : (d.Cout >= 128 ? 128 : (d.Cout >= 64 ? 64 : (d.Cout > 16 ? 32 : 16)));
   a.tiles_n = ceil_div(d.Cout, bn);
   a.k_chunks = ceil_div(d.Cin, kBlockK);  // a ragged last chunk is zero-filled by TMA (A and W alike)
+  a.k_chunks1 = a.k_chunks;
+  const bool dual = x2 && x2->x;
+  if (dual) a.k_chunks += ceil_div(x2->Cin, kBlockK);
   a.relu = d.relu;
   a.residual_mode = d.residual_mode;
   a.out_fp32 = d.out_fp32;
@@ -747,7 +845,14 @@ int conv2d_launch(const pe_conv_desc& d, const void* x, const void* w, const flo
   a.residual = reinterpret_cast<const __nv_bfloat16*>(residual);
   a.out = y;
 
-  CUtensorMap ma, mb;
+  CUtensorMap ma, mb, ma2;
+  if (dual) {
+    const cuuint64_t s2 = (cuuint64_t)x2->stride;
+    cuuint64_t dims[4] = {(cuuint64_t)x2->Cin, (cuuint64_t)a.Wo, (cuuint64_t)a.Ho, (cuuint64_t)d.N};
+    cuuint64_t strides[3] = {s2 * x2->Cin * 2, s2 * (cuuint64_t)x2->W * x2->Cin * 2, (cuuint64_t)x2->H * x2->W * x2->Cin * 2};
+    cuuint32_t box[4] = {(cuuint32_t)kBlockK, (cuuint32_t)a.TW, (cuuint32_t)a.TH, 1};
+    if (!make_map(&ma2, x2->x, 4, dims, strides, box)) return PE_ERR_CUDA;
+  }
   {
     const cuuint64_t s = (cuuint64_t)d.stride;
     cuuint64_t dims[4] = {(cuuint64_t)d.Cin, (cuuint64_t)a.Wo, (cuuint64_t)a.Ho, (cuuint64_t)d.N};
@@ -756,14 +861,16 @@ int conv2d_launch(const pe_conv_desc& d, const void* x, const void* w, const flo
     if (!make_map(&ma, x, 4, dims, strides, box)) return PE_ERR_CUDA;
   }
   {
-    cuuint64_t dims[2] = {(cuuint64_t)d.KH * d.KW * d.Cin, (cuuint64_t)d.Cout};
-    cuuint64_t strides[1] = {(cuuint64_t)d.KH * d.KW * d.Cin * 2};
+    const cuuint64_t ktot = (cuuint64_t)d.KH * d.KW * d.Cin + (dual ? (cuuint64_t)x2->Cin : 0);
+    cuuint64_t dims[2] = {ktot, (cuuint64_t)d.Cout};
+    cuuint64_t strides[1] = {ktot * 2};
     cuuint32_t box[2] = {(cuuint32_t)kBlockK, (cuuint32_t)bn};
     if (!make_map(&mb, w, 2, dims, strides, box)) return PE_ERR_CUDA;
   }
   // bf16 outputs with whole 64-channel groups take the smem-staged TMA-store epilogue
   const bool staged = !d.out_fp32 && bn >= 64 && d.Cout % 64 == 0;
   CUtensorMap mo = ma, mr = ma;
+  if (!dual) ma2 = ma;
   if (staged) {
     cuuint64_t dims[4] = {(cuuint64_t)d.Cout, (cuuint64_t)a.Wo, (cuuint64_t)a.Ho, (cuuint64_t)d.N};
     cuuint64_t strides[3] = {(cuuint64_t)d.Cout * 2, (cuuint64_t)a.Wo * d.Cout * 2, (cuuint64_t)a.Ho * a.Wo * d.Cout * 2};
@@ -825,17 +932,17 @@ int conv2d_launch(const pe_conv_desc& d, const void* x, const void* w, const flo
   }
   if (staged) {
     switch (bn) {
-      case 256: return launch_conv<256, true>(ma, mb, mo, mr, a, st);
-      case 128: return launch_conv<128, true>(ma, mb, mo, mr, a, st);
-      default: return launch_conv<64, true>(ma, mb, mo, mr, a, st);
+      case 256: return launch_conv<256, true>(ma, mb, mo, mr, ma2, a, st);
+      case 128: return launch_conv<128, true>(ma, mb, mo, mr, ma2, a, st);
+      default: return launch_conv<64, true>(ma, mb, mo, mr, ma2, a, st);
     }
   }
   switch (bn) {
-    case 256: return launch_conv<256, false>(ma, mb, mo, mr, a, st);
-    case 128: return launch_conv<128, false>(ma, mb, mo, mr, a, st);
-    case 64: return launch_conv<64, false>(ma, mb, mo, mr, a, st);
-    case 32: return launch_conv<32, false>(ma, mb, mo, mr, a, st);
-    default: return launch_conv<16, false>(ma, mb, mo, mr, a, st);
+    case 256: return launch_conv<256, false>(ma, mb, mo, mr, ma2, a, st);
+    case 128: return launch_conv<128, false>(ma, mb, mo, mr, ma2, a, st);
+    case 64: return launch_conv<64, false>(ma, mb, mo, mr, ma2, a, st);
+    case 32: return launch_conv<32, false>(ma, mb, mo, mr, ma2, a, st);
+    default: return launch_conv<16, false>(ma, mb, mo, mr, ma2, a, st);
   }
 }
 
@@ -858,6 +965,7 @@ int conv_stem_launch(const void* canvas, const void* w, const float* bias, void*
   a.tiles_w = ceil_div(a.Wo, a.TW);
   a.tiles_n = 1;
   a.k_chunks = 1;
+  a.k_chunks1 = 1;
   a.relu = 1; a.residual_mode = 0; a.out_fp32 = 0; a.in_fp16 = 1; a.stem_mode = mode;
   a.canvas = reinterpret_cast<const unsigned char*>(canvas);
   a.canvas_hp = Hp;
@@ -893,7 +1001,7 @@ int conv_stem_launch(const void* canvas, const void* w, const float* bias, void*
     cuuint32_t box[4] = {64, (cuuint32_t)a.TW, (cuuint32_t)a.TH, 1};
     if (!make_map(&mo, y, 4, dims, strides, box)) return PE_ERR_CUDA;
   }
-  return launch_conv<64, true>(ma, mb, mo, mo, a, st);
+  return launch_conv<64, true>(ma, mb, mo, mo, mo, a, st);
 }
 
 }  // namespace pe
@@ -902,4 +1010,11 @@ extern "C" PE_API int pe_conv2d_fwd(const pe_conv_desc* desc, const void* x, con
                                     const void* residual, void* y, void* stream) {
   if (!desc) return PE_ERR_INVALID_ARGUMENT;
   return pe::conv2d_launch(*desc, x, w, bias, residual, y, reinterpret_cast<cudaStream_t>(stream));
+}
+
+extern "C" PE_API int pe_conv1x1_dual_fwd(const pe_conv_desc* desc, const void* x, const void* x2, int cin2, int h2, int w2, int stride2,
+                                          const void* w, const float* bias, void* y, void* stream) {
+  if (!desc || !x2) return PE_ERR_INVALID_ARGUMENT;
+  pe::ConvSecondInput s2 = {x2, cin2, h2, w2, stride2};
+  return pe::conv2d_launch(*desc, x, w, bias, nullptr, y, reinterpret_cast<cudaStream_t>(stream), &s2);
 }

@@ -16,7 +16,10 @@ namespace {
 
 constexpr int kMaxProps = 1000;  // RPN POST_NMS_TOPK_TEST (configs/Base-RCNN-FPN.yaml:19)
 
-enum ParamKind { kConvBN = 0, kConvBias = 1, kStem = 2, kRpnPred = 3, kFc1 = 4, kLinear = 5, kPredictor = 6 };
+// kConv3Shortcut: [conv3 | shortcut] of a stage's first bottleneck block concatenated along K (both FrozenBN-folded, biases summed):
+// out = relu(conv3(t) + shortcut(x)) runs as one dual-input GEMM (pe_conv1x1_dual_fwd); the manifest entry carries conv3's name, the
+// host derives the shortcut's (".conv3" -> ".shortcut")
+enum ParamKind { kConvBN = 0, kConvBias = 1, kStem = 2, kRpnPred = 3, kFc1 = 4, kLinear = 5, kPredictor = 6, kConv3Shortcut = 7 };
 
 struct Param {
   std::string name;
@@ -110,10 +113,10 @@ void build_plan(pe_detector* d) {
     for (int b = 0; b < blocks[s]; ++b) {
       char q[96];
       snprintf(q, sizeof(q), "%s.res%d.%d", bu.c_str(), s + 2, b);
-      if (b == 0) d->add_param(std::string(q) + ".shortcut", kConvBN, cout, 1, 1, cin, 2);
       d->add_param(std::string(q) + ".conv1", kConvBN, mid, 1, 1, cin, 2);
       d->add_param(std::string(q) + ".conv2", kConvBN, mid, 3, 3, mid, 2);
-      d->add_param(std::string(q) + ".conv3", kConvBN, cout, 1, 1, mid, 2);
+      if (b == 0) d->add_param(std::string(q) + ".conv3", kConv3Shortcut, cout, 1, 1, mid + cin, 2);
+      else d->add_param(std::string(q) + ".conv3", kConvBN, cout, 1, 1, mid, 2);
       cin = cout;
     }
   }
@@ -139,7 +142,6 @@ void build_plan(pe_detector* d) {
   d->add_buf("pool_out", B, d->H[1], d->W[1], 64, 2);
   d->add_buf("x0", B, d->H[1], d->W[1], 256, 2);
   d->add_buf("x1", B, d->H[1], d->W[1], 256, 2);
-  d->add_buf("sc", B, d->H[1], d->W[1], 256, 2);
   d->add_buf("t1", B, d->H[1], d->W[1], 64, 2);
   d->add_buf("t2", B, d->H[1], d->W[1], 64, 2);
   for (int s = 0; s < 4; ++s) {
@@ -188,7 +190,8 @@ struct Runner {
 
   void* buf(const char* name) const { return ws + d->find_buf(name)->off; }
 
-  int gemm(const pe_conv_desc& cd, const void* x, const void* w, const float* bias, const void* res, void* y) {
+  int gemm(const pe_conv_desc& cd, const void* x, const void* w, const float* bias, const void* res, void* y,
+           const ConvSecondInput* x2 = nullptr) {
     cudaEvent_t e0 = nullptr, e1 = nullptr;
     if (d->profiling) {
       while ((int)d->ev.size() < d->ev_used + 2) {
@@ -200,16 +203,17 @@ struct Runner {
       e1 = d->ev[d->ev_used++];
       const int pad = (cd.KH - 1) / 2;
       const double Ho = (cd.H + 2 * pad - cd.KH) / cd.stride + 1, Wo = (cd.W + 2 * pad - cd.KW) / cd.stride + 1;
-      const double taps = (double)cd.KH * cd.KW * cd.Cin, opix = (double)cd.N * Ho * Wo;
+      const double taps = (double)cd.KH * cd.KW * cd.Cin + (x2 ? x2->Cin : 0), opix = (double)cd.N * Ho * Wo;
       double bytes = (double)cd.N * cd.H * cd.W * cd.Cin * 2 / ((cd.KH == 1 && cd.stride == 2) ? 4.0 : 1.0) +
                      taps * cd.Cout * 2 + cd.Cout * 4.0 + opix * cd.Cout * (cd.out_fp32 ? 4 : 2);
+      if (x2) bytes += opix * x2->Cin * 2;  // the block input at the positions the (strided) shortcut reads
       if (cd.residual_mode == 1) bytes += opix * cd.Cout * 2;
       if (cd.residual_mode == 2) bytes += opix * cd.Cout * 2 / 4.0;
       d->prof_flops.push_back(2.0 * opix * cd.Cout * taps);
       d->prof_bytes.push_back(bytes);
       cudaEventRecord(e0, st);
     }
-    const int s = conv2d_launch(cd, x, w, bias, res, y, st);
+    const int s = conv2d_launch(cd, x, w, bias, res, y, st, x2);
     if (d->profiling) cudaEventRecord(e1, st);
     d->last_launches++;
     d->last_gemm_launches++;
@@ -287,18 +291,26 @@ struct Runner {
         snprintf(q, sizeof(q), "backbone.bottom_up.res%d.%d", s + 2, b);
         const std::string base(q);
         const int stride = (b == 0 && s > 0) ? 2 : 1;
-        const void* shortcut = x;
-        if (b == 0) {
-          conv(base + ".shortcut", x, H, W, stride, false, 0, nullptr, buf("sc"));
-          shortcut = buf("sc");
-        }
+        const int Hin = H, Win = W;
         conv(base + ".conv1", x, H, W, stride, true, 0, nullptr, buf("t1"));
         if (stride == 2) { H = (H - 1) / 2 + 1; W = (W - 1) / 2 + 1; }
         conv(base + ".conv2", buf("t1"), H, W, 1, true, 0, nullptr, buf("t2"));
         char rq[16];
         snprintf(rq, sizeof(rq), "res%d", s + 2);
         void* y = (b == blocks[s] - 1) ? buf(rq) : (x == buf("x0") ? buf("x1") : buf("x0"));
-        conv(base + ".conv3", buf("t2"), H, W, 1, true, 1, shortcut, y);
+        if (b == 0) {  // conv3 + projection shortcut as one GEMM over K = [t2 | block input] (the shortcut tensor never exists)
+          if (status == PE_OK) {
+            const Param& p = d->params[d->find_param(base + ".conv3")];
+            const int mid = 64 << s;
+            pe_conv_desc cd;
+            cd.N = B; cd.H = H; cd.W = W; cd.Cin = mid; cd.Cout = p.Cout; cd.KH = 1; cd.KW = 1; cd.stride = 1;
+            cd.relu = 1; cd.residual_mode = 0; cd.out_fp32 = 0; cd.in_fp16 = 0;
+            ConvSecondInput x2 = {x, p.Cin - mid, Hin, Win, stride};
+            status = gemm(cd, buf("t2"), wts + p.w_off, reinterpret_cast<const float*>(wts + p.b_off), nullptr, y, &x2);
+          }
+        } else {
+          conv(base + ".conv3", buf("t2"), H, W, 1, true, 1, x, y);
+        }
         x = y;
       }
     }

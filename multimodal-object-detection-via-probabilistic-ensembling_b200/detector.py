@@ -60,6 +60,14 @@ def pack_weights(sd, manifest, total_bytes, num_classes):
             w = w.permute(0, 2, 3, 1)
             assert tuple(w.shape) == (p["cout"], p["kh"], p["kw"], p["cin"]), (name, tuple(w.shape), p)
             put(p["weight_offset"], w.to(torch.bfloat16))
+        elif kind == 7:
+            # conv3 | projection shortcut of a stage's first block, concatenated along K (biases add): see engine.cu
+            w3, b3 = _fold_bn(sd, name)
+            wsc, bsc = _fold_bn(sd, name[: -len("conv3")] + "shortcut")
+            w = torch.cat([w3.reshape(w3.shape[0], -1), wsc.reshape(wsc.shape[0], -1)], 1)
+            b = b3 + bsc
+            assert tuple(w.shape) == (p["cout"], p["cin"]), (name, tuple(w.shape), p)
+            put(p["weight_offset"], w.to(torch.bfloat16))
         elif kind == 2:
             # stem: K index = kh*32 + kw*4 + c over a 7 x 8 x 4 window (kw = 7 and c >= C are zero)
             w, b = _fold_bn(sd, name)

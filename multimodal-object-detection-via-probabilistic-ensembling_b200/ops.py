@@ -28,6 +28,26 @@ def conv2d_nhwc(x, w, bias=None, residual=None, stride=1, relu=False, residual_m
     return y
 
 
+def conv1x1_dual_nhwc(x, x2, w, bias=None, stride2=1, relu=False):
+    """``pe_conv1x1_dual_fwd``: y = act([x | x2 at stride2] . w + bias) with x [N,H,W,Cin], x2 [N,H2,W2,Cin2], w [Cout, Cin + Cin2]
+    (bottleneck conv3 + projection shortcut as one GEMM, resnet.py:205-221)."""
+    lib = _lib.load()
+    _lib.require_cuda(x, x2, w, bias)
+    if not (x.dtype == x2.dtype == w.dtype == torch.bfloat16):
+        raise RuntimeError("probenb200.conv1x1_dual_nhwc: bfloat16 operands expected")
+    N, H, W, Cin = x.shape
+    _, H2, W2, Cin2 = x2.shape
+    Cout = w.shape[0]
+    if w.numel() != Cout * (Cin + Cin2):
+        raise RuntimeError("probenb200.conv1x1_dual_nhwc: weight must be [Cout, Cin + Cin2]")
+    y = torch.empty((N, H, W, Cout), dtype=torch.bfloat16, device=x.device)
+    d = _lib.ConvDesc(N, H, W, Cin, Cout, 1, 1, 1, int(relu), 0, 0, 0)
+    st = lib.pe_conv1x1_dual_fwd(ctypes.byref(d), _lib.ptr(x), _lib.ptr(x2), Cin2, H2, W2, int(stride2), _lib.ptr(w), _lib.ptr(bias),
+                                 _lib.ptr(y), _lib.current_stream_ptr(x.device))
+    _lib.check(st, "pe_conv1x1_dual_fwd")
+    return y
+
+
 def linear(x, w, bias=None, relu=False, out_fp32=False):
     """x [M,K] bf16, w [N,K] bf16 -> [M,N]; the H=1 case of the conv kernel."""
     M, K = x.shape

@@ -105,7 +105,9 @@ class ProbEnPipeline:
         B = images[0].shape[0]
         def run(det, img, buf):
             if net_hw is not None:
-                det.forward_frames_device(img, net_hw, out=buf)
+                # 3-channel uint8 frames take Pillow's 8-bit resize in the reference, 4-/6-channel arrays cv2's float path
+                # (data/transforms/transform.py:81-99)
+                det.forward_frames_device(img, net_hw, out=buf, round_u8=img.shape[3] == 3)
             else:
                 det.forward_device(img, (self.frame_h, self.frame_w), out=buf)
         if B != self.B:
@@ -139,6 +141,23 @@ class ProbEnPipeline:
     def gather(self, out, group=None):
         return all_gather_flat(out.flat, group)
 
+    def capture(self, images, net_hw=None):
+        """Records one ``forward_device`` over ``images`` (device buffers whose ADDRESSES the graph keeps: refill them in
+        place) into a CUDA graph - the ~200 kernel launches of a step (M detector plans on their streams, pack, fuse)
+        become ONE submission per step.  Returns the ``torch.cuda.CUDAGraph``; ``graph.replay()`` on the current stream
+        runs the step.  The reference needs several host syncs per image here (rpn.py:174-177, rpn_outputs.py:132,145,
+        ROIAlign_cuda.cu:363); the engine has none, which is what makes the capture possible."""
+        self.forward_device(images, net_hw)  # outside the capture: first-launch attribute setup, lazy module loading
+        torch.cuda.synchronize(self.device)
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            self.forward_device(images, net_hw)
+        return graph
+
+    def launches_per_step(self):
+        """Kernel launches of the last forward (detector plans + 2 pack + 2 fuse kernels)."""
+        return sum(d.last_profile()[2] for d in self.detectors) + 4
+
 
 def all_gather_flat(flat, group=None):
     """The one collective of the path: every rank's flat result buffer -> every rank, one all-gather (NCCL on
@@ -149,6 +168,62 @@ def all_gather_flat(flat, group=None):
     full = torch.empty(world * flat.numel(), dtype=flat.dtype, device=flat.device)
     dist.all_gather_into_tensor(full, flat, group=group)
     return full.view(world, flat.numel())
+
+
+class AsyncGather:
+    """The path's one collective, taken off the compute stream: step i's flat result is snapshotted (double buffer) and
+    all-gathered on a side stream while step i + 1 computes, so a rank never waits for the slowest rank of the SAME step
+    (with the gather on the compute stream every step ends in a rank barrier and straggler skew accumulates).
+    ``submit`` returns (gathered [world, n] tensor, event recorded on the gather stream when it is complete)."""
+
+    def __init__(self, flat, group=None):
+        import torch.distributed as dist
+        self.group = group
+        self.world = dist.get_world_size(group)
+        self.stream = torch.cuda.Stream(device=flat.device)
+        self.snap = [torch.empty_like(flat) for _ in range(2)]
+        self.full = [torch.empty(self.world * flat.numel(), dtype=flat.dtype, device=flat.device) for _ in range(2)]
+        self.ready = [torch.cuda.Event() for _ in range(2)]
+        self.done = [torch.cuda.Event() for _ in range(2)]
+        self.i = 0
+
+    def submit(self, flat, host_out=None):
+        import torch.distributed as dist
+        s = self.i & 1
+        main = torch.cuda.current_stream(flat.device)
+        main.wait_event(self.done[s])             # the gather of step i - 2 has consumed this snapshot slot
+        self.snap[s].copy_(flat, non_blocking=True)
+        self.ready[s].record(main)
+        with torch.cuda.stream(self.stream):
+            self.stream.wait_event(self.ready[s])
+            dist.all_gather_into_tensor(self.full[s], self.snap[s], group=self.group)
+            if host_out is not None:
+                host_out.copy_(self.full[s], non_blocking=True)
+            self.done[s].record(self.stream)
+        self.i += 1
+        return self.full[s].view(self.world, flat.numel()), self.done[s]
+
+    def finish(self):
+        """Joins the gather stream into the current stream (end of a timed region / before reading results)."""
+        torch.cuda.current_stream(self.snap[0].device).wait_stream(self.stream)
+
+
+def all_gather_ragged(rows, group=None):
+    """Gather of UNEQUAL shards (a 1013-image validation set over 8 ranks: InferenceSampler's last shard is short,
+    data/samplers/distributed_sampler.py:190-193): ``rows`` [n_local, w] -> list over ranks of [n_r, w] tensors.  Two
+    collectives: the shard lengths, then the rows padded to the longest shard."""
+    import torch.distributed as dist
+    world = dist.get_world_size(group)
+    n = torch.tensor([rows.shape[0]], dtype=torch.int64, device=rows.device)
+    counts = torch.empty(world, dtype=torch.int64, device=rows.device)
+    dist.all_gather_into_tensor(counts, n, group=group)
+    counts = counts.tolist()
+    cap = max(counts)
+    padded = torch.zeros((cap,) + tuple(rows.shape[1:]), dtype=rows.dtype, device=rows.device)
+    padded[: rows.shape[0]] = rows
+    full = torch.empty((world * cap,) + tuple(rows.shape[1:]), dtype=rows.dtype, device=rows.device)
+    dist.all_gather_into_tensor(full, padded, group=group)
+    return [full[r * cap: r * cap + counts[r]] for r in range(world)]
 
 
 def shard_range(num_items, rank, world):

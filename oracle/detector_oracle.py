@@ -53,7 +53,51 @@ class DetCfg:
         self.middle_fusion = middle_fusion
 
 
+# ---- precision bisect (test infrastructure for tests/golden/bisect_bf16.py and the mAP-parity harness) ---------------------------
+# EMULATE names the stages whose arithmetic is restated the way the B200 engine computes it: FrozenBN folded into the weights,
+# operands rounded to bf16 (stem: fp16), fp32 accumulation, bias / residual / ReLU in fp32, ONE rounding of the stored activation
+# to bf16.  Stages: "stem", "res2".."res5", "fpn", "rpn", "head".  Empty set = the fp32 reference arithmetic (the pinned oracle).
+EMULATE = set()
+
+
+def _bf(t):
+    return t.bfloat16().float()
+
+
+def _stage_of(name):
+    for st in ("stem", "res2", "res3", "res4", "res5"):
+        if "." + st + "." in name:
+            return st
+    if "fpn_" in name:
+        return "fpn"
+    if "rpn_head" in name:
+        return "rpn"
+    return "head"
+
+
+def _conv_emulated(x, sd, name, stride, padding, relu, add=None, round_out=True):
+    w = sd[name + ".weight"]
+    if name + ".norm.weight" in sd:
+        scale = sd[name + ".norm.weight"] / torch.sqrt(sd[name + ".norm.running_var"] + 1e-5)
+        b = sd[name + ".norm.bias"] - sd[name + ".norm.running_mean"] * scale
+        w = w * scale.view(-1, 1, 1, 1)
+    else:
+        b = sd.get(name + ".bias")
+    if ".stem." in name:
+        x, w = x.half().float(), w.half().float()
+    else:
+        x, w = _bf(x), _bf(w)
+    y = F.conv2d(x, w, b, stride=stride, padding=padding)
+    if add is not None:
+        y = y + add
+    if relu:
+        y = F.relu(y)
+    return _bf(y) if round_out else y
+
+
 def _conv(x, sd, name, stride=1, padding=0, relu=False):
+    if _stage_of(name) in EMULATE:
+        return _conv_emulated(x, sd, name, stride, padding, relu, round_out="rpn_head.objectness" not in name and "rpn_head.anchor" not in name)
     y = F.conv2d(x, sd[name + ".weight"], sd.get(name + ".bias"), stride=stride, padding=padding)
     if name + ".norm.weight" in sd:  # FrozenBatchNorm2d, eps 1e-5
         y = F.batch_norm(y, sd[name + ".norm.running_mean"], sd[name + ".norm.running_var"],
@@ -65,11 +109,22 @@ def resnet(x, sd, depth, prefix="backbone.bottom_up"):
     x = _conv(x, sd, prefix + ".stem.conv1", stride=2, padding=3, relu=True)
     x = F.max_pool2d(x, kernel_size=3, stride=2, padding=1)
     outs = {}
+    if EMULATE:
+        x = _bf(x)
     for si, nblocks in enumerate(STAGE_BLOCKS[depth]):
         stage = "res%d" % (si + 2)
         for b in range(nblocks):
             p = "%s.%s.%d" % (prefix, stage, b)
             stride = 2 if (b == 0 and si > 0) else 1
+            if stage in EMULATE:  # engine: conv3 accumulator + bias (+ shortcut GEMM / residual tile) -> ReLU -> one bf16 rounding
+                y = _conv(x, sd, p + ".conv1", stride=stride, relu=True)
+                y = _conv(y, sd, p + ".conv2", padding=1, relu=True)
+                if (p + ".shortcut.weight") in sd:
+                    short = _conv_emulated(x, sd, p + ".shortcut", stride, 0, False, round_out=False)
+                else:
+                    short = x
+                x = _conv_emulated(y, sd, p + ".conv3", 1, 0, True, add=short)
+                continue
             short = _conv(x, sd, p + ".shortcut", stride=stride) if (p + ".shortcut.weight") in sd else x
             y = _conv(x, sd, p + ".conv1", stride=stride, relu=True)     # stride lives in the 1x1 (stride_in_1x1)
             y = _conv(y, sd, p + ".conv2", padding=1, relu=True)
@@ -83,7 +138,11 @@ def fpn(c, sd, prefix="backbone"):
     prev = _conv(c["res5"], sd, prefix + ".fpn_lateral5")
     p = {"p5": _conv(prev, sd, prefix + ".fpn_output5", padding=1)}
     for lvl in (4, 3, 2):
-        prev = _conv(c["res%d" % lvl], sd, prefix + ".fpn_lateral%d" % lvl) + F.interpolate(prev, scale_factor=2, mode="nearest")
+        if "fpn" in EMULATE:  # engine: lateral accumulator + bias + nearest-2x top-down tile, one bf16 rounding
+            prev = _conv_emulated(c["res%d" % lvl], sd, prefix + ".fpn_lateral%d" % lvl, 1, 0, False,
+                                  add=F.interpolate(prev, scale_factor=2, mode="nearest"))
+        else:
+            prev = _conv(c["res%d" % lvl], sd, prefix + ".fpn_lateral%d" % lvl) + F.interpolate(prev, scale_factor=2, mode="nearest")
         p["p%d" % lvl] = _conv(prev, sd, prefix + ".fpn_output%d" % lvl, padding=1)
     p["p6"] = F.max_pool2d(p["p5"], kernel_size=1, stride=2, padding=0)
     return p
@@ -195,9 +254,17 @@ def roi_pool(feats, boxes_per_image):
 
 def box_head(pooled, sd, prefix="roi_heads"):
     x = pooled.flatten(1)
+    p = prefix + ".box_predictor"
+    if "head" in EMULATE:  # engine: bf16 ROI features / fc operands, fp32 accumulate, bf16 fc1 / fc2 outputs, fp32 predictor outputs
+        x = _bf(x)
+        x = _bf(F.relu(F.linear(x, _bf(sd[prefix + ".box_head.fc1.weight"]), sd[prefix + ".box_head.fc1.bias"])))
+        x = _bf(F.relu(F.linear(x, _bf(sd[prefix + ".box_head.fc2.weight"]), sd[prefix + ".box_head.fc2.bias"])))
+        logits = F.linear(x, _bf(sd[p + ".cls_score.weight"]), sd[p + ".cls_score.bias"])
+        deltas = F.linear(x, _bf(sd[p + ".bbox_pred.weight"]), sd[p + ".bbox_pred.bias"])
+        var = torch.exp(F.linear(x, _bf(sd[p + ".var_pred.weight"]), sd[p + ".var_pred.bias"]))
+        return logits, deltas, var
     x = F.relu(F.linear(x, sd[prefix + ".box_head.fc1.weight"], sd[prefix + ".box_head.fc1.bias"]))
     x = F.relu(F.linear(x, sd[prefix + ".box_head.fc2.weight"], sd[prefix + ".box_head.fc2.bias"]))
-    p = prefix + ".box_predictor"
     logits = F.linear(x, sd[p + ".cls_score.weight"], sd[p + ".cls_score.bias"])
     deltas = F.linear(x, sd[p + ".bbox_pred.weight"], sd[p + ".bbox_pred.bias"])
     var = torch.exp(F.linear(x, sd[p + ".var_pred.weight"], sd[p + ".var_pred.bias"]))

@@ -76,3 +76,27 @@ def test_linear_large_k():
     want = F.relu(x.float() @ w.float().t() + b)
     err = (y.float() - want).abs()
     assert bool((err <= 2e-3 + want.abs() * 2 ** -8).all()), float(err.max())
+
+
+@pytest.mark.parametrize("case", [
+    # N, H, W, Cin (t2), Cin2 (block input), H2, W2, stride2, Cout
+    (2, 50, 64, 64, 64, 50, 64, 1, 256),      # res2.0: conv3 64->256 + shortcut 64->256
+    (2, 25, 32, 128, 256, 50, 64, 2, 512),    # res3.0: conv3 128->512 + stride-2 shortcut 256->512
+    (1, 13, 16, 256, 512, 25, 31, 2, 1024),   # res4.0-like with odd input size, 4 n-tiles
+])
+def test_dual_input_1x1_equals_conv3_plus_projection_shortcut(case):
+    """relu(conv3(t) + shortcut(x)) of a stage's first bottleneck block (resnet.py:205-221) as ONE GEMM over K = [t | x]."""
+    N, H, W, Cin, Cin2, H2, W2, s2, Cout = case
+    g = torch.Generator(device="cuda").manual_seed(sum(case))
+    t = torch.randn(N, H, W, Cin, device="cuda", generator=g).bfloat16()
+    x = torch.randn(N, H2, W2, Cin2, device="cuda", generator=g).bfloat16()
+    w3 = (torch.randn(Cout, 1, 1, Cin, device="cuda", generator=g) / Cin ** 0.5).bfloat16()
+    wsc = (torch.randn(Cout, 1, 1, Cin2, device="cuda", generator=g) / Cin2 ** 0.5).bfloat16()
+    b3, bsc = torch.randn(Cout, device="cuda", generator=g), torch.randn(Cout, device="cuda", generator=g)
+    w = torch.cat([w3.view(Cout, Cin), wsc.view(Cout, Cin2)], 1).contiguous()
+    y = ops.conv1x1_dual_nhwc(t, x, w, b3 + bsc, stride2=s2, relu=True)
+    torch.cuda.synchronize()
+    want = F.relu(ref_conv(t, w3, b3, None, 1, False, 0) + ref_conv(x, wsc, bsc, None, s2, False, 0))
+    assert y.shape == want.shape
+    err = (y.float() - want).abs()
+    assert bool((err <= 1e-3 + want.abs() * 2 ** -8).all()), "max err %g" % float(err.max())

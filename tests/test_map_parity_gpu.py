@@ -1,0 +1,124 @@
+"""Does bf16 tensor-core inference move COCO AP?  (north_star: "identical COCO mAP to two decimals";
+FLIR_evaluation.py:496-563, fast_rcnn.py:86-147, demo_probEn.py:198-298.)
+
+The harness (tests/golden/make_map_harness.py, which also documents how the detector was fitted) stores the fp32
+oracle's detections of two R50-FPN detectors on 64 held-out synthetic RGB+thermal pairs with ground truth, and their
+ProbEn fusion.  Here the B200 engine runs the SAME models on the SAME uint8 frames at the benchmarked shape
+(512x640 frames -> 800x1000 -> 800x1024 canvas, batch 16); its detections and their fusion are scored with the
+COCOeval restatement against the same ground truth.  Tolerance: |AP_gpu - AP_oracle| < 0.5 on the 0..100 scale
+(0.005 absolute = the second decimal of mAP) for AP and AP50 of the fused output and of each model alone, and at
+least 95 % of the oracle's detections must have a same-class GPU detection with IoU > 0.9 and |score diff| < 0.05.
+The measured deltas are written to gpurun_out/map_parity.json (and committed under profiles/).
+"""
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import make_map_harness as H
+from probenb200 import detector, evaluation, pipeline
+
+pytestmark = pytest.mark.gpu
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+GOLD = os.path.join(ROOT, "tests", "golden")
+
+
+def _coco_gt(gold):
+    anns = []
+    off = gold["gt_offsets"]
+    for i in range(len(off) - 1):
+        for g in gold["gt"][off[i]: off[i + 1]]:
+            w, h = float(g[2] - g[0]), float(g[3] - g[1])
+            anns.append({"id": len(anns) + 1, "image_id": i, "category_id": int(g[4]), "bbox": [float(g[0]), float(g[1]), w, h],
+                         "area": w * h, "iscrowd": 0})
+    return anns
+
+
+def _ap(anns, dets, n_img):
+    if not dets:
+        return {"AP": 0.0, "AP50": 0.0, "AP75": 0.0}
+    return evaluation.COCOBBoxEval(anns, dets, image_ids=list(range(n_img))).evaluate()
+
+
+def _match_rate(want, got):
+    """fraction of `want` rows (boxes, scores, classes per image) with a same-class `got` box at IoU > 0.9, |ds| < 0.05"""
+    from torchvision.ops import box_iou
+    hit = tot = 0
+    for (wb, ws, wc), (gb, gs, gc) in zip(want, got):
+        tot += len(ws)
+        if len(ws) == 0 or len(gs) == 0:
+            continue
+        iou = box_iou(torch.as_tensor(wb, dtype=torch.float32).reshape(-1, 4), torch.as_tensor(gb, dtype=torch.float32).reshape(-1, 4))
+        ok = (iou > 0.9) & (torch.as_tensor(wc).reshape(-1, 1) == torch.as_tensor(gc).reshape(1, -1)) & \
+             ((torch.as_tensor(ws, dtype=torch.float32).reshape(-1, 1) - torch.as_tensor(gs, dtype=torch.float32).reshape(1, -1)).abs() < 0.05)
+        hit += int(ok.any(dim=1).sum())
+    return hit / max(1, tot), tot
+
+
+def test_bf16_engine_keeps_coco_ap_of_fp32_oracle():
+    gold = np.load(os.path.join(GOLD, "map_harness_oracle.npz"))
+    heads = np.load(os.path.join(GOLD, "map_harness_heads.npz"))
+    n_img, B = H.N_EVAL, 16
+    anns = _coco_gt(gold)
+    scenes = [H.scene(i, 1) for i in range(n_img)]
+    for i, sc in enumerate(scenes):  # the generator is seeded: the stored ground truth must be reproduced exactly
+        assert np.array_equal(sc[2], gold["gt"][gold["gt_offsets"][i]: gold["gt_offsets"][i + 1]])
+    frames = [np.stack([sc[m] for sc in scenes]) for m in range(2)]
+    dets = [detector.Detector(H.fitted_state_dict(m, heads), depth=50, num_classes=3, max_batch=B, canvas=(800, 1024)) for m in range(2)]
+    pipe = pipeline.ProbEnPipeline(dets, ("probEn", "v-avg"), frame_size=H.FRAME_HW)
+    per_model = [[], []]
+    fused = []
+    for i0 in range(0, n_img, B):
+        dev = [torch.from_numpy(f[i0:i0 + B]).cuda() for f in frames]
+        out = pipe.forward_device(dev, net_hw=H.NET_HW)
+        torch.cuda.synchronize()
+        fused += pipeline.FusedOutput.split(out.flat, B, 2)
+        for m in range(2):
+            per_model[m] += pipe.dets[m].to_instances([H.FRAME_HW] * B)
+    report = {"images": n_img, "gt_boxes": len(anns), "shape": "512x640 -> 800x1000 (canvas 800x1024), batch 16, R50-FPN x2"}
+    # ---- single models
+    for m in range(2):
+        off = gold["m%d_offsets" % m]
+        want = [(gold["m%d_boxes" % m][off[i]: off[i + 1]], gold["m%d_scores" % m][off[i]: off[i + 1]], gold["m%d_classes" % m][off[i]: off[i + 1]])
+                for i in range(n_img)]
+        got = [(inst.pred_boxes.tensor.numpy(), inst.scores.numpy(), inst.pred_classes.numpy()) for inst in per_model[m]]
+        d_want, d_got = [], []
+        for i in range(n_img):
+            d_want += evaluation.instances_to_coco_json(*want[i], i)
+            d_got += evaluation.instances_to_coco_json(*got[i], i)
+        a_w, a_g = _ap(anns, d_want, n_img), _ap(anns, d_got, n_img)
+        rate, tot = _match_rate(want, got)
+        report["model%d" % m] = {"oracle_AP": a_w["AP"], "gpu_AP": a_g["AP"], "oracle_AP50": a_w["AP50"], "gpu_AP50": a_g["AP50"],
+                                 "oracle_AP75": a_w["AP75"], "gpu_AP75": a_g["AP75"],
+                                 "oracle_detections": tot, "gpu_detections": int(sum(len(g[1]) for g in got)), "box_match_rate": rate}
+    # ---- ProbEn fusion of the two models
+    off = gold["fused_offsets"]
+    want = [(gold["fused_boxes"][off[i]: off[i + 1]], gold["fused_scores"][off[i]: off[i + 1]], gold["fused_classes"][off[i]: off[i + 1]])
+            for i in range(n_img)]
+    got = [(np.zeros((0, 4)), np.zeros(0), np.zeros(0)) if f is None else tuple(t.numpy() for t in f) for f in fused]
+    d_want, d_got = [], []
+    for i in range(n_img):
+        d_want += evaluation.instances_to_coco_json(*want[i], i)
+        d_got += evaluation.instances_to_coco_json(*got[i], i)
+    a_w, a_g = _ap(anns, d_want, n_img), _ap(anns, d_got, n_img)
+    rate, tot = _match_rate(want, got)
+    report["proben_fused"] = {"oracle_AP": a_w["AP"], "gpu_AP": a_g["AP"], "oracle_AP50": a_w["AP50"], "gpu_AP50": a_g["AP50"],
+                              "oracle_AP75": a_w["AP75"], "gpu_AP75": a_g["AP75"],
+                              "oracle_detections": tot, "gpu_detections": int(sum(len(g[1]) for g in got)), "box_match_rate": rate}
+    for k in ("model0", "model1", "proben_fused"):
+        r = report[k]
+        r["abs_dAP"], r["abs_dAP50"] = abs(r["gpu_AP"] - r["oracle_AP"]), abs(r["gpu_AP50"] - r["oracle_AP50"])
+    print(json.dumps(report, indent=1))
+    try:
+        os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+        json.dump(report, open(os.path.join(ROOT, "gpurun_out", "map_parity.json"), "w"), indent=1)
+    except OSError:
+        pass
+    for k in ("model0", "model1", "proben_fused"):
+        r = report[k]
+        assert r["oracle_AP"] > 5.0, (k, r)                      # the harness model must actually detect something
+        assert r["abs_dAP"] < 0.5 and r["abs_dAP50"] < 0.5, (k, r)  # 0..100 scale: mAP identical to two decimals
+        assert r["box_match_rate"] >= 0.95, (k, r)
