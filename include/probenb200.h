@@ -155,6 +155,18 @@ PE_API int pe_detector_buffer_info(const pe_detector* d, const char* name, size_
 PE_API int pe_detector_forward(pe_detector* d, const void* weights, const float* images, int B, int img_h, int img_w,
                                float out_h, float out_w, const pe_detections* out, void* workspace, size_t workspace_bytes,
                                void* stream);
+/* Module seams of the reference's registries (modeling/backbone/build.py:20-33, proposal_generator/build.py, roi_heads/roi_heads.py,
+ * meta_arch/build.py:12-19): the same plan, restricted to the stages in `stages`; the stages exchange their tensors through the
+ * named workspace buffers (p2..p6 / pout*_0, proposals + prop_count, head_out), which the host may read or overwrite in between.
+ * prenormalized != 0: `images` already went through rcnn.py:269-286 (what Backbone.forward receives). */
+#define PE_STAGE_BACKBONE 1
+#define PE_STAGE_RPN 2
+#define PE_STAGE_ROI_HEADS 4
+#define PE_STAGE_ALL 7
+PE_API int pe_detector_forward_stages(pe_detector* d, const void* weights, const float* images, int B, int img_h, int img_w,
+                                      float out_h, float out_w, const pe_detections* out, void* workspace, size_t workspace_bytes,
+                                      int stages, int prenormalized, void* stream);
+
 /* Same, from raw uint8 HWC frames [B, src_h, src_w, in_channels]: DefaultPredictor's resize to (img_h, img_w)
  * (pe_resize_frames arithmetic) is fused into the stem's input staging, so no float32 image is materialised. */
 PE_API int pe_detector_forward_frames(pe_detector* d, const void* weights, const uint8_t* frames, int B, int src_h, int src_w,

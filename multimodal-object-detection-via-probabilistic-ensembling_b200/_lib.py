@@ -64,6 +64,8 @@ SIGNATURES.update({
     "pe_detector_buffer_info": (c_int, [c_void_p, c_char_p, ctypes.POINTER(c_size_t), ctypes.POINTER(c_int * 4), ctypes.POINTER(c_int)]),
     "pe_detector_forward": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_float, c_float,
                                     ctypes.POINTER(Detections), c_void_p, c_size_t, c_void_p]),
+    "pe_detector_forward_stages": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_float, c_float,
+                                           ctypes.POINTER(Detections), c_void_p, c_size_t, c_int, c_int, c_void_p]),
     "pe_detector_forward_frames": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_float, c_float,
                                            ctypes.POINTER(Detections), c_void_p, c_size_t, c_void_p]),
     "pe_pack_detections": (c_int, [ctypes.POINTER(Detections), c_int, c_int, c_int] + [c_void_p] * 7),

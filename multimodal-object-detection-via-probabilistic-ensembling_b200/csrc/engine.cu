@@ -244,13 +244,18 @@ struct Runner {
   // raw uint8 frames (resized on the fly) instead of a float32 tensor when frames != nullptr
   const unsigned char* frames = nullptr;
   int src_h = 0, src_w = 0, round_u8 = 0;
+  // module seams (pe_detector_forward_stages): which of backbone / proposal generator / ROI heads run, and whether the images
+  // are already normalised (Backbone.forward receives ImageList.tensor, rcnn.py:269-286 has been applied by the caller)
+  int stages = PE_STAGE_ALL;
+  bool prenormalized = false;
 
   // ResNet bottom-up + FPN for one backbone pass (input channels [c0, c0 + stem_c) of the image tensor)
   void backbone(const float* images, int Ctot, int c0, int img_h, int img_w, int pass) {
     const pe_detector_config& c = d->cfg;
     StemNorm nrm;
     for (int i = 0; i < 8; ++i) { nrm.mean[i] = 0.f; nrm.std[i] = 1.f; }
-    for (int i = 0; i < d->stem_c; ++i) { nrm.mean[i] = c.pixel_mean[c0 + i]; nrm.std[i] = c.pixel_std[c0 + i]; }
+    if (!prenormalized)
+      for (int i = 0; i < d->stem_c; ++i) { nrm.mean[i] = c.pixel_mean[c0 + i]; nrm.std[i] = c.pixel_std[c0 + i]; }
     if (frames)
       check(launch_stem_im2col_u8(frames, buf("stem_canvas"), nullptr, B, Ctot, c0, d->stem_c, src_h, src_w, img_h, img_w, c.canvas_h,
                                   c.canvas_w, round_u8, nrm, st, buf("pil_taps")));
@@ -342,54 +347,59 @@ struct Runner {
   int run(const float* images, int img_h, int img_w, float out_h, float out_w, const pe_detections& o) {
     const pe_detector_config& c = d->cfg;
     const int Ctot = c.in_channels;
-    if (c.middle_fusion) {  // shared backbone on both halves, channel concat (rcnn.py:240-248)
-      backbone(images, Ctot, 0, img_h, img_w, 0);
-      backbone(images, Ctot, 3, img_h, img_w, 1);
-      for (int l = 2; l <= 5 && status == PE_OK; ++l) {
-        char qa[24], qb[24], qp[16];
-        snprintf(qa, sizeof(qa), "pout%d_0", l);
-        snprintf(qb, sizeof(qb), "pout%d_1", l);
-        snprintf(qp, sizeof(qp), "p%d", l);
-        check(launch_concat_channels(buf(qa), buf(qb), buf(qp), (long long)B * d->H[l - 1] * d->W[l - 1], 256, st));
+    if (stages & PE_STAGE_BACKBONE) {
+      if (c.middle_fusion) {  // shared backbone on both halves, channel concat (rcnn.py:240-248)
+        backbone(images, Ctot, 0, img_h, img_w, 0);
+        backbone(images, Ctot, 3, img_h, img_w, 1);
+        for (int l = 2; l <= 5 && status == PE_OK; ++l) {
+          char qa[24], qb[24], qp[16];
+          snprintf(qa, sizeof(qa), "pout%d_0", l);
+          snprintf(qb, sizeof(qb), "pout%d_1", l);
+          snprintf(qp, sizeof(qp), "p%d", l);
+          check(launch_concat_channels(buf(qa), buf(qb), buf(qp), (long long)B * d->H[l - 1] * d->W[l - 1], 256, st));
+        }
+      } else {
+        backbone(images, Ctot, 0, img_h, img_w, 0);
       }
-    } else {
-      backbone(images, Ctot, 0, img_h, img_w, 0);
+      check(launch_subsample2(level_feat(5), buf("p6"), B, d->H[4], d->W[4], d->fc, st));
     }
-    check(launch_subsample2(level_feat(5), buf("p6"), B, d->H[4], d->W[4], d->fc, st));
-    // RPN head on p2..p6 (rpn.py:74-85): 3x3+ReLU, then objectness + deltas as one 16-wide fp32 GEMM
-    RpnLevels lv;
-    for (int l = 2; l <= 6; ++l) {
-      char q[16];
-      snprintf(q, sizeof(q), "rpn_out%d", l);
-      conv("proposal_generator.rpn_head.conv", level_feat(l), d->H[l - 1], d->W[l - 1], 1, true, 0, nullptr, buf("rpn_t"));
-      conv("proposal_generator.rpn_head", buf("rpn_t"), d->H[l - 1], d->W[l - 1], 1, false, 0, nullptr, buf(q), true);
-      lv.out[l - 2] = reinterpret_cast<const float*>(buf(q));
-      lv.H[l - 2] = d->H[l - 1];
-      lv.W[l - 2] = d->W[l - 1];
-      lv.stride[l - 2] = 2 << (l - 1);
-      const double size = 32.0 * (1 << (l - 2));
-      const double ratios[3] = {0.5, 1.0, 2.0};
-      for (int a = 0; a < 3; ++a) {  // anchor_generator.py:151-187
-        const double w = sqrt(size * size / ratios[a]), h = ratios[a] * w;
-        lv.anchor[l - 2][a][0] = (float)(-w / 2.0);
-        lv.anchor[l - 2][a][1] = (float)(-h / 2.0);
-        lv.anchor[l - 2][a][2] = (float)(w / 2.0);
-        lv.anchor[l - 2][a][3] = (float)(h / 2.0);
-      }
-    }
-    RpnScratch rs;
-    rs.cand_box = reinterpret_cast<float4*>(buf("cand_box"));
-    rs.cand_score = reinterpret_cast<float*>(buf("cand_score"));
-    rs.cand_valid = reinterpret_cast<unsigned char*>(buf("cand_valid"));
-    rs.cand_count = reinterpret_cast<int*>(buf("cand_count"));
-    rs.keep_idx = reinterpret_cast<int*>(buf("keep_idx"));
-    rs.keep_count = reinterpret_cast<int*>(buf("keep_count"));
-    rs.nms_mask = reinterpret_cast<unsigned*>(buf("nms_mask"));
     float4* props = reinterpret_cast<float4*>(buf("proposals"));
     int* prop_count = reinterpret_cast<int*>(buf("prop_count"));
-    if (status == PE_OK)
-      check(launch_rpn_proposals(lv, B, c.pre_nms_topk, c.post_nms_topk, c.rpn_nms_thresh, (float)img_h, (float)img_w, rs, kMaxProps,
-                                 props, prop_count, st), 4);
+    if (stages & PE_STAGE_RPN) {
+      // RPN head on p2..p6 (rpn.py:74-85): 3x3+ReLU, then objectness + deltas as one 16-wide fp32 GEMM
+      RpnLevels lv;
+      for (int l = 2; l <= 6; ++l) {
+        char q[16];
+        snprintf(q, sizeof(q), "rpn_out%d", l);
+        conv("proposal_generator.rpn_head.conv", level_feat(l), d->H[l - 1], d->W[l - 1], 1, true, 0, nullptr, buf("rpn_t"));
+        conv("proposal_generator.rpn_head", buf("rpn_t"), d->H[l - 1], d->W[l - 1], 1, false, 0, nullptr, buf(q), true);
+        lv.out[l - 2] = reinterpret_cast<const float*>(buf(q));
+        lv.H[l - 2] = d->H[l - 1];
+        lv.W[l - 2] = d->W[l - 1];
+        lv.stride[l - 2] = 2 << (l - 1);
+        const double size = 32.0 * (1 << (l - 2));
+        const double ratios[3] = {0.5, 1.0, 2.0};
+        for (int a = 0; a < 3; ++a) {  // anchor_generator.py:151-187
+          const double w = sqrt(size * size / ratios[a]), h = ratios[a] * w;
+          lv.anchor[l - 2][a][0] = (float)(-w / 2.0);
+          lv.anchor[l - 2][a][1] = (float)(-h / 2.0);
+          lv.anchor[l - 2][a][2] = (float)(w / 2.0);
+          lv.anchor[l - 2][a][3] = (float)(h / 2.0);
+        }
+      }
+      RpnScratch rs;
+      rs.cand_box = reinterpret_cast<float4*>(buf("cand_box"));
+      rs.cand_score = reinterpret_cast<float*>(buf("cand_score"));
+      rs.cand_valid = reinterpret_cast<unsigned char*>(buf("cand_valid"));
+      rs.cand_count = reinterpret_cast<int*>(buf("cand_count"));
+      rs.keep_idx = reinterpret_cast<int*>(buf("keep_idx"));
+      rs.keep_count = reinterpret_cast<int*>(buf("keep_count"));
+      rs.nms_mask = reinterpret_cast<unsigned*>(buf("nms_mask"));
+      if (status == PE_OK)
+        check(launch_rpn_proposals(lv, B, c.pre_nms_topk, c.post_nms_topk, c.rpn_nms_thresh, (float)img_h, (float)img_w, rs, kMaxProps,
+                                   props, prop_count, st), 4);
+    }
+    if (!(stages & PE_STAGE_ROI_HEADS)) return status;
     // ROI heads (roi_heads.py:595-631)
     RoiLevels fl;
     for (int l = 2; l <= 5; ++l) {
@@ -521,7 +531,16 @@ extern "C" PE_API int pe_detector_buffer_info(const pe_detector* d, const char* 
 extern "C" PE_API int pe_detector_forward(pe_detector* d, const void* weights, const float* images, int B, int img_h, int img_w,
                                           float out_h, float out_w, const pe_detections* out, void* workspace, size_t workspace_bytes,
                                           void* stream) {
-  if (!d || !weights || !images || !out || !workspace) return PE_ERR_INVALID_ARGUMENT;
+  return pe_detector_forward_stages(d, weights, images, B, img_h, img_w, out_h, out_w, out, workspace, workspace_bytes, PE_STAGE_ALL, 0,
+                                    stream);
+}
+
+extern "C" PE_API int pe_detector_forward_stages(pe_detector* d, const void* weights, const float* images, int B, int img_h, int img_w,
+                                                 float out_h, float out_w, const pe_detections* out, void* workspace,
+                                                 size_t workspace_bytes, int stages, int prenormalized, void* stream) {
+  if (!d || !weights || !workspace || !(stages & PE_STAGE_ALL)) return PE_ERR_INVALID_ARGUMENT;
+  if ((stages & PE_STAGE_BACKBONE) && !images) return PE_ERR_INVALID_ARGUMENT;
+  if ((stages & PE_STAGE_ROI_HEADS) && !out) return PE_ERR_INVALID_ARGUMENT;
   if (B < 1 || B > d->cfg.max_batch) return PE_ERR_INVALID_ARGUMENT;
   if (img_h < 1 || img_w < 1 || img_h > d->cfg.canvas_h || img_w > d->cfg.canvas_w) return PE_ERR_INVALID_ARGUMENT;
   if (workspace_bytes < d->ws_bytes) return PE_ERR_WORKSPACE_TOO_SMALL;
@@ -536,7 +555,10 @@ extern "C" PE_API int pe_detector_forward(pe_detector* d, const void* weights, c
   r.ws = reinterpret_cast<unsigned char*>(workspace);
   r.st = reinterpret_cast<cudaStream_t>(stream);
   r.B = B;
-  return r.run(images, img_h, img_w, out_h, out_w, *out);
+  r.stages = stages;
+  r.prenormalized = prenormalized != 0;
+  static const pe_detections none = {};
+  return r.run(images, img_h, img_w, out_h, out_w, out ? *out : none);
 }
 
 extern "C" PE_API int pe_detector_forward_frames(pe_detector* d, const void* weights, const uint8_t* frames, int B, int src_h, int src_w,

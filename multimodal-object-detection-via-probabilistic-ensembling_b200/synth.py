@@ -75,14 +75,19 @@ def image_info(det, i):
             "vars": det["vars"][i]}
 
 
-def synth_packed(num_images, num_models=2, mean_dets=7.5, seed=0, K=3, img_w=640, img_h=512):
+def synth_packed(num_images, num_models=2, mean_dets=7.5, seed=0, K=3, img_w=640, img_h=512, force_count=None):
     """Fast vectorised generator for benchmark-scale batches (millions of images): returns the packed SoA
     numpy arrays of ``fusion.pack_detections`` directly.  Per (image, model) Poisson(mean_dets) detections;
-    consecutive models re-detect the same objects with jitter so that cross-model clusters form."""
+    consecutive models re-detect the same objects with jitter so that cross-model clusters form.
+    ``force_count``: every model detects exactly that many objects per image (the detector's 100-per-image regime)."""
     rng = np.random.default_rng(seed)
     B, M = num_images, num_models
-    cnt_obj = rng.poisson(mean_dets / 0.8, size=B)
-    hit = [rng.random(int(cnt_obj.sum())) < 0.8 for _ in range(M)]
+    if force_count is None:
+        cnt_obj = rng.poisson(mean_dets / 0.8, size=B)
+        hit = [rng.random(int(cnt_obj.sum())) < 0.8 for _ in range(M)]
+    else:
+        cnt_obj = np.full(B, int(force_count))
+        hit = [np.ones(int(cnt_obj.sum()), bool) for _ in range(M)]
     obj_img = np.repeat(np.arange(B), cnt_obj)
     oxy = rng.uniform([0, 0], [img_w - 130, img_h - 130], size=(len(obj_img), 2))
     owh = rng.uniform(10, 120, size=(len(obj_img), 2))

@@ -20,7 +20,7 @@ model's:
 tests/test_map_parity_gpu.py rebuilds the same state dicts, runs the B200 engine on the same uint8 frames and compares
 COCO AP (probenb200.evaluation.COCOBBoxEval) of GPU vs oracle detections against the same ground truth.
 
-Run:  python tests/golden/make_map_harness.py            (about 15 minutes on 8 cores)
+Run:  python tests/golden/make_map_harness.py            (about 25 minutes on 8 cores)
 """
 import os
 import sys
@@ -39,7 +39,7 @@ from oracle import proben_oracle as O  # noqa: E402
 from oracle import resize_oracle as R  # noqa: E402
 from probenb200 import weights  # noqa: E402
 
-N_TRAIN, N_EVAL = 24, 64
+N_TRAIN, N_EVAL = 48, 96
 SEEDS = (11, 12)            # RGB model, thermal model (the bench's seeds)
 FRAME_HW = (512, 640)
 NET_HW = (800, 1000)
@@ -233,7 +233,14 @@ def fit_model(sd, modality, log):
             lg, dl = D.rpn_head(list(p4) + [p6], sd)
             props, _ = D.find_top_proposals(lg, dl, sizes, cfg)
         pb = props[0][0]
-        jit = gtb.repeat(6, 1) * (1 + 0.08 * torch.randn(len(gtb) * 6, 4, generator=g))
+        # jittered copies of the ground truth (roi_heads.py appends the GT boxes to the proposals during training; many
+        # jitters per box give the 1024-feature ridge regression enough foreground rows to pull near-duplicate proposals onto
+        # the SAME refined box - without that, which duplicate survives NMS decides the output box and detections become chaotic)
+        reps = 30
+        sig = torch.cat([torch.full((len(gtb) * (reps // 2), 1), 0.05), torch.full((len(gtb) * (reps - reps // 2), 1), 0.15)])
+        wh = torch.cat([gtb[:, 2:] - gtb[:, :2], gtb[:, 2:] - gtb[:, :2]], 1).repeat(reps, 1)
+        jit = gtb.repeat(reps, 1) + sig * wh * torch.randn(len(gtb) * reps, 4, generator=g)
+        jit = jit[(jit[:, 2] > jit[:, 0] + 4) & (jit[:, 3] > jit[:, 1] + 4)]
         pb = torch.cat([pb, D.clip_boxes(jit, sizes[0])])
         with torch.no_grad():
             pooled = D.roi_pool(list(p4), [pb])
