@@ -310,6 +310,12 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  // Programmatic dependent launch: this grid may have been scheduled while the previous kernel of the stream was still
+  // draining (its CTAs retire one by one; ours take the freed SMs and run the prologue above).  Everything below reads or
+  // writes tensors of the layer chain, so it waits for the previous grid to complete and flush; our own dependents may be
+  // scheduled as soon as every CTA of this grid got here.
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 
   // tile -> (n tile, patch column, patch row, image) without integer division
   auto decompose = [&](int tile, int& nt, int& tw, int& th, int& img) {
@@ -784,8 +790,19 @@ int launch_conv(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap&
   }
   const int tiles = a.N * a.tiles_h * a.tiles_w * a.tiles_n;
   const int grid = tiles < sm_count() ? tiles : sm_count();
-  conv_gemm_kernel<BLOCK_N, kStaged><<<grid, kThreads, Cfg::kSmemBytes, st>>>(ma, mb, mo, mr, ma2, a);
-  PE_LAUNCH_CHECK();
+  // PE_CONV_PDL=0 launches the layers fully serialised (A/B switch)
+  static const int pdl = [] { const char* e = getenv("PE_CONV_PDL"); return e ? atoi(e) : 1; }();
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)grid);
+  cfg.blockDim = dim3((unsigned)kThreads);
+  cfg.dynamicSmemBytes = Cfg::kSmemBytes;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl ? 1 : 0;
+  PE_CUDA_CHECK(cudaLaunchKernelEx(&cfg, conv_gemm_kernel<BLOCK_N, kStaged>, ma, mb, mo, mr, ma2, a));
   return PE_OK;
 }
 
