@@ -11,16 +11,14 @@ void set_last_error(cudaError_t e, const char* where) {
 }
 
 int sm_count() {
-  static int cached = 0;
-  if (cached == 0) {
-    int dev = 0, n = 0;
-    if (cudaGetDevice(&dev) == cudaSuccess &&
-        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && n > 0)
-      cached = n;
-    else
-      return 148;
+  static int cached[128] = {0};  // per device ordinal; a benign race writes the same value twice
+  int dev = 0, n = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 128) return 148;
+  if (cached[dev] == 0) {
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && n > 0) cached[dev] = n;
+    else return 148;
   }
-  return cached;
+  return cached[dev];
 }
 }  // namespace pe
 

@@ -28,7 +28,24 @@ void set_last_error(cudaError_t e, const char* where);
 
 constexpr unsigned kFullMask = 0xffffffffu;
 
-int sm_count();
+int sm_count();  // of the CURRENT device (cached per device)
+
+// Per-device, thread-safe "do once" guard for cudaFuncSetAttribute(MaxDynamicSharedMemorySize): the attribute belongs to the
+// (function, device) pair, so a process that drives several GPUs - or two host threads racing through the first launch -
+// must set it once per device.  Returns true when the caller has to perform the setup for the current device.
+struct DeviceOnce {
+  unsigned long long done[2] = {0ull, 0ull};  // bit per device ordinal (up to 128 devices)
+  bool needed() const {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 128) return true;
+    return !((__atomic_load_n(&done[dev >> 6], __ATOMIC_ACQUIRE) >> (dev & 63)) & 1ull);
+  }
+  void mark() {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 128) return;
+    __atomic_fetch_or(&done[dev >> 6], 1ull << (dev & 63), __ATOMIC_RELEASE);
+  }
+};
 
 template <typename T>
 __host__ __device__ constexpr T ceil_div(T a, T b) { return (a + b - 1) / b; }

@@ -782,11 +782,11 @@ int launch_conv(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap&
   a.mul_tiles_w = div_mul(a.tiles_w);
   a.mul_tiles_h = div_mul(a.tiles_h);
   if ((long long)a.N * a.tiles_h * a.tiles_w * a.tiles_n * 2048 >= (1ll << 32)) return PE_ERR_UNSUPPORTED;  // fast_div range
-  static bool attr_done = false;
-  if (!attr_done) {
+  static DeviceOnce attr_once;  // one per template instantiation
+  if (attr_once.needed()) {
     PE_CUDA_CHECK(cudaFuncSetAttribute(conv_gemm_kernel<BLOCK_N, kStaged>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        Cfg::kSmemBytes));
-    attr_done = true;
+    attr_once.mark();
   }
   const int tiles = a.N * a.tiles_h * a.tiles_w * a.tiles_n;
   const int grid = tiles < sm_count() ? tiles : sm_count();

@@ -1339,19 +1339,19 @@ int launch_concat_channels(const void* a, const void* b, void* y, long long pixe
 int launch_rpn_proposals(const RpnLevels& lv, int B, int pre_topk, int post_topk, float nms_thr, float img_h, float img_w,
                          const RpnScratch& s, int max_props, float4* props, int* prop_count, cudaStream_t st) {
   if (pre_topk > kTopkCap || pre_topk < 1) return PE_ERR_UNSUPPORTED;
-  static bool topk_attr = false;
-  if (!topk_attr) {
+  static DeviceOnce topk_once;
+  if (topk_once.needed()) {
     PE_CUDA_CHECK(cudaFuncSetAttribute(rpn_topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTopkSmemBytes));
-    topk_attr = true;
+    topk_once.mark();
   }
   rpn_topk_kernel<<<dim3(kRpnLevels, B), kTopkThreads, kTopkSmemBytes, st>>>(lv, pre_topk, img_h, img_w, s.cand_box, s.cand_score, s.cand_valid,
                                                                              s.cand_count);
   PE_LAUNCH_CHECK();
   const size_t smem = 1024 * 32 * sizeof(unsigned);
-  static bool attr = false;
-  if (!attr) {
+  static DeviceOnce scan_once;
+  if (scan_once.needed()) {
     PE_CUDA_CHECK(cudaFuncSetAttribute(nms_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr = true;
+    scan_once.mark();
   }
   nms_mask_kernel<<<dim3(B * kRpnLevels, 1024 / kNmsRowsPerBlock), kNmsThreads, 0, st>>>(s.cand_box, s.cand_count, kTopkCap, nms_thr, s.nms_mask);
   PE_LAUNCH_CHECK();

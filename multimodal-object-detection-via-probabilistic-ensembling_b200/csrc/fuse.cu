@@ -718,11 +718,11 @@ int launch_fuse(const FuseArgs& a, cudaStream_t st) {
   else if (a.score_mode == PE_SCORE_AVG) fuse_packed_kernel<K, PE_SCORE_AVG, false><<<grid, kBlockThreads, 0, st>>>(a);
   else fuse_packed_kernel<K, PE_SCORE_MAX, false><<<grid, kBlockThreads, 0, st>>>(a);
   PE_LAUNCH_CHECK();
-  static bool attr_set[8] = {false};
-  if (!attr_set[K]) {
+  static DeviceOnce attr_once;  // one per K instantiation
+  if (attr_once.needed()) {
     PE_CUDA_CHECK(cudaFuncSetAttribute(fuse_block_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        (int)block_smem_bytes()));
-    attr_set[K] = true;
+    attr_once.mark();
   }
   const int grid_b = a.B < sms ? a.B : sms;
   fuse_block_kernel<K><<<grid_b, kBlockThreads, block_smem_bytes(), st>>>(a);

@@ -236,8 +236,9 @@ class Detector:
         B, _, h, w = images.shape
         out = out or self.out
         det = out.struct()
-        st = self.lib.pe_detector_forward(self.handle, _lib.ptr(self.weights), _lib.ptr(images), B, h, w, float(out_hw[0]), float(out_hw[1]),
-                                          ctypes.byref(det), _lib.ptr(self.workspace), self.ws_bytes, _lib.current_stream_ptr(images.device))
+        with torch.cuda.device(images.device):  # the engine launches on the CURRENT device: make it the tensors' device
+            st = self.lib.pe_detector_forward(self.handle, _lib.ptr(self.weights), _lib.ptr(images), B, h, w, float(out_hw[0]), float(out_hw[1]),
+                                              ctypes.byref(det), _lib.ptr(self.workspace), self.ws_bytes, _lib.current_stream_ptr(images.device))
         _lib.check(st, "pe_detector_forward")
         return out
 
@@ -250,9 +251,10 @@ class Detector:
         B, H, W, _ = frames_u8.shape
         out = out or self.out
         det = out.struct()
-        st = self.lib.pe_detector_forward_frames(self.handle, _lib.ptr(self.weights), _lib.ptr(frames_u8), B, H, W, int(net_hw[0]), int(net_hw[1]),
-                                                 int(round_u8), float(H), float(W), ctypes.byref(det), _lib.ptr(self.workspace), self.ws_bytes,
-                                                 _lib.current_stream_ptr(frames_u8.device))
+        with torch.cuda.device(frames_u8.device):
+            st = self.lib.pe_detector_forward_frames(self.handle, _lib.ptr(self.weights), _lib.ptr(frames_u8), B, H, W, int(net_hw[0]), int(net_hw[1]),
+                                                     int(round_u8), float(H), float(W), ctypes.byref(det), _lib.ptr(self.workspace), self.ws_bytes,
+                                                     _lib.current_stream_ptr(frames_u8.device))
         _lib.check(st, "pe_detector_forward_frames")
         return out
 

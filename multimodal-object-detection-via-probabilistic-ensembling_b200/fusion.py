@@ -109,11 +109,12 @@ def fuse_packed(dev, method, iou_thr=0.5, img_w=640.0, img_h=512.0, buffers=None
         return buffers
     # a zero-row batch still needs valid pointers
     p = lambda t: _lib.ptr(t if t.numel() else buffers.out_boxes)
-    st = lib.pe_fuse_batch(p(dev["boxes"]), p(dev["scores"]), p(dev["classes"]), p(dev["probs"]), p(dev["vars"]),
-                           _lib.ptr(dev["offsets"]), B, M, K, float(iou_thr), sm, bm, float(img_w), float(img_h),
-                           _lib.ptr(buffers.out_boxes), _lib.ptr(buffers.out_scores), _lib.ptr(buffers.out_classes),
-                           _lib.ptr(buffers.out_counts), _lib.ptr(buffers.workspace), buffers.ws_bytes,
-                           _lib.current_stream_ptr(dev["boxes"].device))
+    with torch.cuda.device(dev["boxes"].device):  # the library launches on the current device
+        st = lib.pe_fuse_batch(p(dev["boxes"]), p(dev["scores"]), p(dev["classes"]), p(dev["probs"]), p(dev["vars"]),
+                               _lib.ptr(dev["offsets"]), B, M, K, float(iou_thr), sm, bm, float(img_w), float(img_h),
+                               _lib.ptr(buffers.out_boxes), _lib.ptr(buffers.out_scores), _lib.ptr(buffers.out_classes),
+                               _lib.ptr(buffers.out_counts), _lib.ptr(buffers.workspace), buffers.ws_bytes,
+                               _lib.current_stream_ptr(dev["boxes"].device))
     _lib.check(st, "pe_fuse_batch")
     return buffers
 

@@ -102,10 +102,11 @@ class _Engine:
     def run(self, stages, images=None, B=1, img_hw=(1, 1), out_hw=(1.0, 1.0), out=None, prenormalized=True):
         d = self.det
         det = out.struct() if out is not None else None
-        st = d.lib.pe_detector_forward_stages(d.handle, _lib.ptr(d.weights), _lib.ptr(images), B, int(img_hw[0]), int(img_hw[1]),
-                                              float(out_hw[0]), float(out_hw[1]), ctypes.byref(det) if det is not None else None,
-                                              _lib.ptr(d.workspace), d.ws_bytes, stages, int(prenormalized),
-                                              _lib.current_stream_ptr(d.device))
+        with torch.cuda.device(d.device):
+            st = d.lib.pe_detector_forward_stages(d.handle, _lib.ptr(d.weights), _lib.ptr(images), B, int(img_hw[0]), int(img_hw[1]),
+                                                  float(out_hw[0]), float(out_hw[1]), ctypes.byref(det) if det is not None else None,
+                                                  _lib.ptr(d.workspace), d.ws_bytes, stages, int(prenormalized),
+                                                  _lib.current_stream_ptr(d.device))
         _lib.check(st, "pe_detector_forward_stages")
 
 

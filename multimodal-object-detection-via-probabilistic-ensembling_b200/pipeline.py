@@ -127,15 +127,16 @@ class ProbEnPipeline:
             for m in range(self.M):
                 main.wait_event(self.ev_done[m])
         o = self.out
-        st = self.lib.pe_pack_detections(self.det_structs, self.M, B, self.K, _lib.ptr(o.offsets), _lib.ptr(self.in_boxes),
-                                         _lib.ptr(self.in_scores), _lib.ptr(self.in_classes), _lib.ptr(self.in_probs),
-                                         _lib.ptr(self.in_vars), stream)
-        _lib.check(st, "pe_pack_detections")
-        st = self.lib.pe_fuse_batch(_lib.ptr(self.in_boxes), _lib.ptr(self.in_scores), _lib.ptr(self.in_classes), _lib.ptr(self.in_probs),
-                                    _lib.ptr(self.in_vars), _lib.ptr(o.offsets), B, self.M, self.K, self.iou_thr, self.codes[0], self.codes[1],
-                                    float(self.frame_w), float(self.frame_h), _lib.ptr(o.boxes), _lib.ptr(o.scores), _lib.ptr(o.classes),
-                                    _lib.ptr(o.counts), _lib.ptr(self.fuse_ws), self.ws_bytes, stream)
-        _lib.check(st, "pe_fuse_batch")
+        with torch.cuda.device(self.device):
+            st = self.lib.pe_pack_detections(self.det_structs, self.M, B, self.K, _lib.ptr(o.offsets), _lib.ptr(self.in_boxes),
+                                             _lib.ptr(self.in_scores), _lib.ptr(self.in_classes), _lib.ptr(self.in_probs),
+                                             _lib.ptr(self.in_vars), stream)
+            _lib.check(st, "pe_pack_detections")
+            st = self.lib.pe_fuse_batch(_lib.ptr(self.in_boxes), _lib.ptr(self.in_scores), _lib.ptr(self.in_classes), _lib.ptr(self.in_probs),
+                                        _lib.ptr(self.in_vars), _lib.ptr(o.offsets), B, self.M, self.K, self.iou_thr, self.codes[0],
+                                        self.codes[1], float(self.frame_w), float(self.frame_h), _lib.ptr(o.boxes), _lib.ptr(o.scores),
+                                        _lib.ptr(o.classes), _lib.ptr(o.counts), _lib.ptr(self.fuse_ws), self.ws_bytes, stream)
+            _lib.check(st, "pe_fuse_batch")
         return o
 
     def gather(self, out, group=None):
