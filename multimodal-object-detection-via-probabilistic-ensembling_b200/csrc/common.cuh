@@ -55,8 +55,8 @@ __host__ __device__ constexpr T ceil_div(T a, T b) { return (a + b - 1) / b; }
 // shortcut of the first block of a stage as one GEMM, resnet.py:205-221)
 struct ConvSecondInput { const void* x; int Cin, H, W, stride; };
 int conv2d_launch(const pe_conv_desc& d, const void* x, const void* w, const float* bias, const void* residual, void* y,
-                  cudaStream_t st, const ConvSecondInput* x2 = nullptr);
+                  cudaStream_t st, const ConvSecondInput* x2 = nullptr, int reverse = 0);
 
-int conv_stem_launch(const void* canvas, const void* w, const float* bias, void* y, int B, int Hc, int Wc, cudaStream_t st);
+int conv_stem_launch(const void* canvas, const void* w, const float* bias, void* y, int B, int Hc, int Wc, cudaStream_t st, int reverse = 0);
 
 }  // namespace pe

@@ -47,6 +47,8 @@ struct ConvArgs {
   int TH, TW, tiles_h, tiles_w, tiles_n;
   uint32_t mul_tiles_n, mul_tiles_w, mul_tiles_h;  // fast_div multipliers of the tile decomposition
   int k_chunks;  // ceil(Cin / 64)
+  int reverse;   // walk the tiles from the last to the first: consecutive layers alternate direction, so a layer starts with
+                 // the part of its input that the previous layer wrote last and that is still in the 126 MB L2
   int k_chunks1; // dual-input 1x1 (bottleneck conv3 + projection shortcut as ONE GEMM over K = [t2 | x]): chunks [0, k_chunks1) come
                  // from map_a, the rest from map_a2 (the block input, strided for stride-2 stages); == k_chunks otherwise
   int relu, residual_mode, out_fp32, in_fp16;
@@ -319,6 +321,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
 
   // tile -> (n tile, patch column, patch row, image) without integer division
   auto decompose = [&](int tile, int& nt, int& tw, int& th, int& img) {
+    if (a.reverse) tile = num_tiles - 1 - tile;
     const uint32_t mt = fast_div((uint32_t)tile, a.mul_tiles_n);
     nt = tile - (int)mt * a.tiles_n;
     const uint32_t r = fast_div(mt, a.mul_tiles_w);
@@ -587,7 +590,8 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
       int p = 0;          // staging buffer of the running sub-tile
       uint32_t par = 0;   // its barrier parity
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const int n0 = (tile - (int)fast_div((uint32_t)tile, a.mul_tiles_n) * a.tiles_n) * BLOCK_N;
+        const int ptile = a.reverse ? num_tiles - 1 - tile : tile;
+        const int n0 = (ptile - (int)fast_div((uint32_t)ptile, a.mul_tiles_n) * a.tiles_n) * BLOCK_N;
         const int left = (a.Cout - n0) >> 6;
         const int nsub = left < kSub ? left : kSub;
         for (int s2 = 0; s2 < nsub; ++s2) {
@@ -809,7 +813,7 @@ int launch_conv(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap&
 }  // namespace
 
 int conv2d_launch(const pe_conv_desc& d, const void* x, const void* w, const float* bias, const void* residual, void* y,
-                  cudaStream_t st, const ConvSecondInput* x2) {
+                  cudaStream_t st, const ConvSecondInput* x2, int reverse) {
   if (x2 && x2->x) {  // dual-input 1x1: y = act([x | x2(strided)] . w + bias), w = [Cout][Cin + Cin2]
     if (d.KH != 1 || d.KW != 1 || d.stride != 1 || d.Cin % 64 || x2->Cin % 8 || (x2->stride != 1 && x2->stride != 2)) return PE_ERR_UNSUPPORTED;
     if ((x2->H - 1) / x2->stride + 1 != d.H || (x2->W - 1) / x2->stride + 1 != d.W) return PE_ERR_INVALID_ARGUMENT;
@@ -846,6 +850,7 @@ int conv2d_launch(const pe_conv_desc& d, const void* x, const void* w, const flo
   a.tiles_n = ceil_div(d.Cout, bn);
   a.k_chunks = ceil_div(d.Cin, kBlockK);  // a ragged last chunk is zero-filled by TMA (A and W alike)
   a.k_chunks1 = a.k_chunks;
+  a.reverse = reverse ? 1 : 0;
   const bool dual = x2 && x2->x;
   if (dual) a.k_chunks += ceil_div(x2->Cin, kBlockK);
   a.relu = d.relu;
@@ -968,7 +973,7 @@ int conv2d_launch(const pe_conv_desc& d, const void* x, const void* w, const flo
 // j = kw*4 + c over an 8-pixel window (kw = 7 and c >= C carry zero weights).  The A operand is read through a
 // 5-D tensor map whose wo dimension has a 16-byte stride (overlapping 64-byte windows) and whose row dimension
 // is split into (parity, row/2), so no im2col matrix is ever written.
-int conv_stem_launch(const void* canvas, const void* w, const float* bias, void* y, int B, int Hc, int Wc, cudaStream_t st) {
+int conv_stem_launch(const void* canvas, const void* w, const float* bias, void* y, int B, int Hc, int Wc, cudaStream_t st, int reverse) {
   if (!canvas || !w || !y || B < 1 || Hc % 32 || Wc % 32) return PE_ERR_INVALID_ARGUMENT;
   const int Hp = Hc + 6, Wp = Wc + 8;
   ConvArgs a = {};
@@ -983,6 +988,7 @@ int conv_stem_launch(const void* canvas, const void* w, const float* bias, void*
   a.tiles_n = 1;
   a.k_chunks = 1;
   a.k_chunks1 = 1;
+  a.reverse = reverse ? 1 : 0;
   a.relu = 1; a.residual_mode = 0; a.out_fp32 = 0; a.in_fp16 = 1; a.stem_mode = mode;
   a.canvas = reinterpret_cast<const unsigned char*>(canvas);
   a.canvas_hp = Hp;

@@ -5,6 +5,7 @@
 // publishes as a manifest (pe_detector_param_*); activations live in a caller-owned workspace.
 #include <math.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 #include <string>
 #include <vector>
@@ -187,6 +188,7 @@ struct Runner {
   cudaStream_t st;
   int B;
   int status = PE_OK;
+  int rev = 0;  // tile direction of the last GEMM launch
 
   void* buf(const char* name) const { return ws + d->find_buf(name)->off; }
 
@@ -213,7 +215,10 @@ struct Runner {
       d->prof_bytes.push_back(bytes);
       cudaEventRecord(e0, st);
     }
-    const int s = conv2d_launch(cd, x, w, bias, res, y, st, x2);
+    // consecutive layers walk their tiles in opposite directions (conv_gemm.cu ConvArgs::reverse); PE_CONV_REVERSE=0 disables
+    static const int alternate = [] { const char* e = getenv("PE_CONV_REVERSE"); return e ? atoi(e) : 1; }();
+    rev ^= alternate;
+    const int s = conv2d_launch(cd, x, w, bias, res, y, st, x2, rev);
     if (d->profiling) cudaEventRecord(e1, st);
     d->last_launches++;
     d->last_gemm_launches++;
@@ -281,7 +286,7 @@ struct Runner {
       }
       if (status == PE_OK)
         status = conv_stem_launch(buf("stem_canvas"), wts + p.w_off, reinterpret_cast<const float*>(wts + p.b_off), buf("stem_out"), B,
-                                  c.canvas_h, c.canvas_w, st);
+                                  c.canvas_h, c.canvas_w, st, rev = 0);
       if (e1) cudaEventRecord(e1, st);
       d->last_launches++;
       d->last_gemm_launches++;
