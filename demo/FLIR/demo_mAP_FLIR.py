@@ -45,7 +45,7 @@ def main(argv=None):
         dets += evaluation.instances_to_coco_json(boxes, scores, classes, iid)
     evaluation.unmap_category_ids(dets, gt.get("categories"))  # FLIR_evaluation.py:163-175
     ev = evaluation.COCOBBoxEval(gt["annotations"], dets, image_ids=[im["id"] for im in gt["images"]])
-    res = ev.evaluate()
+    res = ev.evaluate(device="cuda")  # matching on the GPU (pe_coco_match)
     print("Evaluation results for bbox:")
     print(" | ".join("%s %.3f" % (k, v) for k, v in res.items()))
     out = os.path.join(args.outfolder, "FLIR_%s_mAP.json" % args.fusion_method)

@@ -142,7 +142,7 @@ def main(argv=None):
     json.dump(coco_dets, open(out_json, "w"))
     if gt is not None:
         ev = evaluation.COCOBBoxEval(gt["annotations"], coco_dets, image_ids=[im["id"] for im in gt["images"]])
-        res = ev.evaluate()
+        res = ev.evaluate(device="cuda")  # matching on the GPU (pe_coco_match); decisions identical to the host evaluator
         print("Evaluation results for bbox:")
         print(" | ".join("%s %.3f" % (k, v) for k, v in res.items()))
         return res

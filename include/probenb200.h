@@ -97,6 +97,14 @@ PE_API int pe_conv2d_fwd(const pe_conv_desc* desc, const void* x, const void* w,
  * read at `stride2` (1 | 2) so that it lands on x's H x W grid.  This is how the engine runs the first bottleneck block of a
  * stage: out = relu(conv3(t) + shortcut(x)) (modeling/backbone/resnet.py:205-221) = relu([t | x] . [W3 | Wsc] + b3 + bsc): the
  * projection-shortcut tensor is never written to HBM.  desc: KH = KW = 1, stride = 1, residual_mode = 0, Cin % 64 == 0. */
+/* 1x1 conv with a CHAINED 1x1 conv on its own output: y = act([x | x2] . w + bias (+ residual)), y_c = act_c(y . wc + bias_c) with
+ * wc = [n_c][Cout] bf16, n_c in {64, 128, 256}, y_c = [N, H, W, n_c] bf16.  The chained GEMM reads y's bf16 tiles from the shared-memory
+ * staging buffers of the first epilogue (they are K-major 128B-swizzled A tiles already), so y is not re-read from HBM.  The engine
+ * runs a bottleneck's conv3 and the NEXT block's conv1 this way (modeling/backbone/resnet.py:205-221).  x2 may be NULL (no second
+ * input).  desc: KH = KW = 1, stride 1, bf16 output, Cout % 256 == 0, residual_mode 0 | 1. */
+PE_API int pe_conv1x1_chain_fwd(const pe_conv_desc* desc, const void* x, const void* x2, int cin2, int h2, int w2, int stride2,
+                                const void* w, const float* bias, const void* residual, void* y, const void* wc,
+                                const float* bias_c, int n_c, int relu_c, void* y_c, void* stream);
 PE_API int pe_conv1x1_dual_fwd(const pe_conv_desc* desc, const void* x, const void* x2, int cin2, int h2, int w2, int stride2,
                                const void* w, const float* bias, void* y, void* stream);
 
@@ -231,6 +239,22 @@ PE_API int pe_batched_nms(const float* boxes, const float* scores, const int64_t
 PE_API int pe_roi_align_forward(const float* input, int N, int C, int H, int W, const float* rois, int num_rois,
                                 float spatial_scale, int pooled_h, int pooled_w, int sampling_ratio, int aligned,
                                 float* out, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * COCO bbox evaluation, matching stage: COCOeval.evaluateImg + computeIoU of the reference's vendored
+ * pycocotools (detectron2/pycocotools/cocoeval.py:124-320; `_mask.iou` = maskApi bbIou) as FLIREvaluator drives them
+ * (detectron2/evaluation/FLIR_evaluation.py:496-563).  Groups p = (image, category) pairs with any ground truth or detection:
+ *   gt_boxes [n_gt,4] xywh float64, gt_area [n_gt], gt_iscrowd [n_gt] (= the 'ignore' flag, cocoeval.py:246), gt_offsets [P+1];
+ *   dt_boxes [n_dt,4] xywh float64 sorted by descending score inside each group (stable) and capped at maxDets, dt_area, dt_offsets;
+ *   iou_thrs [T], area_rng [A][2]; T * A <= 64.
+ * Outputs (uint8): dt_matched [A][T][n_dt], dt_ignore [A][T][n_dt], gt_ignore [A][n_gt].  The accumulate stage stays on the host
+ * (probenb200/evaluation.py).  max_gt_per_group sizes the per-block scratch (<= pe_coco_match_max_gt()).
+ */
+PE_API int pe_coco_match_max_gt(void);
+PE_API int pe_coco_match(const double* gt_boxes, const double* gt_area, const uint8_t* gt_iscrowd, const int32_t* gt_offsets,
+                         const double* dt_boxes, const double* dt_area, const int32_t* dt_offsets, int P, const double* iou_thrs, int T,
+                         const double* area_rng, int A, long long n_dt, long long n_gt, int max_gt_per_group, uint8_t* dt_matched,
+                         uint8_t* dt_ignore, uint8_t* gt_ignore, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Input side (demo/FLIR/demo_FLIR_save_predictions.py:93-121: cv2.imread of the RGB / thermal JPEGs, cv2.resize of

@@ -31,6 +31,8 @@ class ConvDesc(ctypes.Structure):
 
 
 SIGNATURES["pe_conv2d_fwd"] = (c_int, [ctypes.POINTER(ConvDesc)] + [c_void_p] * 6)
+SIGNATURES["pe_conv1x1_chain_fwd"] = (c_int, [ctypes.POINTER(ConvDesc), c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p,
+                                               c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p])
 SIGNATURES["pe_conv1x1_dual_fwd"] = (c_int, [ctypes.POINTER(ConvDesc), c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p,
                                               c_void_p, c_void_p])
 
@@ -97,6 +99,12 @@ SIGNATURES.update({
     "pe_jpeg_image_info": (c_int, [c_void_p, c_void_p, c_size_t, ctypes.POINTER(c_int), ctypes.POINTER(c_int), ctypes.POINTER(c_int)]),
     "pe_jpeg_decode_batch": (c_int, [c_void_p, ctypes.POINTER(c_void_p), ctypes.POINTER(c_size_t), c_int, c_void_p, c_int, c_int, c_void_p]),
     "pe_resize_u8_cv": (c_int, [c_void_p, c_int, c_int, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p]),
+})
+
+SIGNATURES.update({
+    "pe_coco_match_max_gt": (c_int, []),
+    "pe_coco_match": (c_int, [c_void_p] * 7 + [c_int, c_void_p, c_int, c_void_p, c_int, ctypes.c_longlong, ctypes.c_longlong, c_int,
+                              c_void_p, c_void_p, c_void_p, c_void_p]),
 })
 
 _lib = None

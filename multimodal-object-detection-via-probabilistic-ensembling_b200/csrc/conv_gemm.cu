@@ -47,6 +47,14 @@ struct ConvArgs {
   int TH, TW, tiles_h, tiles_w, tiles_n;
   uint32_t mul_tiles_n, mul_tiles_w, mul_tiles_h;  // fast_div multipliers of the tile decomposition
   int k_chunks;  // ceil(Cin / 64)
+  // chained 1x1 (bottleneck conv3 -> the NEXT block's conv1 in the same kernel): the bf16 output sub-tiles that the epilogue
+  // stages in shared memory for the TMA store are exactly K-major 128B-swizzled A tiles, so a second tcgen05 GEMM consumes them
+  // in place: acc2[128 px, chain_n] += out_tile[:, 64-channel chunk] . W2[chunk]; its epilogue (bias2, ReLU) is stored through
+  // map_out2.  The next block's conv1 launch and its re-read of this layer's output from HBM disappear.
+  int chain_n;        // 0 = off; 64 | 128 | 256 output channels of the chained conv
+  int chain_relu;
+  int b2_stages;      // ring depth of the chained weight chunks ([chain_n x 64] bf16 each)
+  const float* chain_bias;
   int reverse;   // walk the tiles from the last to the first: consecutive layers alternate direction, so a layer starts with
                  // the part of its input that the previous layer wrote last and that is still in the 126 MB L2
   int k_chunks1; // dual-input 1x1 (bottleneck conv3 + projection shortcut as ONE GEMM over K = [t2 | x]): chunks [0, k_chunks1) come
@@ -253,7 +261,8 @@ template <int BLOCK_N, bool kStaged>
 __global__ void __launch_bounds__(kThreads, 1)
 conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                  const __grid_constant__ CUtensorMap map_out, const __grid_constant__ CUtensorMap map_res,
-                 const __grid_constant__ CUtensorMap map_a2, const ConvArgs a) {
+                 const __grid_constant__ CUtensorMap map_a2, const __grid_constant__ CUtensorMap map_b2,
+                 const __grid_constant__ CUtensorMap map_out2, const ConvArgs a) {
   using Cfg = TileCfg<BLOCK_N, kStaged>;
   extern __shared__ unsigned char smem_dyn[];
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~(uintptr_t)1023);
@@ -263,6 +272,8 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
   unsigned char* io_stage = a.halo ? halo_b + a.b_stages * Cfg::kBBytes
                                    : (a.stem_mode == 2 ? stem_w + kStemWBytes : smem + n_stages * Cfg::kStageBytes);
   unsigned char* coarse_stage = io_stage + (kStaged ? a.io_bufs * kIoBytes : 0);
+  unsigned char* b2_stage = coarse_stage + (a.residual_mode == 2 ? a.io_bufs * kCoarseBytes : 0);  // chained weight chunks
+  const int b2_bytes = a.chain_n * 128;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::kBudget);
   uint64_t* full_bar = bars;
   uint64_t* empty_bar = bars + 8;
@@ -274,7 +285,14 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
   uint64_t* a_empty = a_full + 4;
   uint64_t* b_full = a_empty + 4;               // halo mode: weight-tile ring
   uint64_t* b_empty = b_full + kMaxBStages;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(b_empty + kMaxBStages);
+  uint64_t* chain_full = b_empty + kMaxBStages;   // chained accumulator stage complete (MMA -> epilogue)
+  uint64_t* chain_empty = chain_full + 2;         // ... drained (epilogue -> MMA)
+  uint64_t* chain_read = chain_empty + 2;         // staging buffer no longer read by the chained MMA / its own store issued
+  uint64_t* b2_full = chain_read + kMaxIoBufs;
+  uint64_t* b2_empty = b2_full + 4;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(b2_empty + 4);
+  const bool chain = kStaged && BLOCK_N == 256 && a.chain_n > 0;
+  const int n_acc = chain ? 1 : 2;                // the chained accumulator takes TMEM columns 256.. : one main stage left
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int tiles_m = a.N * a.tiles_h * a.tiles_w;
@@ -285,6 +303,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
     tma_prefetch_desc(&map_a);
     tma_prefetch_desc(&map_b);
     if (a.k_chunks1 < a.k_chunks) tma_prefetch_desc(&map_a2);
+    if (a.chain_n) { tma_prefetch_desc(&map_b2); tma_prefetch_desc(&map_out2); }
     if (kStaged) {
       tma_prefetch_desc(&map_out);
       if (a.residual_mode) tma_prefetch_desc(&map_res);
@@ -305,6 +324,9 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
     }
     for (int s = 0; s < 4; ++s) { mbar_init(&a_full[s], 1); mbar_init(&a_empty[s], 1); }
     for (int s = 0; s < kMaxBStages; ++s) { mbar_init(&b_full[s], 1); mbar_init(&b_empty[s], 1); }
+    for (int s = 0; s < 2; ++s) { mbar_init(&chain_full[s], 1); mbar_init(&chain_empty[s], kEpilogueWarps); }
+    for (int s = 0; s < kMaxIoBufs; ++s) mbar_init(&chain_read[s], 1);
+    for (int s = 0; s < 4; ++s) { mbar_init(&b2_full[s], 1); mbar_init(&b2_empty[s], 1); }
     fence_barrier_init();
   }
   if (warp == 2) tmem_alloc<Cfg::kTmemCols>(tmem_slot);
@@ -330,16 +352,27 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
     th = (int)r - img * a.tiles_h;
   };
 
+  // Tile schedule of this CTA: static round-robin over the (m, n) tiles; chained layers keep all n tiles of an m tile on the
+  // same CTA, back to back (the chained GEMM accumulates over them), and round-robin over the m tiles instead.
+  auto tile_at = [&](int it) -> int {
+    if (!chain) { const int t = (int)blockIdx.x + it * (int)gridDim.x; return t < num_tiles ? t : -1; }
+    const int grp = it / a.tiles_n;
+    const int mt = (int)blockIdx.x + grp * (int)gridDim.x;
+    return mt < tiles_m ? mt * a.tiles_n + (it - grp * a.tiles_n) : -1;
+  };
+  constexpr int kSubMain = BLOCK_N / 64;
+  const int nsub2 = a.chain_n >> 6;                // 64-channel sub-tiles of the chained output
+
   if (warp == 0) {
     // ================================ TMA producer (warp-uniform loops, one elected lane issues) ================================
     const bool leader = elect_one();
-    int stage = 0, hstage = 0;
-    uint32_t phase = 0, hphase = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+    int stage = 0, hstage = 0, bs = 0;
+    uint32_t phase = 0, hphase = 0, bphase = 0;
+    for (int it = 0, tile; (tile = tile_at(it)) >= 0; ++it) {
       int nt, tw, th, img;
       decompose(tile, nt, tw, th, img);
       const int h0 = th * a.TH - a.pad, w0 = tw * a.TW - a.pad, n0 = nt * BLOCK_N;
-      const bool first = tile == (int)blockIdx.x;
+      const bool first = it == 0;
       if (a.halo) {  // one halo tile per K chunk, then the 9 weight tiles of that chunk
         for (int kc = 0; kc < a.k_chunks; ++kc) {
           mbar_wait(&a_empty[hstage], hphase ^ 1);
@@ -405,6 +438,16 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
             }
             if (++stage == n_stages) { stage = 0; phase ^= 1; }
           }
+      if (chain) {  // the chained weights of this n tile's four 64-channel K chunks: W2[:, n0 + 64 s .. +64]
+        for (int s2 = 0; s2 < kSubMain; ++s2) {
+          mbar_wait(&b2_empty[bs], bphase ^ 1);
+          if (leader) {
+            mbar_expect_tx(&b2_full[bs], (uint32_t)b2_bytes);
+            tma_load_2d(&map_b2, &b2_full[bs], b2_stage + bs * b2_bytes, n0 + s2 * 64, 0);
+          }
+          if (++bs == a.b2_stages) { bs = 0; bphase ^= 1; }
+        }
+      }
     }
   } else if (warp == 1) {
     // ================================ MMA issuer (warp-uniform loops, one elected lane issues) ================================
@@ -415,8 +458,14 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
     uint32_t phase = 0, hphase = 0;
     int acc = 0;
     uint32_t acc_phase = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-      const bool first = tile == (int)blockIdx.x;
+    // chained GEMM state: staging-buffer cursor (the same running sub-tile sequence the epilogue / io warp walk), weight ring,
+    // chained accumulator stage
+    const uint32_t idesc2 = umma_instr_desc(kBlockM, a.chain_n > 0 ? a.chain_n : 64, false);
+    const int n_cacc = a.chain_n <= 128 ? 2 : 1;
+    int cp = 0, bs = 0, cs = 0;
+    uint32_t cpar = 0, bphase = 0, cphase = 0;
+    for (int it = 0, tile; (tile = tile_at(it)) >= 0; ++it) {
+      const bool first = it == 0;
       mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
       tc_fence_after();
       const uint32_t d_tmem = tmem_base + acc * BLOCK_N;
@@ -438,7 +487,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
           umma_commit(&tmem_full[acc]);
         }
         if (++stage == n_stages) { stage = 0; phase ^= 1; }
-        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+        if (++acc == n_acc) { acc = 0; acc_phase ^= 1; }
         continue;
       }
       if (a.halo) {
@@ -487,11 +536,11 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
           }
           if (++hstage == a.a_stages) { hstage = 0; hphase ^= 1; }
         }
-        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+        if (++acc == n_acc) { acc = 0; acc_phase ^= 1; }
         continue;
       }
       const bool sw64 = a.stem_mode == 1;
-      for (int it = 0; it < k_iters; ++it) {
+      for (int ki = 0; ki < k_iters; ++ki) {
         mbar_wait(&full_bar[stage], phase);
         tc_fence_after();
         if (leader) {
@@ -501,36 +550,74 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
 #pragma unroll
           for (int k = 0; k < kBlockK / kUmmaK; ++k) {
             // advance 32 B (= 2 x 16 B) along K inside the swizzle atom
-            if (k < n_mma) umma_bf16(d_tmem, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (it | k) != 0);
+            if (k < n_mma) umma_bf16(d_tmem, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (ki | k) != 0);
           }
           umma_commit(&empty_bar[stage]);  // frees the smem stage once these MMAs retire
-          if (it == k_iters - 1) umma_commit(&tmem_full[acc]);
+          if (ki == k_iters - 1) umma_commit(&tmem_full[acc]);
         }
         if (++stage == n_stages) { stage = 0; phase ^= 1; }
       }
-      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      if (++acc == n_acc) { acc = 0; acc_phase ^= 1; }
+      if (chain) {
+        const int grp_pos = it % a.tiles_n;          // position of this n tile inside its m-tile group
+        const uint32_t d2 = tmem_base + 256u + (uint32_t)(cs * a.chain_n);
+        if (grp_pos == 0) {                           // chained accumulator stage drained by the epilogue two groups ago
+          mbar_wait(&chain_empty[cs], cphase ^ 1);
+          tc_fence_after();
+        }
+        for (int s2 = 0; s2 < kSubMain; ++s2) {
+          mbar_wait(&io_written[cp], cpar);           // the epilogue finished this 128 x 64 bf16 sub-tile (swizzled, K-major)
+          mbar_wait(&b2_full[bs], bphase);
+          tc_fence_after();
+          if (leader) {
+            const uint64_t da = umma_smem_desc(smem_u32(io_stage + cp * kIoBytes));
+            const uint64_t db = umma_smem_desc(smem_u32(b2_stage + bs * b2_bytes));
+#pragma unroll
+            for (int k = 0; k < kBlockK / kUmmaK; ++k)
+              umma_bf16(d2, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc2, (grp_pos | s2 | k) != 0);
+            umma_commit(&b2_empty[bs]);
+            umma_commit(&chain_read[cp]);             // the io warp may recycle the buffer once these MMAs retired
+          }
+          if (++bs == a.b2_stages) { bs = 0; bphase ^= 1; }
+          if (++cp == a.io_bufs) { cp = 0; cpar ^= 1; }
+        }
+        if (grp_pos == a.tiles_n - 1) {
+          if (leader) umma_commit(&chain_full[cs]);
+          if (++cs == n_cacc) { cs = 0; cphase ^= 1; }
+          for (int c2 = 0; c2 < nsub2; ++c2)          // skip the buffers the chained epilogue will fill
+            if (++cp == a.io_bufs) { cp = 0; cpar ^= 1; }
+        }
+      }
     }
   } else if (kStaged && warp == 3) {
     // ================================ io warp (staged epilogue) ================================
     // Owns the 16 KB staging buffers: hands them to the epilogue warps (io_ready: free, or - on residual layers -
     // filled with the TMA-loaded residual sub-tile, running up to io_bufs sub-tiles ahead) and TMA-stores them once
     // all epilogue threads have written their rows (io_written).  The epilogue warps never wait on a store.
+    // The sub-tiles of a CTA form one running sequence; chained layers append the chained output's sub-tiles after the last
+    // n tile of every m-tile group.  A buffer is recycled when its store has read it AND (chained layers) the chained MMA has.
     const bool leader = elect_one();
-    constexpr int kSub = BLOCK_N / 64;
     const int rmode = a.residual_mode;
     const int R = a.io_bufs;
     const uint32_t res_bytes = rmode == 2 ? kCoarseBytes : kIoBytes;
-    auto sub_count = [&](int n0) { const int left = (a.Cout - n0) >> 6; return left < kSub ? left : kSub; };
-    int rd_tile = blockIdx.x, rd_sub = 0, rd_p = 0;  // cursor of the next sub-tile to be made ready, its buffer
+    auto sub_count = [&](int n0) { const int left = (a.Cout - n0) >> 6; return left < kSubMain ? left : kSubMain; };
+    // ---- cursor of the next sub-tile to be made ready
+    int rd_it = 0, rd_tile = tile_at(0), rd_sub = 0, rd_chain = 0, rd_p = 0;
     int rd_n0 = 0, rd_w0 = 0, rd_h0 = 0, rd_img = 0;
     auto rd_coords = [&]() {
       int nt, tw, th;
       decompose(rd_tile, nt, tw, th, rd_img);
       rd_n0 = nt * BLOCK_N; rd_w0 = tw * a.TW; rd_h0 = th * a.TH;
     };
-    if (rd_tile < num_tiles) rd_coords();
+    if (rd_tile >= 0) rd_coords();
     auto make_ready = [&]() {
-      if (rd_tile >= num_tiles) return;
+      if (rd_tile < 0) return;
+      if (rd_chain > 0) {          // a chained-output sub-tile: no residual, the buffer only has to be free
+        if (leader) mbar_arrive(&io_ready[rd_p]);
+        if (++rd_p == R) rd_p = 0;
+        if (--rd_chain == 0) { rd_tile = tile_at(++rd_it); if (rd_tile >= 0) rd_coords(); }
+        return;
+      }
       if (leader) {
         if (rmode == 0) {
           mbar_arrive(&io_ready[rd_p]);
@@ -543,31 +630,40 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
       if (++rd_p == R) rd_p = 0;
       if (++rd_sub == sub_count(rd_n0)) {
         rd_sub = 0;
-        rd_tile += gridDim.x;
-        if (rd_tile < num_tiles) rd_coords();
+        if (chain && rd_it % a.tiles_n == a.tiles_n - 1) { rd_chain = nsub2; return; }  // the group's chained sub-tiles come next
+        rd_tile = tile_at(++rd_it);
+        if (rd_tile >= 0) rd_coords();
       }
     };
     for (int i = 0; i < R; ++i) make_ready();
-    int p = 0;
-    uint32_t par = 0;
+    int p = 0, pprev = 0;
+    uint32_t par = 0, parprev = 0;
     bool any = false;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+    auto store_one = [&](const CUtensorMap* map, int c0, int w0, int h0, int img, bool chained_out) {
+      mbar_wait(&io_written[p], par);
+      if (leader) {
+        tma_store_4d(map, io_stage + p * kIoBytes, c0, w0, h0, img);
+        tma_store_commit();
+        if (chain && chained_out) mbar_arrive(&chain_read[p]);  // nobody else reads a chained-output buffer
+        if (any) tma_store_wait_read<1>();  // the previous store has drained its buffer: recycle it for R sub-tiles ahead
+      }
+      __syncwarp();
+      if (any) {
+        if (chain) mbar_wait(&chain_read[pprev], parprev);      // ... and the chained MMA is done with it as well
+        make_ready();
+      }
+      any = true;
+      pprev = p; parprev = par;
+      if (++p == R) { p = 0; par ^= 1; }
+    };
+    for (int it = 0, tile; (tile = tile_at(it)) >= 0; ++it) {
       int nt, tw, th, img;
       decompose(tile, nt, tw, th, img);
       const int n0 = nt * BLOCK_N, w0 = tw * a.TW, h0 = th * a.TH;
       const int nsub = sub_count(n0);
-      for (int s2 = 0; s2 < nsub; ++s2) {
-        mbar_wait(&io_written[p], par);
-        if (leader) {
-          tma_store_4d(&map_out, io_stage + p * kIoBytes, n0 + s2 * 64, w0, h0, img);
-          tma_store_commit();
-          if (any) tma_store_wait_read<1>();  // the previous store has drained its buffer: recycle it for R sub-tiles ahead
-        }
-        __syncwarp();
-        if (any) make_ready();
-        any = true;
-        if (++p == R) { p = 0; par ^= 1; }
-      }
+      for (int s2 = 0; s2 < nsub; ++s2) store_one(&map_out, n0 + s2 * 64, w0, h0, img, false);
+      if (chain && it % a.tiles_n == a.tiles_n - 1)
+        for (int c2 = 0; c2 < nsub2; ++c2) store_one(&map_out2, c2 * 64, w0, h0, img, true);
     }
     if (leader) tma_store_wait_all();
   } else if (warp >= kEpilogueWarp0) {
@@ -582,82 +678,96 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
     int acc = 0;
     uint32_t acc_phase = 0;
     if constexpr (kStaged) {
-      constexpr int kSub = BLOCK_N / 64;
       const int rmode = a.residual_mode;  // 1: same-size residual tile, 2: coarser map (nearest 2x); both arrive by TMA
       const int R = a.io_bufs;
       const int crow = (ph >> 1) * (a.TW >> 1) + (pw >> 1);  // this thread's pixel in the coarse (mode 2) tile
-      const bool has_bias = a.bias != nullptr;
       int p = 0;          // staging buffer of the running sub-tile
       uint32_t par = 0;   // its barrier parity
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      // One 128 x 64 sub-tile: this warp's 32 accumulator columns (TMEM column tcol + half * 32) + bias (+ residual) -> ReLU ->
+      // bf16 -> the swizzled staging buffer.  full_bar: accumulator-complete barrier to wait for first (or null);
+      // release: barrier to arrive on once the TMEM columns have been read (or null).
+      auto sub_tile = [&](uint32_t tcol, const float* bias_ptr, int rm, int relu, uint64_t* full_bar_w, uint32_t full_par,
+                          uint64_t* release) {
+        unsigned char* io = io_stage + p * kIoBytes;
+        // this warp's 32 bias values are fetched before any wait, so their latency hides behind the barrier / TMEM loads
+        float4 bv[8];
+        if (bias_ptr) {
+          const float4* bp = reinterpret_cast<const float4*>(bias_ptr + half * 32);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) bv[j] = __ldg(bp + j);
+        }
+        if (full_bar_w) {
+          mbar_wait(full_bar_w, full_par);
+          tc_fence_after();
+        }
+        uint32_t v[32];
+        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + tcol + (uint32_t)(half * 32);
+        tmem_ld_32x32b_x16(taddr, v);
+        tmem_ld_32x32b_x16(taddr + 16, v + 16);
+        tmem_ld_wait();
+        if (release) {  // accumulator fully read: hand the TMEM stage back to the MMA warp
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(release);
+        }
+        mbar_wait(&io_ready[p], par);  // buffer free and (residual layers) its residual sub-tile landed
+        uint4* myrow = reinterpret_cast<uint4*>(io + row * 128);
+        const uint4* crs = reinterpret_cast<const uint4*>(coarse_stage + p * kCoarseBytes + crow * 128);
+        // this warp's four residual chunks of the row are read up front: inside the loop every load would have to wait
+        // for the previous chunk's store (same buffer, the compiler cannot prove the swizzled slots distinct)
+        uint4 res[4];
+        if (rm) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) res[j] = rm == 1 ? myrow[(half * 4 + j) ^ (row & 7)] : crs[(half * 4 + j) ^ (crow & 7)];
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int c = half * 4 + j;
+          float f[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) f[i] = __uint_as_float(v[j * 8 + i]);
+          if (bias_ptr) {
+            const float4 b0 = bv[2 * j], b1 = bv[2 * j + 1];
+            f[0] += b0.x; f[1] += b0.y; f[2] += b0.z; f[3] += b0.w;
+            f[4] += b1.x; f[5] += b1.y; f[6] += b1.z; f[7] += b1.w;
+          }
+          uint4* slot = myrow + (c ^ (row & 7));  // 128B swizzle: 16-byte chunk index XOR (row mod 8)
+          if (rm) {
+            const uint4 r = res[j];
+            f[0] += bf16_lo(r.x); f[1] += bf16_hi(r.x); f[2] += bf16_lo(r.y); f[3] += bf16_hi(r.y);
+            f[4] += bf16_lo(r.z); f[5] += bf16_hi(r.z); f[6] += bf16_lo(r.w); f[7] += bf16_hi(r.w);
+          }
+          if (relu) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) f[i] = fmaxf(f[i], 0.f);
+          }
+          *slot = make_uint4(pack_bf16(f[0], f[1]), pack_bf16(f[2], f[3]), pack_bf16(f[4], f[5]), pack_bf16(f[6], f[7]));
+        }
+        fence_proxy_async();            // make the generic-proxy row writes visible to the TMA store (and the chained MMA)
+        mbar_arrive(&io_written[p]);    // 256 arrivals release the buffer to the io warp
+        if (++p == R) { p = 0; par ^= 1; }
+      };
+      const int n_cacc = a.chain_n <= 128 ? 2 : 1;
+      int cs = 0;
+      uint32_t cphase = 0;
+      for (int it = 0, tile; (tile = tile_at(it)) >= 0; ++it) {
         const int ptile = a.reverse ? num_tiles - 1 - tile : tile;
         const int n0 = (ptile - (int)fast_div((uint32_t)ptile, a.mul_tiles_n) * a.tiles_n) * BLOCK_N;
         const int left = (a.Cout - n0) >> 6;
-        const int nsub = left < kSub ? left : kSub;
-        for (int s2 = 0; s2 < nsub; ++s2) {
-          unsigned char* io = io_stage + p * kIoBytes;
-          // this warp's 32 bias values are fetched before any wait, so their latency hides behind the barrier / TMEM loads
-          float4 bv[8];
-          if (has_bias) {
-            const float4* bp = reinterpret_cast<const float4*>(a.bias + n0 + s2 * 64 + half * 32);
-#pragma unroll
-            for (int j = 0; j < 8; ++j) bv[j] = __ldg(bp + j);
-          }
-          if (s2 == 0) {
-            mbar_wait(&tmem_full[acc], acc_phase);
-            tc_fence_after();
-          }
-          uint32_t v[32];
-          const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BLOCK_N + s2 * 64 + half * 32);
-          tmem_ld_32x32b_x16(taddr, v);
-          tmem_ld_32x32b_x16(taddr + 16, v + 16);
-          tmem_ld_wait();
-          if (s2 == nsub - 1) {  // accumulator fully read: hand the TMEM stage back to the MMA warp
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&tmem_empty[acc]);
-          }
-          mbar_wait(&io_ready[p], par);  // buffer free and (residual layers) its residual sub-tile landed
-          uint4* myrow = reinterpret_cast<uint4*>(io + row * 128);
-          const uint4* crs = reinterpret_cast<const uint4*>(coarse_stage + p * kCoarseBytes + crow * 128);
-          // this warp's four residual chunks of the row are read up front: inside the loop every load would have to wait
-          // for the previous chunk's store (same buffer, the compiler cannot prove the swizzled slots distinct)
-          uint4 res[4];
-          if (rmode) {
-#pragma unroll
-            for (int j = 0; j < 4; ++j) res[j] = rmode == 1 ? myrow[(half * 4 + j) ^ (row & 7)] : crs[(half * 4 + j) ^ (crow & 7)];
-          }
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const int c = half * 4 + j;
-            float f[8];
-#pragma unroll
-            for (int i = 0; i < 8; ++i) f[i] = __uint_as_float(v[j * 8 + i]);
-            if (has_bias) {
-              const float4 b0 = bv[2 * j], b1 = bv[2 * j + 1];
-              f[0] += b0.x; f[1] += b0.y; f[2] += b0.z; f[3] += b0.w;
-              f[4] += b1.x; f[5] += b1.y; f[6] += b1.z; f[7] += b1.w;
-            }
-            uint4* slot = myrow + (c ^ (row & 7));  // 128B swizzle: 16-byte chunk index XOR (row mod 8)
-            if (rmode) {
-              const uint4 r = res[j];
-              f[0] += bf16_lo(r.x); f[1] += bf16_hi(r.x); f[2] += bf16_lo(r.y); f[3] += bf16_hi(r.y);
-              f[4] += bf16_lo(r.z); f[5] += bf16_hi(r.z); f[6] += bf16_lo(r.w); f[7] += bf16_hi(r.w);
-            }
-            if (a.relu) {
-#pragma unroll
-              for (int i = 0; i < 8; ++i) f[i] = fmaxf(f[i], 0.f);
-            }
-            *slot = make_uint4(pack_bf16(f[0], f[1]), pack_bf16(f[2], f[3]), pack_bf16(f[4], f[5]), pack_bf16(f[6], f[7]));
-          }
-          fence_proxy_async();            // make the generic-proxy row writes visible to the TMA store
-          mbar_arrive(&io_written[p]);    // 256 arrivals release the buffer to the io warp
-          if (++p == R) { p = 0; par ^= 1; }
+        const int nsub = left < kSubMain ? left : kSubMain;
+        for (int s2 = 0; s2 < nsub; ++s2)
+          sub_tile((uint32_t)(acc * BLOCK_N + s2 * 64), a.bias ? a.bias + n0 + s2 * 64 : nullptr, rmode, a.relu,
+                   s2 == 0 ? &tmem_full[acc] : nullptr, acc_phase, s2 == nsub - 1 ? &tmem_empty[acc] : nullptr);
+        if (++acc == n_acc) { acc = 0; acc_phase ^= 1; }
+        if (chain && it % a.tiles_n == a.tiles_n - 1) {  // the m-tile group is complete: chained epilogue (bias2, ReLU) -> map_out2
+          for (int c2 = 0; c2 < nsub2; ++c2)
+            sub_tile(256u + (uint32_t)(cs * a.chain_n + c2 * 64), a.chain_bias ? a.chain_bias + c2 * 64 : nullptr, 0, a.chain_relu,
+                     c2 == 0 ? &chain_full[cs] : nullptr, cphase, c2 == nsub2 - 1 ? &chain_empty[cs] : nullptr);
+          if (++cs == n_cacc) { cs = 0; cphase ^= 1; }
         }
-        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       }
     } else {
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      for (int it = 0, tile; (tile = tile_at(it)) >= 0; ++it) {
         int nt, tw, th, img;
         decompose(tile, nt, tw, th, img);
         const int h = th * a.TH + ph, w = tw * a.TW + pw, n0 = nt * BLOCK_N;
@@ -720,7 +830,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&tmem_empty[acc]);
-        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+        if (++acc == n_acc) { acc = 0; acc_phase ^= 1; }
       }
     }
   }
@@ -779,7 +889,7 @@ uint32_t div_mul(int d) { return d <= 1 ? 0u : (uint32_t)(((1ull << 32) + (uint6
 
 template <int BLOCK_N, bool kStaged>
 int launch_conv(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& mo, const CUtensorMap& mr, const CUtensorMap& ma2,
-                const ConvArgs& a_in, cudaStream_t st) {
+                const ConvArgs& a_in, cudaStream_t st, const CUtensorMap* mb2 = nullptr, const CUtensorMap* mo2 = nullptr) {
   using Cfg = TileCfg<BLOCK_N, kStaged>;
   ConvArgs a = a_in;
   a.mul_tiles_n = div_mul(a.tiles_n);
@@ -792,7 +902,8 @@ int launch_conv(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap&
                                        Cfg::kSmemBytes));
     attr_once.mark();
   }
-  const int tiles = a.N * a.tiles_h * a.tiles_w * a.tiles_n;
+  // chained layers keep the n tiles of an m tile on one CTA: the grid is sized in m tiles
+  const int tiles = a.N * a.tiles_h * a.tiles_w * (a.chain_n ? 1 : a.tiles_n);
   const int grid = tiles < sm_count() ? tiles : sm_count();
   // PE_CONV_PDL=0 launches the layers fully serialised (A/B switch)
   static const int pdl = [] { const char* e = getenv("PE_CONV_PDL"); return e ? atoi(e) : 1; }();
@@ -806,14 +917,18 @@ int launch_conv(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap&
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
   cfg.numAttrs = pdl ? 1 : 0;
-  PE_CUDA_CHECK(cudaLaunchKernelEx(&cfg, conv_gemm_kernel<BLOCK_N, kStaged>, ma, mb, mo, mr, ma2, a));
+  PE_CUDA_CHECK(cudaLaunchKernelEx(&cfg, conv_gemm_kernel<BLOCK_N, kStaged>, ma, mb, mo, mr, ma2, mb2 ? *mb2 : ma, mo2 ? *mo2 : ma, a));
   return PE_OK;
 }
 
 }  // namespace
 
 int conv2d_launch(const pe_conv_desc& d, const void* x, const void* w, const float* bias, const void* residual, void* y,
-                  cudaStream_t st, const ConvSecondInput* x2, int reverse) {
+                  cudaStream_t st, const ConvSecondInput* x2, int reverse, const ConvChain* ch) {
+  if (ch && ch->w) {  // chained 1x1 on this layer's output tile (see ConvArgs::chain_n)
+    if (d.out_fp32 || d.Cout % 256 || d.residual_mode == 2 || d.KH != 1 || (ch->N != 64 && ch->N != 128 && ch->N != 256) || !ch->y)
+      return PE_ERR_UNSUPPORTED;
+  }
   if (x2 && x2->x) {  // dual-input 1x1: y = act([x | x2(strided)] . w + bias), w = [Cout][Cin + Cin2]
     if (d.KH != 1 || d.KW != 1 || d.stride != 1 || d.Cin % 64 || x2->Cin % 8 || (x2->stride != 1 && x2->stride != 2)) return PE_ERR_UNSUPPORTED;
     if ((x2->H - 1) / x2->stride + 1 != d.H || (x2->W - 1) / x2->stride + 1 != d.W) return PE_ERR_INVALID_ARGUMENT;
@@ -851,6 +966,11 @@ int conv2d_launch(const pe_conv_desc& d, const void* x, const void* w, const flo
   a.k_chunks = ceil_div(d.Cin, kBlockK);  // a ragged last chunk is zero-filled by TMA (A and W alike)
   a.k_chunks1 = a.k_chunks;
   a.reverse = reverse ? 1 : 0;
+  const bool chained = ch && ch->w;
+  a.chain_n = chained ? ch->N : 0;
+  a.chain_relu = chained ? ch->relu : 0;
+  a.chain_bias = chained ? ch->bias : nullptr;
+  a.b2_stages = 0;
   const bool dual = x2 && x2->x;
   if (dual) a.k_chunks += ceil_div(x2->Cin, kBlockK);
   a.relu = d.relu;
@@ -906,6 +1026,18 @@ int conv2d_launch(const pe_conv_desc& d, const void* x, const void* w, const flo
       if (!make_map(&mr, residual, 4, cdims, cstr, cbox)) return PE_ERR_CUDA;
     }
   }
+  CUtensorMap mb2, mo2;
+  if (chained) {
+    if (!staged || bn != 256) return PE_ERR_UNSUPPORTED;
+    cuuint64_t wd[2] = {(cuuint64_t)d.Cout, (cuuint64_t)ch->N};           // W2 [N2][Cout], K-major
+    cuuint64_t ws[1] = {(cuuint64_t)d.Cout * 2};
+    cuuint32_t wb[2] = {(cuuint32_t)kBlockK, (cuuint32_t)ch->N};
+    if (!make_map(&mb2, ch->w, 2, wd, ws, wb)) return PE_ERR_CUDA;
+    cuuint64_t od[4] = {(cuuint64_t)ch->N, (cuuint64_t)a.Wo, (cuuint64_t)a.Ho, (cuuint64_t)d.N};
+    cuuint64_t os[3] = {(cuuint64_t)ch->N * 2, (cuuint64_t)a.Wo * ch->N * 2, (cuuint64_t)a.Ho * a.Wo * ch->N * 2};
+    cuuint32_t ob[4] = {64, (cuuint32_t)a.TW, (cuuint32_t)a.TH, 1};
+    if (!make_map(&mo2, ch->y, 4, od, os, ob)) return PE_ERR_CUDA;
+  }
   {  // split the smem budget: short K loops need few operand stages and profit from a deep residual/store queue
     const int stage_bytes = kBlockM * kBlockK * 2 + bn * kBlockK * 2;
     const int max_stages = bn >= 256 ? 4 : (bn >= 128 ? 6 : 8);
@@ -926,9 +1058,16 @@ int conv2d_launch(const pe_conv_desc& d, const void* x, const void* w, const flo
         if (st_want < max_stages) st_want = (st_want + max_stages + 1) / 2;
       }
       const int io_bytes = kIoBytes + (d.residual_mode == 2 ? kCoarseBytes : 0);
-      int io = (budget - st_want * stage_bytes) / io_bytes;
+      int b2_total = 0;
+      if (chained) {  // chained weight ring: [N2 x 64] bf16 chunks; the operand pipeline gives way (these layers are HBM-bound)
+        a.b2_stages = ch->N <= 64 ? 4 : (ch->N <= 128 ? 3 : 2);
+        b2_total = a.b2_stages * ch->N * 128;
+        if (st_want > 2) st_want = 2;
+      }
+      int io = (budget - b2_total - st_want * stage_bytes) / io_bytes;
       if (io > kMaxIoBufs) io = kMaxIoBufs;
-      if (io < 2) { io = 2; st_want = (budget - 2 * io_bytes) / stage_bytes; }
+      if (io < 2) { io = 2; st_want = (budget - b2_total - 2 * io_bytes) / stage_bytes; }
+      if (chained && (io < 3 || st_want < 2)) return PE_ERR_UNSUPPORTED;
       a.stages = st_want;
       a.io_bufs = io;
       if (halo) {
@@ -954,7 +1093,7 @@ int conv2d_launch(const pe_conv_desc& d, const void* x, const void* w, const flo
   }
   if (staged) {
     switch (bn) {
-      case 256: return launch_conv<256, true>(ma, mb, mo, mr, ma2, a, st);
+      case 256: return launch_conv<256, true>(ma, mb, mo, mr, ma2, a, st, chained ? &mb2 : nullptr, chained ? &mo2 : nullptr);
       case 128: return launch_conv<128, true>(ma, mb, mo, mr, ma2, a, st);
       default: return launch_conv<64, true>(ma, mb, mo, mr, ma2, a, st);
     }
@@ -1033,6 +1172,15 @@ extern "C" PE_API int pe_conv2d_fwd(const pe_conv_desc* desc, const void* x, con
                                     const void* residual, void* y, void* stream) {
   if (!desc) return PE_ERR_INVALID_ARGUMENT;
   return pe::conv2d_launch(*desc, x, w, bias, residual, y, reinterpret_cast<cudaStream_t>(stream));
+}
+
+extern "C" PE_API int pe_conv1x1_chain_fwd(const pe_conv_desc* desc, const void* x, const void* x2, int cin2, int h2, int w2s, int stride2,
+                                           const void* w, const float* bias, const void* residual, void* y, const void* wc,
+                                           const float* bias_c, int n_c, int relu_c, void* y_c, void* stream) {
+  if (!desc || !wc || !y_c) return PE_ERR_INVALID_ARGUMENT;
+  pe::ConvSecondInput s2 = {x2, cin2, h2, w2s, stride2};
+  pe::ConvChain ch = {wc, bias_c, y_c, n_c, relu_c};
+  return pe::conv2d_launch(*desc, x, w, bias, residual, y, reinterpret_cast<cudaStream_t>(stream), x2 ? &s2 : nullptr, 0, &ch);
 }
 
 extern "C" PE_API int pe_conv1x1_dual_fwd(const pe_conv_desc* desc, const void* x, const void* x2, int cin2, int h2, int w2, int stride2,

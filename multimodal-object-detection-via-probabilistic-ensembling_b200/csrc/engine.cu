@@ -193,7 +193,7 @@ struct Runner {
   void* buf(const char* name) const { return ws + d->find_buf(name)->off; }
 
   int gemm(const pe_conv_desc& cd, const void* x, const void* w, const float* bias, const void* res, void* y,
-           const ConvSecondInput* x2 = nullptr) {
+           const ConvSecondInput* x2 = nullptr, const ConvChain* chain = nullptr) {
     cudaEvent_t e0 = nullptr, e1 = nullptr;
     if (d->profiling) {
       while ((int)d->ev.size() < d->ev_used + 2) {
@@ -211,14 +211,19 @@ struct Runner {
       if (x2) bytes += opix * x2->Cin * 2;  // the block input at the positions the (strided) shortcut reads
       if (cd.residual_mode == 1) bytes += opix * cd.Cout * 2;
       if (cd.residual_mode == 2) bytes += opix * cd.Cout * 2 / 4.0;
-      d->prof_flops.push_back(2.0 * opix * cd.Cout * taps);
+      double flops = 2.0 * opix * cd.Cout * taps;
+      if (chain) {  // + the chained 1x1 (the next block's conv1): its weights and its output; its input never leaves the SM
+        flops += 2.0 * opix * cd.Cout * chain->N;
+        bytes += (double)chain->N * cd.Cout * 2 + chain->N * 4.0 + opix * chain->N * 2;
+      }
+      d->prof_flops.push_back(flops);
       d->prof_bytes.push_back(bytes);
       cudaEventRecord(e0, st);
     }
     // consecutive layers walk their tiles in opposite directions (conv_gemm.cu ConvArgs::reverse); PE_CONV_REVERSE=0 disables
     static const int alternate = [] { const char* e = getenv("PE_CONV_REVERSE"); return e ? atoi(e) : 1; }();
     rev ^= alternate;
-    const int s = conv2d_launch(cd, x, w, bias, res, y, st, x2, rev);
+    const int s = conv2d_launch(cd, x, w, bias, res, y, st, x2, rev, chain);
     if (d->profiling) cudaEventRecord(e1, st);
     d->last_launches++;
     d->last_gemm_launches++;
@@ -295,6 +300,7 @@ struct Runner {
     const int* blocks = c.depth == 101 ? kStageBlocks101 : kStageBlocks50;
     const void* x = buf("pool_out");
     int H = d->H[1], W = d->W[1];
+    bool chained_c1 = false;
     for (int s = 0; s < 4; ++s) {
       for (int b = 0; b < blocks[s]; ++b) {
         char q[96];
@@ -302,12 +308,26 @@ struct Runner {
         const std::string base(q);
         const int stride = (b == 0 && s > 0) ? 2 : 1;
         const int Hin = H, Win = W;
-        conv(base + ".conv1", x, H, W, stride, true, 0, nullptr, buf("t1"));
+        // conv1 of every block but the first was already computed by the previous block's conv3 kernel (chained 1x1)
+        if (!chained_c1) conv(base + ".conv1", x, H, W, stride, true, 0, nullptr, buf("t1"));
         if (stride == 2) { H = (H - 1) / 2 + 1; W = (W - 1) / 2 + 1; }
         conv(base + ".conv2", buf("t1"), H, W, 1, true, 0, nullptr, buf("t2"));
         char rq[16];
         snprintf(rq, sizeof(rq), "res%d", s + 2);
         void* y = (b == blocks[s] - 1) ? buf(rq) : (x == buf("x0") ? buf("x1") : buf("x0"));
+        // chain the NEXT block's conv1 (cout -> mid, ReLU) onto this conv3: its A operand is this kernel's own output tile
+        static const int chain_mask = [] { const char* e = getenv("PE_CONV_CHAIN"); return e ? atoi(e) : 3; }();  // bit s: stage res(2+s); measured:
+        // res2 / res3 gain (conv1's 419 / 210 MB re-read disappears), res4 loses (its single main accumulator serialises the longer K loop)
+        ConvChain ch = {nullptr, nullptr, nullptr, 0, 0};
+        chained_c1 = false;
+        if (b + 1 < blocks[s] && ((chain_mask >> s) & 1) && (64 << s) <= 256 && status == PE_OK) {
+          char nq[96];
+          snprintf(nq, sizeof(nq), "backbone.bottom_up.res%d.%d.conv1", s + 2, b + 1);
+          const Param& p1 = d->params[d->find_param(nq)];
+          ch.w = wts + p1.w_off; ch.bias = reinterpret_cast<const float*>(wts + p1.b_off); ch.y = buf("t1"); ch.N = p1.Cout; ch.relu = 1;
+          chained_c1 = true;
+        }
+        const ConvChain* chp = chained_c1 ? &ch : nullptr;
         if (b == 0) {  // conv3 + projection shortcut as one GEMM over K = [t2 | block input] (the shortcut tensor never exists)
           if (status == PE_OK) {
             const Param& p = d->params[d->find_param(base + ".conv3")];
@@ -316,10 +336,14 @@ struct Runner {
             cd.N = B; cd.H = H; cd.W = W; cd.Cin = mid; cd.Cout = p.Cout; cd.KH = 1; cd.KW = 1; cd.stride = 1;
             cd.relu = 1; cd.residual_mode = 0; cd.out_fp32 = 0; cd.in_fp16 = 0;
             ConvSecondInput x2 = {x, p.Cin - mid, Hin, Win, stride};
-            status = gemm(cd, buf("t2"), wts + p.w_off, reinterpret_cast<const float*>(wts + p.b_off), nullptr, y, &x2);
+            status = gemm(cd, buf("t2"), wts + p.w_off, reinterpret_cast<const float*>(wts + p.b_off), nullptr, y, &x2, chp);
           }
-        } else {
-          conv(base + ".conv3", buf("t2"), H, W, 1, true, 1, x, y);
+        } else if (status == PE_OK) {
+          const Param& p = d->params[d->find_param(base + ".conv3")];
+          pe_conv_desc cd;
+          cd.N = B; cd.H = H; cd.W = W; cd.Cin = p.Cin; cd.Cout = p.Cout; cd.KH = 1; cd.KW = 1; cd.stride = 1;
+          cd.relu = 1; cd.residual_mode = 1; cd.out_fp32 = 0; cd.in_fp16 = 0;
+          status = gemm(cd, buf("t2"), wts + p.w_off, reinterpret_cast<const float*>(wts + p.b_off), x, y, nullptr, chp);
         }
         x = y;
       }

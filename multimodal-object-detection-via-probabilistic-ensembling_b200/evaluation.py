@@ -127,14 +127,85 @@ class COCOBBoxEval:
         dt_ig = dt_ig | ((dtm < 0) & np.repeat(d_area, T, 0))
         return {"dtm": dtm, "dt_scores": np.array([d["score"] for d in dt]), "g_ign": g_ign, "dt_ig": dt_ig}
 
-    def evaluate(self):
+    def _match_host(self):
+        """evaluateImg for every (category, area range, image) on the host (numpy): {(ki, ai): [per-image results]}."""
+        out = {}
+        md = self.MAX_DETS[-1]
+        for ki, cat in enumerate(self.cat_ids):
+            for ai, rng in enumerate(self.AREA_RNG):
+                out[(ki, ai)] = [e for e in (self._evaluate_img(i, cat, rng, md) for i in self.img_ids) if e is not None]
+        return out
+
+    def _match_gpu(self, device):
+        """The same matching on the GPU (``pe_coco_match``, csrc/coco_eval.cu): one block per (image, category) group, one thread
+        per (IoU threshold, area range); float64 IoUs in the host evaluator's operation order, so every decision is identical."""
+        import ctypes
+
+        import torch
+
+        from . import _lib
+        lib = _lib.load()
+        md = self.MAX_DETS[-1]
+        groups, gt_rows, dt_rows, gt_off, dt_off = [], [], [], [0], [0]
+        for ki, cat in enumerate(self.cat_ids):
+            for img in self.img_ids:
+                gt = self.gts.get((img, cat), [])
+                dt = self.dts.get((img, cat), [])
+                if not gt and not dt:
+                    continue
+                order = np.argsort([-d["score"] for d in dt], kind="mergesort")[:md]
+                dt = [dt[i] for i in order]
+                groups.append((ki, len(gt), [d["score"] for d in dt]))
+                gt_rows += [(g["bbox"][0], g["bbox"][1], g["bbox"][2], g["bbox"][3], g["area"], int(g.get("iscrowd", 0)), g["ignore"]) for g in gt]
+                dt_rows += [(d["bbox"][0], d["bbox"][1], d["bbox"][2], d["bbox"][3], d["area"]) for d in dt]
+                gt_off.append(len(gt_rows))
+                dt_off.append(len(dt_rows))
+        T, A, P = len(self.IOU_THRS), len(self.AREA_RNG), len(groups)
+        G, D = len(gt_rows), len(dt_rows)
+        gt_np = np.asarray(gt_rows, np.float64).reshape(-1, 7)
+        dt_np = np.asarray(dt_rows, np.float64).reshape(-1, 5)
+        if np.any(gt_np[:, 5] != gt_np[:, 6]):
+            raise RuntimeError("probenb200.COCOBBoxEval: 'ignore' differs from 'iscrowd' (the GPU path assumes cocoeval.py:246)")
+        max_g = max([g[1] for g in groups] + [0])
+        if max_g > lib.pe_coco_match_max_gt():
+            raise RuntimeError("probenb200.COCOBBoxEval: %d ground-truth boxes in one (image, category) exceed the supported %d"
+                               % (max_g, lib.pe_coco_match_max_gt()))
+        dev = torch.device(device)
+
+        def up(a, dtype):
+            return torch.from_numpy(np.ascontiguousarray(a)).to(dev, dtype)
+        t_gt_box, t_gt_area = up(gt_np[:, :4], torch.float64), up(gt_np[:, 4], torch.float64)
+        t_gt_crowd = up(gt_np[:, 5].astype(np.uint8), torch.uint8)
+        t_dt_box, t_dt_area = up(dt_np[:, :4], torch.float64), up(dt_np[:, 4], torch.float64)
+        t_gt_off, t_dt_off = up(np.asarray(gt_off, np.int32), torch.int32), up(np.asarray(dt_off, np.int32), torch.int32)
+        t_thr = up(self.IOU_THRS, torch.float64)
+        t_rng = up(np.asarray(self.AREA_RNG, np.float64).reshape(-1), torch.float64)
+        matched = torch.zeros((A, T, max(D, 1)), dtype=torch.uint8, device=dev)
+        dt_ig = torch.zeros((A, T, max(D, 1)), dtype=torch.uint8, device=dev)
+        gt_ig = torch.zeros((A, max(G, 1)), dtype=torch.uint8, device=dev)
+        with torch.cuda.device(dev):
+            st = lib.pe_coco_match(_lib.ptr(t_gt_box), _lib.ptr(t_gt_area), _lib.ptr(t_gt_crowd), _lib.ptr(t_gt_off), _lib.ptr(t_dt_box),
+                                   _lib.ptr(t_dt_area), _lib.ptr(t_dt_off), P, _lib.ptr(t_thr), T, _lib.ptr(t_rng), A, max(D, 1), max(G, 1),
+                                   max_g, _lib.ptr(matched), _lib.ptr(dt_ig), _lib.ptr(gt_ig), _lib.current_stream_ptr(dev))
+        _lib.check(st, "pe_coco_match")
+        matched, dt_ig, gt_ig = matched.cpu().numpy(), dt_ig.cpu().numpy().astype(bool), gt_ig.cpu().numpy().astype(bool)
+        out = {(ki, ai): [] for ki in range(len(self.cat_ids)) for ai in range(A)}
+        for p, (ki, n_gt, scores) in enumerate(groups):
+            d0, d1, g0 = dt_off[p], dt_off[p + 1], gt_off[p]
+            for ai in range(A):
+                out[(ki, ai)].append({"dtm": np.where(matched[ai, :, d0:d1] > 0, 1, -1), "dt_scores": np.asarray(scores, np.float64),
+                                      "g_ign": gt_ig[ai, g0:g0 + n_gt], "dt_ig": dt_ig[ai, :, d0:d1]})
+        return out
+
+    def evaluate(self, device=None):
+        """``device``: None = match on the host (numpy); a CUDA device = match on the GPU (identical decisions)."""
         T, R, K, A, M = len(self.IOU_THRS), len(self.REC_THRS), len(self.cat_ids), len(self.AREA_RNG), len(self.MAX_DETS)
         precision = -np.ones((T, R, K, A, M))
         recall = -np.ones((T, K, A, M))
-        max_det_all = self.MAX_DETS[-1]
+        matches = self._match_host() if device is None else self._match_gpu(device)
         for ki, cat in enumerate(self.cat_ids):
             for ai, rng in enumerate(self.AREA_RNG):
-                evs = [e for e in (self._evaluate_img(i, cat, rng, max_det_all) for i in self.img_ids) if e is not None]
+                evs = matches[(ki, ai)]
                 if not evs:
                     continue
                 for mi, md in enumerate(self.MAX_DETS):

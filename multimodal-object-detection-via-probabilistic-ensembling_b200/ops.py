@@ -48,6 +48,24 @@ def conv1x1_dual_nhwc(x, x2, w, bias=None, stride2=1, relu=False):
     return y
 
 
+def conv1x1_chain_nhwc(x, w, bias, wc, bias_c, residual=None, x2=None, stride2=1, relu=True, relu_c=True):
+    """``pe_conv1x1_chain_fwd``: y = act([x | x2] . w + bias (+ residual)); y_c = act_c(y . wc + bias_c) computed from y's
+    shared-memory tiles in the same kernel.  Returns (y, y_c)."""
+    lib = _lib.load()
+    _lib.require_cuda(x, w, bias, wc, bias_c, residual, x2)
+    N, H, W, Cin = x.shape
+    Cout, Nc = w.shape[0], wc.shape[0]
+    y = torch.empty((N, H, W, Cout), dtype=torch.bfloat16, device=x.device)
+    yc = torch.empty((N, H, W, Nc), dtype=torch.bfloat16, device=x.device)
+    d = _lib.ConvDesc(N, H, W, Cin, Cout, 1, 1, 1, int(relu), 1 if residual is not None else 0, 0, 0)
+    c2, h2, w2 = (x2.shape[3], x2.shape[1], x2.shape[2]) if x2 is not None else (0, 0, 0)
+    st = lib.pe_conv1x1_chain_fwd(ctypes.byref(d), _lib.ptr(x), _lib.ptr(x2), c2, h2, w2, int(stride2), _lib.ptr(w), _lib.ptr(bias),
+                                  _lib.ptr(residual), _lib.ptr(y), _lib.ptr(wc), _lib.ptr(bias_c), Nc, int(relu_c), _lib.ptr(yc),
+                                  _lib.current_stream_ptr(x.device))
+    _lib.check(st, "pe_conv1x1_chain_fwd")
+    return y, yc
+
+
 def linear(x, w, bias=None, relu=False, out_fp32=False):
     """x [M,K] bf16, w [N,K] bf16 -> [M,N]; the H=1 case of the conv kernel."""
     M, K = x.shape

@@ -100,3 +100,41 @@ def test_dual_input_1x1_equals_conv3_plus_projection_shortcut(case):
     assert y.shape == want.shape
     err = (y.float() - want).abs()
     assert bool((err <= 1e-3 + want.abs() * 2 ** -8).all()), "max err %g" % float(err.max())
+
+
+@pytest.mark.parametrize("case", [
+    # N, H, W, Cin, Cout, N_chain, residual, Cin2 (dual input), H2, W2, stride2
+    (2, 40, 48, 64, 256, 64, True, 0, 0, 0, 1),       # res2.x conv3 (+residual) -> next conv1 256->64; one n tile
+    (16, 50, 64, 64, 256, 64, True, 0, 0, 0, 1),      # many tiles per CTA: staging ring wraps, both chained accumulator stages
+    (2, 25, 32, 128, 512, 128, True, 0, 0, 0, 1),     # res3: two n tiles per m tile, chained K accumulates over them
+    (3, 13, 16, 256, 1024, 256, True, 0, 0, 0, 1),    # res4: four n tiles, single chained accumulator stage
+    (2, 25, 32, 128, 512, 128, False, 256, 50, 64, 2),  # first block of a stage: [conv3 | stride-2 shortcut] dual input + chain
+])
+def test_chained_1x1_equals_conv3_then_next_conv1(case):
+    """conv3 (+residual / + projection shortcut) followed by the NEXT bottleneck's conv1 in one kernel (the second GEMM reads the
+    first one's bf16 output tiles from shared memory): both outputs against the fp32 reference of the two ops, the second one
+    evaluated on the bf16-rounded first output exactly as the separate launches would."""
+    N, H, W, Cin, Cout, Nc, use_res, Cin2, H2, W2, s2 = case
+    g = torch.Generator(device="cuda").manual_seed(sum(case))
+    x = torch.randn(N, H, W, Cin, device="cuda", generator=g).bfloat16()
+    w = (torch.randn(Cout, 1, 1, Cin, device="cuda", generator=g) / Cin ** 0.5).bfloat16()
+    b = torch.randn(Cout, device="cuda", generator=g)
+    wc = (torch.randn(Nc, 1, 1, Cout, device="cuda", generator=g) / Cout ** 0.5).bfloat16()
+    bc = torch.randn(Nc, device="cuda", generator=g)
+    res = torch.randn(N, H, W, Cout, device="cuda", generator=g).bfloat16() if use_res else None
+    x2 = wsc = None
+    want = ref_conv(x, w, b, res, 1, False, 1 if use_res else 0)
+    wfull = w.view(Cout, Cin)
+    if Cin2:
+        x2 = torch.randn(N, H2, W2, Cin2, device="cuda", generator=g).bfloat16()
+        wsc = (torch.randn(Cout, 1, 1, Cin2, device="cuda", generator=g) / Cin2 ** 0.5).bfloat16()
+        want = want + ref_conv(x2, wsc, None, None, s2, False, 0)
+        wfull = torch.cat([wfull, wsc.view(Cout, Cin2)], 1).contiguous()
+    want = F.relu(want)
+    y, yc = ops.conv1x1_chain_nhwc(x, wfull.contiguous(), b, wc.view(Nc, Cout).contiguous(), bc, residual=res, x2=x2, stride2=s2)
+    torch.cuda.synchronize()
+    err = (y.float() - want).abs()
+    assert bool((err <= 1e-3 + want.abs() * 2 ** -8).all()), "main output: max err %g" % float(err.max())
+    want_c = ref_conv(y, wc, bc, None, 1, True, 0)   # the chained conv sees the bf16 output, like a separate launch would
+    err_c = (yc.float() - want_c).abs()
+    assert bool((err_c <= 2e-3 + want_c.abs() * 2 ** -8).all()), "chained output: max err %g" % float(err_c.max())
