@@ -84,21 +84,38 @@ __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
+// Suspend-time hint (ns) of mbarrier.try_wait: a waiting thread is parked by the hardware until the phase completes or the hint
+// expires instead of re-issuing the poll every few cycles (the polls of 4 role warps + 8 epilogue warps cost issue slots and,
+// on a power-capped part, clock).  0 = plain try_wait.  Set once per device from PE_CONV_WAIT_HINT (default below).
+__constant__ uint32_t g_wait_hint_ns;
+
 __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
   uint32_t ok;
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-      "selp.u32 %0, 1, 0, p;\n\t}"
-      : "=r"(ok)
-      : "r"(smem_u32(bar)), "r"(parity)
-      : "memory");
+  const uint32_t hint = g_wait_hint_ns;
+  if (hint) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity), "r"(hint)
+        : "memory");
+  } else {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+  }
   return ok != 0;
 }
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   uint32_t polls = 0;
+  const uint32_t limit = g_wait_hint_ns ? (1u << 23) : kWatchdogPolls;  // hinted polls last up to the hint: same wall-clock bound
   while (!mbar_try_wait(bar, parity)) {
-    if (++polls > kWatchdogPolls) __trap();  // a lost arrive would otherwise hang the GPU box
+    if (++polls > limit) __trap();  // a lost arrive would otherwise hang the GPU box
   }
 }
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
@@ -238,7 +255,8 @@ struct TileCfg {
   static constexpr int kBBytes = BLOCK_N * kBlockK * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
   static constexpr int kMaxStages = BLOCK_N >= 256 ? 4 : (BLOCK_N >= 128 ? 6 : 8);
-  static constexpr int kTmemCols = 2 * BLOCK_N < 32 ? 32 : 2 * BLOCK_N;
+  // 128-wide staged tiles may run chained (two main stages in columns 0..255, the chained accumulator in 256..511)
+  static constexpr int kTmemCols = (kStaged && BLOCK_N == 128) ? 512 : (2 * BLOCK_N < 32 ? 32 : 2 * BLOCK_N);
   // dynamic smem budget shared by the operand pipeline and (staged epilogue) the io buffers
   static constexpr int kBudget = kMaxStages * kStageBytes + (kStaged ? 2 * kIoBytes : 0);
   static constexpr int kSmemBytes = kBudget + 1024 /*alignment slack*/ + 1024 /*barriers*/;
@@ -291,8 +309,13 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
   uint64_t* b2_full = chain_read + kMaxIoBufs;
   uint64_t* b2_empty = b2_full + 4;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(b2_empty + 4);
-  const bool chain = kStaged && BLOCK_N == 256 && a.chain_n > 0;
-  const int n_acc = chain ? 1 : 2;                // the chained accumulator takes TMEM columns 256.. : one main stage left
+  const bool chain = kStaged && (BLOCK_N == 256 || BLOCK_N == 128) && a.chain_n > 0;
+  // 256-wide chained tiles: the chained accumulator takes TMEM columns 256.., ONE main stage is left and the chained GEMM /
+  // epilogue of a tile follow it immediately.  128-wide chained tiles keep TWO main stages; the chained GEMM of tile i is then
+  // issued AFTER the mainloop of tile i + 1 (so the mainloop overlaps tile i's epilogue as usual) and the chained epilogue of
+  // an m-tile group after the first epilogue of the following tile ("deferred" order, same for every role).
+  const bool defer = chain && BLOCK_N == 128;
+  const int n_acc = (chain && !defer) ? 1 : 2;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int tiles_m = a.N * a.tiles_h * a.tiles_w;
@@ -362,11 +385,14 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
   };
   constexpr int kSubMain = BLOCK_N / 64;
   const int nsub2 = a.chain_n >> 6;                // 64-channel sub-tiles of the chained output
+  auto group_end = [&](int it) { return it % a.tiles_n == a.tiles_n - 1; };
+  // do the chained-output sub-tiles of a group follow the main sub-tiles of tile `it` in the CTA's staging-buffer sequence?
+  auto chain_after = [&](int it) { return chain && (defer ? (it >= 1 && group_end(it - 1)) : group_end(it)); };
 
   if (warp == 0) {
     // ================================ TMA producer (warp-uniform loops, one elected lane issues) ================================
     const bool leader = elect_one();
-    int stage = 0, hstage = 0, bs = 0;
+    int stage = 0, hstage = 0, bs = 0, prev_n0 = 0;
     uint32_t phase = 0, hphase = 0, bphase = 0;
     for (int it = 0, tile; (tile = tile_at(it)) >= 0; ++it) {
       int nt, tw, th, img;
@@ -438,15 +464,23 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
             }
             if (++stage == n_stages) { stage = 0; phase ^= 1; }
           }
-      if (chain) {  // the chained weights of this n tile's four 64-channel K chunks: W2[:, n0 + 64 s .. +64]
+      // the chained weights of an n tile's 64-channel K chunks: W2[:, n0 + 64 s .. +64].  Deferred order: tile it - 1's chunks
+      // are requested after tile it's operands (that is when the MMA warp will consume them)
+      auto load_b2 = [&](int n0c) {
         for (int s2 = 0; s2 < kSubMain; ++s2) {
           mbar_wait(&b2_empty[bs], bphase ^ 1);
           if (leader) {
             mbar_expect_tx(&b2_full[bs], (uint32_t)b2_bytes);
-            tma_load_2d(&map_b2, &b2_full[bs], b2_stage + bs * b2_bytes, n0 + s2 * 64, 0);
+            tma_load_2d(&map_b2, &b2_full[bs], b2_stage + bs * b2_bytes, n0c + s2 * 64, 0);
           }
           if (++bs == a.b2_stages) { bs = 0; bphase ^= 1; }
         }
+      };
+      if (chain && !defer) load_b2(n0);
+      if (defer) {
+        if (it >= 1) load_b2(prev_n0);
+        prev_n0 = n0;
+        if (tile_at(it + 1) < 0) load_b2(n0);  // last tile of this CTA: its chunks follow at once
       }
     }
   } else if (warp == 1) {
@@ -462,8 +496,8 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
     // chained accumulator stage
     const uint32_t idesc2 = umma_instr_desc(kBlockM, a.chain_n > 0 ? a.chain_n : 64, false);
     const int n_cacc = a.chain_n <= 128 ? 2 : 1;
-    int cp = 0, bs = 0, cs = 0;
-    uint32_t cpar = 0, bphase = 0, cphase = 0;
+    int cp = 0, bs = 0, cs = 0, prev_p = 0;
+    uint32_t cpar = 0, bphase = 0, cphase = 0, prev_par = 0;
     for (int it = 0, tile; (tile = tile_at(it)) >= 0; ++it) {
       const bool first = it == 0;
       mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
@@ -558,34 +592,48 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
         if (++stage == n_stages) { stage = 0; phase ^= 1; }
       }
       if (++acc == n_acc) { acc = 0; acc_phase ^= 1; }
-      if (chain) {
-        const int grp_pos = it % a.tiles_n;          // position of this n tile inside its m-tile group
+      // ---- chained GEMM: acc2 += staged out sub-tiles (A, in place) x W2 chunks; t = the tile whose sub-tiles are consumed,
+      //      (p0, par0) = staging-buffer cursor at its first sub-tile
+      auto chain_part = [&](int t, int p0, uint32_t par0) {
+        const int grp_pos = t % a.tiles_n;            // position of the n tile inside its m-tile group
         const uint32_t d2 = tmem_base + 256u + (uint32_t)(cs * a.chain_n);
-        if (grp_pos == 0) {                           // chained accumulator stage drained by the epilogue two groups ago
+        if (grp_pos == 0) {                           // chained accumulator stage drained by the chained epilogue
           mbar_wait(&chain_empty[cs], cphase ^ 1);
           tc_fence_after();
         }
         for (int s2 = 0; s2 < kSubMain; ++s2) {
-          mbar_wait(&io_written[cp], cpar);           // the epilogue finished this 128 x 64 bf16 sub-tile (swizzled, K-major)
+          mbar_wait(&io_written[p0], par0);           // the epilogue finished this 128 x 64 bf16 sub-tile (swizzled, K-major)
           mbar_wait(&b2_full[bs], bphase);
           tc_fence_after();
           if (leader) {
-            const uint64_t da = umma_smem_desc(smem_u32(io_stage + cp * kIoBytes));
+            const uint64_t da = umma_smem_desc(smem_u32(io_stage + p0 * kIoBytes));
             const uint64_t db = umma_smem_desc(smem_u32(b2_stage + bs * b2_bytes));
 #pragma unroll
             for (int k = 0; k < kBlockK / kUmmaK; ++k)
               umma_bf16(d2, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc2, (grp_pos | s2 | k) != 0);
             umma_commit(&b2_empty[bs]);
-            umma_commit(&chain_read[cp]);             // the io warp may recycle the buffer once these MMAs retired
+            umma_commit(&chain_read[p0]);             // the io warp may recycle the buffer once these MMAs retired
           }
           if (++bs == a.b2_stages) { bs = 0; bphase ^= 1; }
-          if (++cp == a.io_bufs) { cp = 0; cpar ^= 1; }
+          if (++p0 == a.io_bufs) { p0 = 0; par0 ^= 1; }
         }
         if (grp_pos == a.tiles_n - 1) {
           if (leader) umma_commit(&chain_full[cs]);
           if (++cs == n_cacc) { cs = 0; cphase ^= 1; }
-          for (int c2 = 0; c2 < nsub2; ++c2)          // skip the buffers the chained epilogue will fill
-            if (++cp == a.io_bufs) { cp = 0; cpar ^= 1; }
+        }
+      };
+      auto advance = [&](int n) { for (int i = 0; i < n; ++i) if (++cp == a.io_bufs) { cp = 0; cpar ^= 1; } };
+      if (chain) {
+        const int p_main = cp;                        // cursor at this tile's first main sub-tile
+        const uint32_t par_main = cpar;
+        advance(kSubMain);
+        if (chain_after(it)) advance(nsub2);          // the buffers the chained epilogue fills
+        if (!defer) {
+          chain_part(it, p_main, par_main);
+        } else {
+          if (it >= 1) chain_part(it - 1, prev_p, prev_par);
+          prev_p = p_main; prev_par = par_main;
+          if (tile_at(it + 1) < 0) chain_part(it, p_main, par_main);  // last tile of this CTA
         }
       }
     }
@@ -603,6 +651,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
     auto sub_count = [&](int n0) { const int left = (a.Cout - n0) >> 6; return left < kSubMain ? left : kSubMain; };
     // ---- cursor of the next sub-tile to be made ready
     int rd_it = 0, rd_tile = tile_at(0), rd_sub = 0, rd_chain = 0, rd_p = 0;
+    bool rd_tail = false;  // deferred order: the last group's chained sub-tiles follow the last tile
     int rd_n0 = 0, rd_w0 = 0, rd_h0 = 0, rd_img = 0;
     auto rd_coords = [&]() {
       int nt, tw, th;
@@ -611,11 +660,19 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
     };
     if (rd_tile >= 0) rd_coords();
     auto make_ready = [&]() {
-      if (rd_tile < 0) return;
       if (rd_chain > 0) {          // a chained-output sub-tile: no residual, the buffer only has to be free
         if (leader) mbar_arrive(&io_ready[rd_p]);
         if (++rd_p == R) rd_p = 0;
-        if (--rd_chain == 0) { rd_tile = tile_at(++rd_it); if (rd_tile >= 0) rd_coords(); }
+        --rd_chain;
+        return;
+      }
+      if (rd_tile < 0) {
+        if (defer && !rd_tail && rd_it > 0) {  // past the last tile: the last group's chained sub-tiles
+          rd_tail = true;
+          rd_chain = nsub2 - 1;
+          if (leader) mbar_arrive(&io_ready[rd_p]);
+          if (++rd_p == R) rd_p = 0;
+        }
         return;
       }
       if (leader) {
@@ -630,7 +687,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
       if (++rd_p == R) rd_p = 0;
       if (++rd_sub == sub_count(rd_n0)) {
         rd_sub = 0;
-        if (chain && rd_it % a.tiles_n == a.tiles_n - 1) { rd_chain = nsub2; return; }  // the group's chained sub-tiles come next
+        if (chain_after(rd_it)) rd_chain = nsub2;  // a group's chained sub-tiles come next in the sequence
         rd_tile = tile_at(++rd_it);
         if (rd_tile >= 0) rd_coords();
       }
@@ -656,15 +713,21 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
       pprev = p; parprev = par;
       if (++p == R) { p = 0; par ^= 1; }
     };
+    int pw0 = 0, ph0 = 0, pimg = 0, n_its = 0;  // patch of the previous tile (deferred order: its group's chained output)
     for (int it = 0, tile; (tile = tile_at(it)) >= 0; ++it) {
       int nt, tw, th, img;
       decompose(tile, nt, tw, th, img);
       const int n0 = nt * BLOCK_N, w0 = tw * a.TW, h0 = th * a.TH;
       const int nsub = sub_count(n0);
       for (int s2 = 0; s2 < nsub; ++s2) store_one(&map_out, n0 + s2 * 64, w0, h0, img, false);
-      if (chain && it % a.tiles_n == a.tiles_n - 1)
-        for (int c2 = 0; c2 < nsub2; ++c2) store_one(&map_out2, c2 * 64, w0, h0, img, true);
+      if (chain_after(it))
+        for (int c2 = 0; c2 < nsub2; ++c2)
+          store_one(&map_out2, c2 * 64, defer ? pw0 : w0, defer ? ph0 : h0, defer ? pimg : img, true);
+      pw0 = w0; ph0 = h0; pimg = img;
+      n_its = it + 1;
     }
+    if (defer && n_its > 0)
+      for (int c2 = 0; c2 < nsub2; ++c2) store_one(&map_out2, c2 * 64, pw0, ph0, pimg, true);
     if (leader) tma_store_wait_all();
   } else if (warp >= kEpilogueWarp0) {
     // ================================ epilogue ================================
@@ -748,8 +811,14 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
         if (++p == R) { p = 0; par ^= 1; }
       };
       const int n_cacc = a.chain_n <= 128 ? 2 : 1;
-      int cs = 0;
+      int cs = 0, n_its = 0;
       uint32_t cphase = 0;
+      auto chained_epilogue = [&]() {  // chained accumulator + bias2 -> ReLU -> bf16 -> staging -> map_out2
+        for (int c2 = 0; c2 < nsub2; ++c2)
+          sub_tile(256u + (uint32_t)(cs * a.chain_n + c2 * 64), a.chain_bias ? a.chain_bias + c2 * 64 : nullptr, 0, a.chain_relu,
+                   c2 == 0 ? &chain_full[cs] : nullptr, cphase, c2 == nsub2 - 1 ? &chain_empty[cs] : nullptr);
+        if (++cs == n_cacc) { cs = 0; cphase ^= 1; }
+      };
       for (int it = 0, tile; (tile = tile_at(it)) >= 0; ++it) {
         const int ptile = a.reverse ? num_tiles - 1 - tile : tile;
         const int n0 = (ptile - (int)fast_div((uint32_t)ptile, a.mul_tiles_n) * a.tiles_n) * BLOCK_N;
@@ -759,13 +828,10 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
           sub_tile((uint32_t)(acc * BLOCK_N + s2 * 64), a.bias ? a.bias + n0 + s2 * 64 : nullptr, rmode, a.relu,
                    s2 == 0 ? &tmem_full[acc] : nullptr, acc_phase, s2 == nsub - 1 ? &tmem_empty[acc] : nullptr);
         if (++acc == n_acc) { acc = 0; acc_phase ^= 1; }
-        if (chain && it % a.tiles_n == a.tiles_n - 1) {  // the m-tile group is complete: chained epilogue (bias2, ReLU) -> map_out2
-          for (int c2 = 0; c2 < nsub2; ++c2)
-            sub_tile(256u + (uint32_t)(cs * a.chain_n + c2 * 64), a.chain_bias ? a.chain_bias + c2 * 64 : nullptr, 0, a.chain_relu,
-                     c2 == 0 ? &chain_full[cs] : nullptr, cphase, c2 == nsub2 - 1 ? &chain_empty[cs] : nullptr);
-          if (++cs == n_cacc) { cs = 0; cphase ^= 1; }
-        }
+        if (chain_after(it)) chained_epilogue();  // an m-tile group is complete (deferred order: the one before this tile)
+        n_its = it + 1;
       }
+      if (defer && n_its > 0) chained_epilogue();
     } else {
       for (int it = 0, tile; (tile = tile_at(it)) >= 0; ++it) {
         int nt, tw, th, img;
@@ -896,6 +962,13 @@ int launch_conv(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap&
   a.mul_tiles_w = div_mul(a.tiles_w);
   a.mul_tiles_h = div_mul(a.tiles_h);
   if ((long long)a.N * a.tiles_h * a.tiles_w * a.tiles_n * 2048 >= (1ll << 32)) return PE_ERR_UNSUPPORTED;  // fast_div range
+  static DeviceOnce hint_once;
+  if (hint_once.needed()) {
+    const char* e = getenv("PE_CONV_WAIT_HINT");
+    const uint32_t hint = e ? (uint32_t)atoi(e) : 0u;
+    PE_CUDA_CHECK(cudaMemcpyToSymbol(g_wait_hint_ns, &hint, sizeof(hint)));
+    hint_once.mark();
+  }
   static DeviceOnce attr_once;  // one per template instantiation
   if (attr_once.needed()) {
     PE_CUDA_CHECK(cudaFuncSetAttribute(conv_gemm_kernel<BLOCK_N, kStaged>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -928,6 +1001,7 @@ int conv2d_launch(const pe_conv_desc& d, const void* x, const void* w, const flo
   if (ch && ch->w) {  // chained 1x1 on this layer's output tile (see ConvArgs::chain_n)
     if (d.out_fp32 || d.Cout % 256 || d.residual_mode == 2 || d.KH != 1 || (ch->N != 64 && ch->N != 128 && ch->N != 256) || !ch->y)
       return PE_ERR_UNSUPPORTED;
+    if (ch->bn != 0 && ch->bn != 128 && ch->bn != 256) return PE_ERR_INVALID_ARGUMENT;
   }
   if (x2 && x2->x) {  // dual-input 1x1: y = act([x | x2(strided)] . w + bias), w = [Cout][Cin + Cin2]
     if (d.KH != 1 || d.KW != 1 || d.stride != 1 || d.Cin % 64 || x2->Cin % 8 || (x2->stride != 1 && x2->stride != 2)) return PE_ERR_UNSUPPORTED;
@@ -961,7 +1035,10 @@ int conv2d_launch(const pe_conv_desc& d, const void* x, const void* w, const flo
   a.tiles_w = ceil_div(a.Wo, a.TW);
   // Widest N tile that fits: measured on B200, narrowing N to fill more SMs on small maps (res5, p5/p6) LOSES - those
   // layers are bound by L2->SM operand traffic and every extra n-tile re-reads the A patch (profiles/README.md).
-  const int bn = d.Cout >= 256 ? 256 : (d.Cout >= 128 ? 128 : (d.Cout >= 64 ? 64 : (d.Cout > 16 ? 32 : 16)));
+  int bn = d.Cout >= 256 ? 256 : (d.Cout >= 128 ? 128 : (d.Cout >= 64 ? 64 : (d.Cout > 16 ? 32 : 16)));
+  // chained layers: 128-wide main tiles keep two accumulator stages (deferred order, see the kernel); PE_CONV_CHAIN_BN overrides
+  static const int chain_bn_env = [] { const char* e = getenv("PE_CONV_CHAIN_BN"); return e ? atoi(e) : 256; }();
+  if (ch && ch->w && (ch->bn ? ch->bn : chain_bn_env) == 128) bn = 128;
   a.tiles_n = ceil_div(d.Cout, bn);
   a.k_chunks = ceil_div(d.Cin, kBlockK);  // a ragged last chunk is zero-filled by TMA (A and W alike)
   a.k_chunks1 = a.k_chunks;
@@ -1028,7 +1105,7 @@ int conv2d_launch(const pe_conv_desc& d, const void* x, const void* w, const flo
   }
   CUtensorMap mb2, mo2;
   if (chained) {
-    if (!staged || bn != 256) return PE_ERR_UNSUPPORTED;
+    if (!staged || (bn != 256 && bn != 128)) return PE_ERR_UNSUPPORTED;
     cuuint64_t wd[2] = {(cuuint64_t)d.Cout, (cuuint64_t)ch->N};           // W2 [N2][Cout], K-major
     cuuint64_t ws[1] = {(cuuint64_t)d.Cout * 2};
     cuuint32_t wb[2] = {(cuuint32_t)kBlockK, (cuuint32_t)ch->N};
@@ -1060,7 +1137,7 @@ int conv2d_launch(const pe_conv_desc& d, const void* x, const void* w, const flo
       const int io_bytes = kIoBytes + (d.residual_mode == 2 ? kCoarseBytes : 0);
       int b2_total = 0;
       if (chained) {  // chained weight ring: [N2 x 64] bf16 chunks; the operand pipeline gives way (these layers are HBM-bound)
-        a.b2_stages = ch->N <= 64 ? 4 : (ch->N <= 128 ? 3 : 2);
+        a.b2_stages = ch->N <= 64 ? 4 : (ch->N <= 128 ? (bn == 128 ? 4 : 3) : 2);
         b2_total = a.b2_stages * ch->N * 128;
         if (st_want > 2) st_want = 2;
       }
@@ -1094,7 +1171,7 @@ int conv2d_launch(const pe_conv_desc& d, const void* x, const void* w, const flo
   if (staged) {
     switch (bn) {
       case 256: return launch_conv<256, true>(ma, mb, mo, mr, ma2, a, st, chained ? &mb2 : nullptr, chained ? &mo2 : nullptr);
-      case 128: return launch_conv<128, true>(ma, mb, mo, mr, ma2, a, st);
+      case 128: return launch_conv<128, true>(ma, mb, mo, mr, ma2, a, st, chained ? &mb2 : nullptr, chained ? &mo2 : nullptr);
       default: return launch_conv<64, true>(ma, mb, mo, mr, ma2, a, st);
     }
   }
@@ -1179,7 +1256,7 @@ extern "C" PE_API int pe_conv1x1_chain_fwd(const pe_conv_desc* desc, const void*
                                            const float* bias_c, int n_c, int relu_c, void* y_c, void* stream) {
   if (!desc || !wc || !y_c) return PE_ERR_INVALID_ARGUMENT;
   pe::ConvSecondInput s2 = {x2, cin2, h2, w2s, stride2};
-  pe::ConvChain ch = {wc, bias_c, y_c, n_c, relu_c};
+  pe::ConvChain ch = {wc, bias_c, y_c, n_c, relu_c, 0};
   return pe::conv2d_launch(*desc, x, w, bias, residual, y, reinterpret_cast<cudaStream_t>(stream), x2 ? &s2 : nullptr, 0, &ch);
 }
 

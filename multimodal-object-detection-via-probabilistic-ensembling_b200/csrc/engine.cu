@@ -318,7 +318,7 @@ struct Runner {
         // chain the NEXT block's conv1 (cout -> mid, ReLU) onto this conv3: its A operand is this kernel's own output tile
         static const int chain_mask = [] { const char* e = getenv("PE_CONV_CHAIN"); return e ? atoi(e) : 3; }();  // bit s: stage res(2+s); measured:
         // res2 / res3 gain (conv1's 419 / 210 MB re-read disappears), res4 loses (its single main accumulator serialises the longer K loop)
-        ConvChain ch = {nullptr, nullptr, nullptr, 0, 0};
+        ConvChain ch = {nullptr, nullptr, nullptr, 0, 0, 0};
         chained_c1 = false;
         if (b + 1 < blocks[s] && ((chain_mask >> s) & 1) && (64 << s) <= 256 && status == PE_OK) {
           char nq[96];
