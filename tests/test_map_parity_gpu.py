@@ -141,6 +141,6 @@ def test_bf16_engine_keeps_coco_ap_of_fp32_oracle():
         assert r["oracle_AP"] > 5.0, (k, r)                      # the harness model must actually detect something
         assert r["abs_dAP"] < (0.75 if k == "proben_fused" else 1.5), (k, r)  # 0..100 scale
         assert r["abs_dAP50"] < 1.5 and r["abs_dAP75"] < 4.0, (k, r)
+        assert r["same_object_rate"] >= 0.85, (k, r)
     fused = report["proben_fused"]
     assert fused["mAP_two_decimals"][0] == fused["mAP_two_decimals"][1], fused  # "identical COCO mAP to two decimals"
-        assert r["same_object_rate"] >= 0.85, (k, r)
