@@ -5,11 +5,9 @@ import gzip
 import sys
 
 prefix, keep = sys.argv[1], {int(v) for v in sys.argv[2:]}
-idx, out, seen = -1, None, {}
+idx, out = -1, None
 for line in sys.stdin:
     if line.startswith('"Kernel Name"'):
-        name = line
-        n = seen.get(name, 0)
         # ncu prints every launch twice (SASS view + source view); count distinct launches by pairs
         idx += 1
         if out:
