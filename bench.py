@@ -410,23 +410,25 @@ def run_detector_workload(name, args, D, steps, warmup, target_s, instrument, sa
            "clocks": clocks, "models": [m[0] for m in spec["models"]], "K": K, "depth": depth,
            "canvas": list(canvas), "net_hw": [nh, nw]}
     if instrument:
-        # instrumented pass: device time of every tensor-core GEMM launch, detectors back to back on one stream so that every
-        # launch is timed alone; averaged over several passes on the now warm (power-steady) GPU
+        # instrumented passes: device time of the tensor-core GEMM launches, detectors back to back on one stream, on the now
+        # warm (power-steady) GPU.  Mode 1 (the roofline number and the per-layer table): one event pair per launch = the launch
+        # durations.  Mode 2 (reported next to it): one pair per RUN of back-to-back GEMM launches, i.e. durations + the gaps
+        # between consecutive layers with PDL active - what the GEMM chain costs inside a real forward.
         saved = pipe.streams
         pipe.streams = None
-        for d in dets:
-            d.set_profiling(True)
-        passes = []
-        for _ in range(args.profile_passes + 1):
-            pipe.forward_device(slots[0], net_hw=(nh, nw))
-            torch.cuda.synchronize()
-            passes.append(([d.last_profile() for d in dets], [d.profile_launches() for d in dets]))
-        passes = passes[1:]
+        rec["_profile"], rec["_profile_runs"] = [], []
+        for mode, key in ((2, "_profile_runs"), (1, "_profile")):
+            for d in dets:
+                d.set_profiling(mode)
+            for i in range(args.profile_passes + 1):
+                pipe.forward_device(slots[0], net_hw=(nh, nw))
+                torch.cuda.synchronize()
+                if i:
+                    rec[key].append(([d.last_profile() for d in dets], [d.profile_launches() for d in dets]))
         for d in dets:
             d.set_profiling(False)
         pipe.streams = saved
         torch.cuda.synchronize()
-        rec["_profile"] = passes
     counts = [int(pipe.dets[m].counts[:B].sum().item()) for m in range(M)]
     rec["detections_per_image"] = [c / B for c in counts]
     rec["fused_per_item"] = int(pipe.out.counts[:B].sum().item()) / B
@@ -437,9 +439,11 @@ def run_detector_workload(name, args, D, steps, warmup, target_s, instrument, sa
 def conv_roofline(rec, args, n_models_flops):
     """Tensor roofline of the conv/GEMM kernel family from the instrumented passes of ``rec``."""
     passes = rec.pop("_profile")
+    run_passes = rec.pop("_profile_runs")
     peaks, peak_kind = measured_peaks()
     peak_tf = peaks.get("bf16_tflops_sustained", peaks["bf16_tflops"])
-    gemm_ms = float(np.mean([sum(p[0] for p in prof) for prof, _ in passes]))
+    gemm_ms = float(np.mean([sum(p[0] for p in prof) for prof, _ in passes]))            # sum of the launch durations
+    gemm_ms_runs = float(np.mean([sum(p[0] for p in prof) for prof, _ in run_passes]))   # ... plus the gaps inside GEMM runs
     span_ms = float(np.mean([sum(p[1] for p in prof) for prof, _ in passes]))
     n_gemm = sum(p[3] for p in passes[0][0])
     l_ms = np.mean([np.concatenate([l[0] for l in layers]) for _, layers in passes], axis=0)
@@ -479,7 +483,13 @@ def conv_roofline(rec, args, n_models_flops):
             "traffic": traffic, "traffic_unit": "DRAM bytes per batch over the GEMM launches", "traffic_source": traffic_src,
             "tensor_pipe_active_pct_time_weighted": tensor_pipe,
             "peak_kind": peak_kind + " (sustained cuBLAS bf16)", "kernel": "conv_gemm_kernel<*> (tcgen05)",
-            "algorithmic_gflop_per_batch": flop_batch / 1e9, "gemm_ms_per_batch": gemm_ms, "gemm_launches_per_batch": n_gemm,
+            "algorithmic_gflop_per_batch": flop_batch / 1e9, "gemm_ms_per_batch": gemm_ms,
+            "gemm_ms_method": "sum of the per-launch durations (one CUDA-event pair per launch, serial instrumented passes)",
+            "gemm_ms_per_batch_incl_gaps": gemm_ms_runs,
+            "gemm_ms_incl_gaps_method": "one CUDA-event pair per RUN of back-to-back GEMM launches (%d runs per batch): launch gaps "
+                                        "between consecutive layers included, PDL overlap active" % sum(len(l[0]) for l in run_passes[0][1]),
+            "frac_incl_gaps": flop_batch / (gemm_ms_runs * 1e-3) / 1e12 / peak_tf,
+            "gemm_launches_per_batch": n_gemm,
             "gemm_share_of_serial_batch": gemm_ms / max(1e-9, span_ms), "profile_passes": len(passes),
             "batch_frac_of_peak": flop_batch / (rec["ms_per_batch"] * 1e-3) / 1e12 / peak_tf,
             "per_launch_roofline": per_launch}

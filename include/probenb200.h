@@ -180,7 +180,9 @@ PE_API int pe_detector_forward_stages(pe_detector* d, const void* weights, const
 PE_API int pe_detector_forward_frames(pe_detector* d, const void* weights, const uint8_t* frames, int B, int src_h, int src_w,
                                       int img_h, int img_w, int round_u8, float out_h, float out_w, const pe_detections* out,
                                       void* workspace, size_t workspace_bytes, void* stream);
-/* Instrumentation for bench.py: CUDA events around every tensor-core GEMM launch of the next forwards. */
+/* Instrumentation for bench.py: enabled = 1: CUDA events around every tensor-core GEMM launch of the next forwards (per-layer table);
+ * enabled = 2: one event pair around every RUN of back-to-back GEMM launches (no event in between, so the launch gaps and the
+ * programmatic-dependent-launch overlap of consecutive layers count exactly as in a real forward); 0 = off. */
 PE_API int pe_detector_set_profiling(pe_detector* d, int enabled);
 PE_API int pe_detector_last_profile(pe_detector* d, float* gemm_ms, float* span_ms, int* launches, int* gemm_launches);
 /* Per GEMM launch of the last profiled forward: device ms, algorithmic FLOPs, algorithmic bytes (every operand once).

@@ -44,6 +44,10 @@ struct pe_detector {
   pe_detector_config cfg;
   // optional per-forward instrumentation (pe_detector_set_profiling): CUDA events around every GEMM launch
   bool profiling = false;
+  // profiling mode 2: ONE event pair per run of back-to-back GEMM launches (no event between them, so programmatic dependent launch
+  // and the launch gaps count exactly as they do in a real forward); mode 1: one pair per launch (per-layer table)
+  bool profile_runs = false;
+  bool run_open = false;
   std::vector<cudaEvent_t> ev;
   int ev_used = 0;
   std::vector<double> prof_flops, prof_bytes;  // algorithmic work of the GEMM launch behind each event pair
@@ -201,8 +205,10 @@ struct Runner {
         if (cudaEventCreate(&e) != cudaSuccess) return PE_ERR_CUDA;
         d->ev.push_back(e);
       }
-      e0 = d->ev[d->ev_used++];
-      e1 = d->ev[d->ev_used++];
+      if (!d->profile_runs || !d->run_open) {
+        e0 = d->ev[d->ev_used++];
+        e1 = d->ev[d->ev_used++];  // recorded by end_run() in run mode
+      }
       const int pad = (cd.KH - 1) / 2;
       const double Ho = (cd.H + 2 * pad - cd.KH) / cd.stride + 1, Wo = (cd.W + 2 * pad - cd.KW) / cd.stride + 1;
       const double taps = (double)cd.KH * cd.KW * cd.Cin + (x2 ? x2->Cin : 0), opix = (double)cd.N * Ho * Wo;
@@ -216,18 +222,32 @@ struct Runner {
         flops += 2.0 * opix * cd.Cout * chain->N;
         bytes += (double)chain->N * cd.Cout * 2 + chain->N * 4.0 + opix * chain->N * 2;
       }
-      d->prof_flops.push_back(flops);
-      d->prof_bytes.push_back(bytes);
-      cudaEventRecord(e0, st);
+      if (e0) {
+        d->prof_flops.push_back(flops);
+        d->prof_bytes.push_back(bytes);
+        cudaEventRecord(e0, st);
+      } else {  // the run's totals accumulate in its slot
+        d->prof_flops.back() += flops;
+        d->prof_bytes.back() += bytes;
+      }
+      if (d->profile_runs) { d->run_open = true; e1 = nullptr; }
     }
     // consecutive layers walk their tiles in opposite directions (conv_gemm.cu ConvArgs::reverse); PE_CONV_REVERSE=0 disables
     static const int alternate = [] { const char* e = getenv("PE_CONV_REVERSE"); return e ? atoi(e) : 1; }();
     rev ^= alternate;
     const int s = conv2d_launch(cd, x, w, bias, res, y, st, x2, rev, chain);
-    if (d->profiling) cudaEventRecord(e1, st);
+    if (d->profiling && e1) cudaEventRecord(e1, st);
     d->last_launches++;
     d->last_gemm_launches++;
     return s;
+  }
+
+  // run mode: closes the open run of GEMM launches (called before every non-GEMM launch and at the end of the forward)
+  void end_run() {
+    if (d->profiling && d->profile_runs && d->run_open) {
+      cudaEventRecord(d->ev[d->ev_used - 1], st);
+      d->run_open = false;
+    }
   }
 
   void conv(const std::string& pname, const void* x, int H, int W, int stride, bool relu, int rmode, const void* res, void* y,
@@ -250,6 +270,7 @@ struct Runner {
     status = gemm(cd, x, wts + p.w_off, reinterpret_cast<const float*>(wts + p.b_off), nullptr, y);
   }
   void check(int s, int launches = 1) { if (status == PE_OK) status = s; d->last_launches += launches; }
+#define PE_NONGEMM(call) do { end_run(); check(call); } while (0)
 
   // raw uint8 frames (resized on the fly) instead of a float32 tensor when frames != nullptr
   const unsigned char* frames = nullptr;
@@ -267,10 +288,10 @@ struct Runner {
     if (!prenormalized)
       for (int i = 0; i < d->stem_c; ++i) { nrm.mean[i] = c.pixel_mean[c0 + i]; nrm.std[i] = c.pixel_std[c0 + i]; }
     if (frames)
-      check(launch_stem_im2col_u8(frames, buf("stem_canvas"), nullptr, B, Ctot, c0, d->stem_c, src_h, src_w, img_h, img_w, c.canvas_h,
+      PE_NONGEMM(launch_stem_im2col_u8(frames, buf("stem_canvas"), nullptr, B, Ctot, c0, d->stem_c, src_h, src_w, img_h, img_w, c.canvas_h,
                                   c.canvas_w, round_u8, nrm, st, buf("pil_taps")));
     else
-      check(launch_stem_im2col(images, buf("stem_canvas"), nullptr, B, Ctot, c0, d->stem_c, img_h, img_w, c.canvas_h, c.canvas_w, nrm, st));
+      PE_NONGEMM(launch_stem_im2col(images, buf("stem_canvas"), nullptr, B, Ctot, c0, d->stem_c, img_h, img_w, c.canvas_h, c.canvas_w, nrm, st));
     if (status == PE_OK) {  // 7x7/2 conv: tcgen05 GEMM whose A operand is TMA-read straight from the canvas (fp16 operands)
       const Param& p = d->params[d->find_param("backbone.bottom_up.stem.conv1")];
       cudaEvent_t e0 = nullptr, e1 = nullptr;
@@ -296,7 +317,7 @@ struct Runner {
       d->last_launches++;
       d->last_gemm_launches++;
     }
-    check(launch_maxpool(buf("stem_out"), buf("pool_out"), B, d->H[0], d->W[0], 64, st));
+    PE_NONGEMM(launch_maxpool(buf("stem_out"), buf("pool_out"), B, d->H[0], d->W[0], 64, st));
     const int* blocks = c.depth == 101 ? kStageBlocks101 : kStageBlocks50;
     const void* x = buf("pool_out");
     int H = d->H[1], W = d->W[1];
@@ -385,12 +406,12 @@ struct Runner {
           snprintf(qa, sizeof(qa), "pout%d_0", l);
           snprintf(qb, sizeof(qb), "pout%d_1", l);
           snprintf(qp, sizeof(qp), "p%d", l);
-          check(launch_concat_channels(buf(qa), buf(qb), buf(qp), (long long)B * d->H[l - 1] * d->W[l - 1], 256, st));
+          PE_NONGEMM(launch_concat_channels(buf(qa), buf(qb), buf(qp), (long long)B * d->H[l - 1] * d->W[l - 1], 256, st));
         }
       } else {
         backbone(images, Ctot, 0, img_h, img_w, 0);
       }
-      check(launch_subsample2(level_feat(5), buf("p6"), B, d->H[4], d->W[4], d->fc, st));
+      PE_NONGEMM(launch_subsample2(level_feat(5), buf("p6"), B, d->H[4], d->W[4], d->fc, st));
     }
     float4* props = reinterpret_cast<float4*>(buf("proposals"));
     int* prop_count = reinterpret_cast<int*>(buf("prop_count"));
@@ -424,11 +445,13 @@ struct Runner {
       rs.keep_idx = reinterpret_cast<int*>(buf("keep_idx"));
       rs.keep_count = reinterpret_cast<int*>(buf("keep_count"));
       rs.nms_mask = reinterpret_cast<unsigned*>(buf("nms_mask"));
-      if (status == PE_OK)
+      if (status == PE_OK) {
+        end_run();
         check(launch_rpn_proposals(lv, B, c.pre_nms_topk, c.post_nms_topk, c.rpn_nms_thresh, (float)img_h, (float)img_w, rs, kMaxProps,
                                    props, prop_count, st), 4);
+      }
     }
-    if (!(stages & PE_STAGE_ROI_HEADS)) return status;
+    if (!(stages & PE_STAGE_ROI_HEADS)) { end_run(); return status; }
     // ROI heads (roi_heads.py:595-631)
     RoiLevels fl;
     for (int l = 2; l <= 5; ++l) {
@@ -437,7 +460,7 @@ struct Runner {
       fl.W[l - 2] = d->W[l - 1];
       fl.scale[l - 2] = 1.0f / (float)(2 << (l - 1));
     }
-    if (status == PE_OK) check(launch_roi_align(fl, props, prop_count, B, kMaxProps, d->fc, buf("roi_feats"), st));
+    if (status == PE_OK) PE_NONGEMM(launch_roi_align(fl, props, prop_count, B, kMaxProps, d->fc, buf("roi_feats"), st));
     linear("roi_heads.box_head.fc1", buf("roi_feats"), B * kMaxProps, true, buf("fc1_out"), false);
     linear("roi_heads.box_head.fc2", buf("fc1_out"), B * kMaxProps, true, buf("fc2_out"), false);
     linear("roi_heads.box_predictor", buf("fc2_out"), B * kMaxProps, false, buf("head_out"), true);
@@ -450,7 +473,8 @@ struct Runner {
     out.boxes = reinterpret_cast<float4*>(o.boxes); out.scores = o.scores; out.classes = o.classes; out.logits = o.class_logits;
     out.probs = o.probs; out.vars = o.vars; out.roi_index = o.roi_index; out.count = o.counts;
     if (status == PE_OK)
-      check(launch_head_post(reinterpret_cast<const float*>(buf("head_out")), d->npad, props, prop_count, B, kMaxProps, c.num_classes, hp, out, st));
+      PE_NONGEMM(launch_head_post(reinterpret_cast<const float*>(buf("head_out")), d->npad, props, prop_count, B, kMaxProps, c.num_classes, hp, out, st));
+    end_run();
     return status;
   }
 };
@@ -485,6 +509,8 @@ extern "C" PE_API void pe_detector_destroy(pe_detector* d) {
 extern "C" PE_API int pe_detector_set_profiling(pe_detector* d, int enabled) {
   if (!d) return PE_ERR_INVALID_ARGUMENT;
   d->profiling = enabled != 0;
+  d->profile_runs = enabled == 2;  // 2: one event pair per run of back-to-back GEMM launches
+  d->run_open = false;
   return PE_OK;
 }
 
@@ -574,6 +600,7 @@ extern "C" PE_API int pe_detector_forward_stages(pe_detector* d, const void* wei
   if (img_h < 1 || img_w < 1 || img_h > d->cfg.canvas_h || img_w > d->cfg.canvas_w) return PE_ERR_INVALID_ARGUMENT;
   if (workspace_bytes < d->ws_bytes) return PE_ERR_WORKSPACE_TOO_SMALL;
   d->ev_used = 0;
+  d->run_open = false;
   d->prof_flops.clear();
   d->prof_bytes.clear();
   d->last_launches = 0;
@@ -598,6 +625,7 @@ extern "C" PE_API int pe_detector_forward_frames(pe_detector* d, const void* wei
   if (img_h < 1 || img_w < 1 || img_h > d->cfg.canvas_h || img_w > d->cfg.canvas_w) return PE_ERR_INVALID_ARGUMENT;
   if (workspace_bytes < d->ws_bytes) return PE_ERR_WORKSPACE_TOO_SMALL;
   d->ev_used = 0;
+  d->run_open = false;
   d->prof_flops.clear();
   d->prof_bytes.clear();
   d->last_launches = 0;
