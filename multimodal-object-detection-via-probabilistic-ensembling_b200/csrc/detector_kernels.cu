@@ -325,11 +325,14 @@ __device__ __forceinline__ uint32_t bf16x2_max(uint32_t a, uint32_t b) {
   return *reinterpret_cast<const uint32_t*>(&r);
 }
 
+// reverse: walk the outputs from the last to the first, so the kernel starts on the part of x its producer (the stem conv, which
+// walks forward) wrote last and that is still in L2; the consumer of y then walks forward for the same reason
 __global__ void maxpool3x3s2_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ y, int B, int H, int W,
-                                    int C, int Ho, int Wo) {
+                                    int C, int Ho, int Wo, int reverse) {
   const int cg = C >> 3;
   const long long total = (long long)B * Ho * Wo * cg;
-  for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
+  for (long long t0 = blockIdx.x * (long long)blockDim.x + threadIdx.x; t0 < total; t0 += (long long)gridDim.x * blockDim.x) {
+    const long long t = reverse ? total - 1 - t0 : t0;
     const int g = (int)(t % cg);
     long long pix = t / cg;
     const int wo = (int)(pix % Wo);
@@ -1402,11 +1405,11 @@ int launch_resize_frames(const unsigned char* src, float* dst, int B, int C, int
   return PE_OK;
 }
 
-int launch_maxpool(const void* x, void* y, int B, int H, int W, int C, cudaStream_t st) {
+int launch_maxpool(const void* x, void* y, int B, int H, int W, int C, cudaStream_t st, int reverse) {
   const int Ho = (H - 1) / 2 + 1, Wo = (W - 1) / 2 + 1;
   const long long total = (long long)B * Ho * Wo * (C / 8);
   maxpool3x3s2_kernel<<<grid_for(total, 256), 256, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(x), reinterpret_cast<__nv_bfloat16*>(y),
-                                                              B, H, W, C, Ho, Wo);
+                                                              B, H, W, C, Ho, Wo, reverse);
   PE_LAUNCH_CHECK();
   return PE_OK;
 }

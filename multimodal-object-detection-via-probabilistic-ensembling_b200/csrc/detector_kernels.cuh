@@ -59,7 +59,7 @@ int launch_stem_im2col_u8(const unsigned char* frames, void* canvas, void* A, in
 constexpr int kStemK = 224;  // 7 rows x (8 px x 4 ch): K of the stem GEMM (147 real taps, the rest meet zero weights)
 int launch_resize_frames(const unsigned char* src, float* dst, int B, int C, int Hs, int Ws, int Hd, int Wd, int round_u8,
                          cudaStream_t st);
-int launch_maxpool(const void* x, void* y, int B, int H, int W, int C, cudaStream_t st);
+int launch_maxpool(const void* x, void* y, int B, int H, int W, int C, cudaStream_t st, int reverse = 0);
 int launch_subsample2(const void* x, void* y, int B, int H, int W, int C, cudaStream_t st);
 int launch_concat_channels(const void* a, const void* b, void* y, long long pixels, int C, cudaStream_t st);
 int launch_rpn_proposals(const RpnLevels& lv, int B, int pre_topk, int post_topk, float nms_thr, float img_h, float img_w,

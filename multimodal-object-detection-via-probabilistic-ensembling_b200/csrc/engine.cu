@@ -242,6 +242,11 @@ struct Runner {
     return s;
   }
 
+  static int stem_reverse() {
+    static const int alternate = [] { const char* e = getenv("PE_CONV_REVERSE"); return e ? atoi(e) : 1; }();
+    return alternate;
+  }
+
   // run mode: closes the open run of GEMM launches (called before every non-GEMM launch and at the end of the forward)
   void end_run() {
     if (d->profiling && d->profile_runs && d->run_open) {
@@ -312,12 +317,15 @@ struct Runner {
       }
       if (status == PE_OK)
         status = conv_stem_launch(buf("stem_canvas"), wts + p.w_off, reinterpret_cast<const float*>(wts + p.b_off), buf("stem_out"), B,
-                                  c.canvas_h, c.canvas_w, st, rev = 0);
+                                  c.canvas_h, c.canvas_w, st, rev = stem_reverse());
       if (e1) cudaEventRecord(e1, st);
       d->last_launches++;
       d->last_gemm_launches++;
     }
-    PE_NONGEMM(launch_maxpool(buf("stem_out"), buf("pool_out"), B, d->H[0], d->W[0], 64, st));
+    // direction chain (L2 reuse, see ConvArgs::reverse): canvas staging walks forward -> stem conv backwards -> max-pool forward ->
+    // res2.0.conv1 backwards -> ...
+    PE_NONGEMM(launch_maxpool(buf("stem_out"), buf("pool_out"), B, d->H[0], d->W[0], 64, st, 0));
+    rev = 0;  // the next GEMM toggles to 1 = backwards
     const int* blocks = c.depth == 101 ? kStageBlocks101 : kStageBlocks50;
     const void* x = buf("pool_out");
     int H = d->H[1], W = d->W[1];
