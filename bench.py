@@ -167,7 +167,10 @@ def fusion_regime(D, images, models, mean_dets, method, steps, warmup, e2e=True,
            "detections_per_pair": N / B, "models": models,
            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": achieved / peaks["hbm_gbs"],
                         "traffic": None, "peak_kind": peak_kind, "algorithmic_bytes_per_launch": alg,
-                        "kernel": "fuse_block_kernel" if N / B / 1 > 32 else "fuse_packed_kernel"}}
+                        "kernel": "fuse_block_kernel" if N / B / 1 > 32 else "fuse_packed_kernel",
+                        "note": ("%.0f detections per pair: n/4 = %.0f pair-flops per byte, the ALU-bound regime of SURVEY.md §8d (> 40 "
+                                 "detections); the HBM fraction is reported for completeness" % (N / B, N / B / 4)) if N / B > 40 else
+                                "HBM-bound regime by arithmetic intensity (SURVEY.md §8d); measured instruction-issue bound"}}
     if e2e:
         host_in = {k: torch.from_numpy(packed[k]).pin_memory() for k in ("boxes", "scores", "classes", "probs", "vars", "offsets")}
         e2e_dev = {k: torch.empty_like(v, device=D.dev) for k, v in host_in.items()}
