@@ -103,6 +103,8 @@ class ProbEnPipeline:
         raw uint8 frames [B, H, W, C_m] that the engine resizes to ``net_hw`` on the fly.  Asynchronous.
         Returns the ``FusedOutput`` (boxes in the frame_size coordinate system)."""
         B = images[0].shape[0]
+        nvtx = torch.cuda.nvtx
+
         def run(det, img, buf):
             if net_hw is not None:
                 # 3-channel uint8 frames take Pillow's 8-bit resize in the reference, 4-/6-channel arrays cv2's float path
@@ -114,19 +116,25 @@ class ProbEnPipeline:
             raise RuntimeError("pipeline was built for batch %d" % self.B)
         main = torch.cuda.current_stream(self.device)
         stream = _lib.current_stream_ptr(self.device)
+        # NVTX ranges (nsys / ncu --nvtx): one per model forward, one for pack + fuse
         if self.streams is None:
-            for det, img, buf in zip(self.detectors, images, self.dets):
+            for m, (det, img, buf) in enumerate(zip(self.detectors, images, self.dets)):
+                nvtx.range_push("probenb200.detector[%d]" % m)
                 run(det, img, buf)
+                nvtx.range_pop()
         else:
             self.ev_start.record(main)
             for m, (det, img, buf) in enumerate(zip(self.detectors, images, self.dets)):
                 with torch.cuda.stream(self.streams[m]):
                     self.streams[m].wait_event(self.ev_start)
+                    nvtx.range_push("probenb200.detector[%d]" % m)
                     run(det, img, buf)
+                    nvtx.range_pop()
                     self.ev_done[m].record(self.streams[m])
             for m in range(self.M):
                 main.wait_event(self.ev_done[m])
         o = self.out
+        nvtx.range_push("probenb200.pack+fuse")
         with torch.cuda.device(self.device):
             st = self.lib.pe_pack_detections(self.det_structs, self.M, B, self.K, _lib.ptr(o.offsets), _lib.ptr(self.in_boxes),
                                              _lib.ptr(self.in_scores), _lib.ptr(self.in_classes), _lib.ptr(self.in_probs),
@@ -137,6 +145,7 @@ class ProbEnPipeline:
                                         self.codes[1], float(self.frame_w), float(self.frame_h), _lib.ptr(o.boxes), _lib.ptr(o.scores),
                                         _lib.ptr(o.classes), _lib.ptr(o.counts), _lib.ptr(self.fuse_ws), self.ws_bytes, stream)
             _lib.check(st, "pe_fuse_batch")
+        nvtx.range_pop()
         return o
 
     def gather(self, out, group=None):
