@@ -428,6 +428,8 @@ def run_detector_workload(name, args, D, steps, warmup, target_s, instrument, sa
                 torch.cuda.synchronize()
                 if i:
                     rec[key].append(([d.last_profile() for d in dets], [d.profile_launches() for d in dets]))
+                    if mode == 1:
+                        rec.setdefault("_profile_kernels", []).append([d.profile_kernels() for d in dets])
         for d in dets:
             d.set_profiling(False)
         pipe.streams = saved
@@ -498,6 +500,44 @@ def conv_roofline(rec, args, n_models_flops):
             "per_launch_roofline": per_launch}
 
 
+def secondary_kernels(rec):
+    """Device time of the non-GEMM launch groups (event pair per group in the instrumented passes, both detectors summed) with the
+    HBM roofline of the ones that stream: algorithmic bytes = every input and output once."""
+    passes = rec.pop("_profile_kernels", None)
+    if not passes:
+        return None
+    peaks, peak_kind = measured_peaks()
+    B, (ch, cw), (nh, nw), n_models = rec["batch_per_gpu"], rec["canvas"], rec["net_hw"], len(rec["models"])
+    tot = {}
+    for p in passes:
+        for det in p:
+            for name, ms in det:
+                tot[name] = tot.get(name, 0.0) + ms / len(passes)
+    lv = [(ch >> s, cw >> s) for s in (2, 3, 4, 5)]
+    feat_b = sum(h * w for h, w in lv) * 256 * 2
+    algo = {  # bytes per batch and detector
+        "launch_stem_im2col_u8": B * (512 * 640 * 3 + (ch + 6) * (cw + 8) * 8),
+        "launch_maxpool": B * ((ch // 2) * (cw // 2) + (ch // 4) * (cw // 4)) * 64 * 2,
+        "launch_roi_align": B * (1000 * 49 * 256 * 2 + feat_b),
+        "launch_rpn_proposals": B * (sum(h * w for h, w in lv) + (ch >> 6) * (cw >> 6)) * 16 * 4,
+    }
+    label = {"launch_stem_im2col_u8": "canvas staging (Pillow-exact resize + normalise, fused)", "launch_maxpool": "stem max-pool 3x3/2",
+             "launch_roi_align": "ROIAlign 7x7, 4 levels, 1000 ROIs per image", "launch_rpn_proposals": "RPN decode + top-k + NMS + merge (4 kernels)",
+             "launch_head_post": "softmax + decode + per-class NMS + top-100", "launch_subsample2": "p6 = p5[::2, ::2]",
+             "launch_concat_channels": "middle-fusion channel concat"}
+    out = {}
+    for name, ms in sorted(tot.items(), key=lambda kv: -kv[1]):
+        e = {"what": label.get(name, name), "ms_per_batch": ms, "share_of_serial_batch": None}
+        if name in algo:
+            by = algo[name] * n_models
+            e["algorithmic_mb_per_batch"] = by / 1e6
+            e["hbm_frac"] = by / (ms * 1e-3) / (peaks["hbm_gbs"] * 1e9)
+        else:
+            e["bound"] = "latency (one block per image / level)"
+        out[name.replace("launch_", "")] = e
+    return out
+
+
 def workload_flops(name, depth, canvas, B):
     spec = WORKLOADS[name]
     tot = 0.0
@@ -535,7 +575,13 @@ def run_pairs(args, D):
         return None
     spec = WORKLOADS[name]
     B = rec["batch_per_gpu"]
+    sec = secondary_kernels(rec)
     roof = conv_roofline(rec, args, workload_flops(name, rec["depth"], rec["canvas"], B))
+    if sec:
+        span = roof["gemm_ms_per_batch"] / max(1e-9, roof["gemm_share_of_serial_batch"])
+        for e in sec.values():
+            e["share_of_serial_batch"] = e["ms_per_batch"] / span
+        extra["secondary_kernels"] = sec
     for k, r in extra.items():
         if isinstance(r, dict):
             r.pop("_profile", None)

@@ -188,6 +188,10 @@ PE_API int pe_detector_last_profile(pe_detector* d, float* gemm_ms, float* span_
 /* Per GEMM launch of the last profiled forward: device ms, algorithmic FLOPs, algorithmic bytes (every operand once).
  * Fills at most `capacity` entries; returns the number of launches recorded (0 when profiling is off). */
 PE_API int pe_detector_profile_launches(pe_detector* d, float* ms, double* flops, double* bytes, int capacity);
+/* Non-GEMM launch groups of the last forward profiled with mode 1 (canvas staging, max-pool, RPN selection + NMS, ROIAlign,
+ * head post-processing ...): `names` receives one 32-byte NUL-terminated launcher name per entry, `ms` the device time.
+ * Fills at most `capacity` entries; returns the number recorded. */
+PE_API int pe_detector_profile_kernels(pe_detector* d, char* names, float* ms, int capacity);
 /* DefaultPredictor's ResizeShortestEdge (engine/defaults.py:186-190): uint8 HWC frames [B,src_h,src_w,C] ->
  * float32 CHW [B,C,dst_h,dst_w], bilinear with half-pixel centres; round_u8 mimics PIL's uint8 output. */
 PE_API int pe_resize_frames(const uint8_t* frames, float* out, int B, int C, int src_h, int src_w, int dst_h, int dst_w,

@@ -75,6 +75,7 @@ SIGNATURES.update({
     "pe_detector_last_profile": (c_int, [c_void_p, ctypes.POINTER(c_float), ctypes.POINTER(c_float), ctypes.POINTER(c_int), ctypes.POINTER(c_int)]),
     "pe_detector_profile_launches": (c_int, [c_void_p, ctypes.POINTER(c_float), ctypes.POINTER(ctypes.c_double),
                                              ctypes.POINTER(ctypes.c_double), c_int]),
+    "pe_detector_profile_kernels": (c_int, [c_void_p, ctypes.c_char_p, ctypes.POINTER(c_float), c_int]),
     "pe_resize_frames": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p]),
     "pe_rpn_proposals_workspace_bytes": (c_size_t, [c_int]),
     "pe_rpn_proposals": (c_int, [ctypes.POINTER(c_void_p), ctypes.POINTER(c_int), ctypes.POINTER(c_int), c_int, c_int, c_int,

@@ -267,6 +267,88 @@ __global__ void stem_canvas_u8_kernel(const unsigned char* __restrict__ frames, 
   }
 }
 
+// Stage 1'', upscales with Pillow rounding (the FLIR / KAIST case, 512x640 -> 800x1000): Pillow's own two-pass order, tiled.
+// A block owns kCanvasRows canvas rows of one image.  Pass 1 filters the source rows those canvas rows touch horizontally
+// (<= kCanvasRows + 3 of them for any upscale; tap windows are monotone in y) into shared memory as rounded uint8 pixels,
+// 4 channels to a word - exactly Pillow's intermediate image; pass 2 filters vertically from shared memory and maps the
+// 256 possible pixel values of each channel through a (v - mean) / std table.  Same arithmetic as stem_canvas_u8_kernel<3>
+// (bit-identical canvas), but every horizontally filtered pixel is computed once per block instead of once per output
+// pixel and row tap, and the per-pixel 64-bit index arithmetic and IEEE divisions are gone: 203 -> see profiles/README.md.
+constexpr int kCanvasRows = 8;
+constexpr int kCanvasSpan = kCanvasRows + 4;
+
+__global__ void __launch_bounds__(256) stem_canvas_u8_tiled_kernel(const unsigned char* __restrict__ frames, __half* __restrict__ canvas,
+                                                                    int Ctot, int c0, int C, int Hs, int Ws, int Hi, int Wi, int Hp, int Wp,
+                                                                    StemNorm nrm, const int4* __restrict__ taps) {
+  extern __shared__ uint32_t s_h[];      // [kCanvasSpan][Wi]
+  __shared__ __half s_lut[4][256];
+  const int tid = threadIdx.x, b = blockIdx.y, yp0 = blockIdx.x * kCanvasRows;
+  for (int i = tid; i < 4 * 256; i += 256) {
+    const int c = i >> 8;
+    s_lut[c][i & 255] = __float2half_rn(c < C ? __fdiv_rn((float)(i & 255) - nrm.mean[c], nrm.std[c]) : 0.f);
+  }
+  const int ya = max(yp0 - 3, 0), yb = min(yp0 + kCanvasRows - 1 - 3, Hi - 1);  // image rows under this block's canvas rows
+  int s0 = 0, ns = 0;
+  if (ya <= yb) {
+    const int4 ea = __ldg(taps + ya), eb = __ldg(taps + yb);
+    s0 = ea.x & 0xffffff;
+    ns = min((eb.x & 0xffffff) + (eb.x >> 24) - s0, kCanvasSpan);
+  }
+  const unsigned char* im = frames + (size_t)b * Hs * Ws * Ctot;
+  for (int x = tid; x < Wi; x += 256) {
+    const PilTaps<3> tx = pil_taps_from_table(__ldg(taps + Hi + x));
+    const unsigned char* colp = im + ((size_t)s0 * Ws + tx.lo) * Ctot + c0;
+    for (int r = 0; r < ns; ++r) {
+      const unsigned char* rowp = colp + (size_t)r * Ws * Ctot;
+      int h[4];
+#pragma unroll
+      for (int c = 0; c < 4; ++c) h[c] = 1 << (kPilPrecisionBits - 1);
+#pragma unroll
+      for (int i = 0; i < 3; ++i) {
+        if (i < tx.n) {
+#pragma unroll
+          for (int c = 0; c < 4; ++c)
+            if (c < C) h[c] += (int)__ldg(rowp + i * Ctot + c) * tx.k[i];
+        }
+      }
+      s_h[r * Wi + x] = (uint32_t)pil_clip8(h[0]) | ((uint32_t)pil_clip8(h[1]) << 8) | ((uint32_t)pil_clip8(h[2]) << 16) |
+                        ((uint32_t)pil_clip8(h[3]) << 24);
+    }
+  }
+  __syncthreads();
+  for (int ry = 0; ry < kCanvasRows; ++ry) {
+    const int yp = yp0 + ry, y = yp - 3;
+    if (yp >= Hp) break;
+    uint2* dst = reinterpret_cast<uint2*>(canvas + ((size_t)b * Hp + yp) * Wp * 4);
+    const bool row_in = y >= 0 && y < Hi;
+    PilTaps<3> ty;
+    ty.lo = 0; ty.n = 0; ty.k[0] = ty.k[1] = ty.k[2] = 0;
+    if (row_in) ty = pil_taps_from_table(__ldg(taps + y));
+    const uint32_t* hrow = s_h + (ty.lo - s0) * Wi;
+    for (int xp = tid; xp < Wp; xp += 256) {
+      const int x = xp - 3;
+      uint2 o = make_uint2(0u, 0u);
+      if (row_in && x >= 0 && x < Wi) {
+        int acc[4];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) acc[c] = 1 << (kPilPrecisionBits - 1);
+#pragma unroll
+        for (int j = 0; j < 3; ++j) {
+          if (j < ty.n) {
+            const uint32_t w = hrow[j * Wi + x];
+#pragma unroll
+            for (int c = 0; c < 4; ++c) acc[c] += (int)((w >> (8 * c)) & 0xffu) * ty.k[j];
+          }
+        }
+        const unsigned short v0 = __half_as_ushort(s_lut[0][pil_clip8(acc[0])]), v1 = __half_as_ushort(s_lut[1][pil_clip8(acc[1])]);
+        const unsigned short v2 = __half_as_ushort(s_lut[2][pil_clip8(acc[2])]), v3 = __half_as_ushort(s_lut[3][pil_clip8(acc[3])]);
+        o = make_uint2((uint32_t)v0 | ((uint32_t)v1 << 16), (uint32_t)v2 | ((uint32_t)v3 << 16));
+      }
+      dst[xp] = o;
+    }
+  }
+}
+
 // Stage 2: A[pixel][kh*32 + kw*4 + c] = canvas[2*ho + kh][2*wo + kw][c] for kh < 7, kw < 8 (kw = 7 and c >= C meet
 // zero weights): every (pixel, kh) is one contiguous 64-byte run of the canvas -> four 16-byte copies.
 __global__ void stem_im2col_kernel(const __half* __restrict__ canvas, __half* __restrict__ A, int B, int Ho, int Wo, int Hp, int Wp) {
@@ -1379,7 +1461,18 @@ int launch_stem_im2col_u8(const unsigned char* frames, void* canvas, void* A, in
     pil_taps_table_kernel<<<ceil_div(Hi + Wi, 256), 256, 0, st>>>(taps, Hs, Ws, Hi, Wi);
     PE_LAUNCH_CHECK();
   }
-  if (kmax == 0) stem_canvas_u8_kernel<0><<<grid, 256, 0, st>>>(frames, cv, B, Ctot, c0, C, Hs, Ws, Hi, Wi, Hp, Wp, nrm, nullptr);
+  // upscales: the tiled two-pass kernel (PE_STEM_TILED=0 keeps the per-pixel kernel, A/B switch)
+  static const int tiled_env = [] { const char* e = getenv("PE_STEM_TILED"); return e ? atoi(e) : 1; }();
+  const size_t tiled_smem = (size_t)kCanvasSpan * Wi * sizeof(uint32_t);
+  if (kmax == 3 && taps && tiled_env && tiled_smem <= 160 * 1024) {
+    static DeviceOnce attr_once;
+    if (attr_once.needed()) {
+      PE_CUDA_CHECK(cudaFuncSetAttribute(stem_canvas_u8_tiled_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+      attr_once.mark();
+    }
+    stem_canvas_u8_tiled_kernel<<<dim3((unsigned)ceil_div(Hp, kCanvasRows), (unsigned)B), 256, tiled_smem, st>>>(frames, cv, Ctot, c0, C, Hs, Ws,
+                                                                                                         Hi, Wi, Hp, Wp, nrm, taps);
+  } else if (kmax == 0) stem_canvas_u8_kernel<0><<<grid, 256, 0, st>>>(frames, cv, B, Ctot, c0, C, Hs, Ws, Hi, Wi, Hp, Wp, nrm, nullptr);
   else if (kmax == 3) stem_canvas_u8_kernel<3><<<grid, 256, 0, st>>>(frames, cv, B, Ctot, c0, C, Hs, Ws, Hi, Wi, Hp, Wp, nrm, taps);
   else stem_canvas_u8_kernel<9><<<grid, 256, 0, st>>>(frames, cv, B, Ctot, c0, C, Hs, Ws, Hi, Wi, Hp, Wp, nrm, nullptr);
   PE_LAUNCH_CHECK();

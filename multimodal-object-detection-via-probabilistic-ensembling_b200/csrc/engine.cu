@@ -51,6 +51,10 @@ struct pe_detector {
   std::vector<cudaEvent_t> ev;
   int ev_used = 0;
   std::vector<double> prof_flops, prof_bytes;  // algorithmic work of the GEMM launch behind each event pair
+  // mode 1 also brackets every NON-GEMM launch group (staging, pooling, RPN selection / NMS, ROIAlign, head post-processing)
+  std::vector<cudaEvent_t> aux_ev;
+  int aux_used = 0;
+  std::vector<std::string> aux_names;
   int last_launches = 0, last_gemm_launches = 0;
   std::vector<pe::Param> params;
   std::vector<pe::Buf> bufs;
@@ -275,7 +279,27 @@ struct Runner {
     status = gemm(cd, x, wts + p.w_off, reinterpret_cast<const float*>(wts + p.b_off), nullptr, y);
   }
   void check(int s, int launches = 1) { if (status == PE_OK) status = s; d->last_launches += launches; }
-#define PE_NONGEMM(call) do { end_run(); check(call); } while (0)
+  // mode 1: event pair around a non-GEMM launch group, labelled with the launcher's name (pe_detector_profile_kernels)
+  void aux_begin(const char* call) {
+    if (!d->profiling || d->profile_runs || status != PE_OK) return;
+    while ((int)d->aux_ev.size() < d->aux_used + 2) {
+      cudaEvent_t e;
+      if (cudaEventCreate(&e) != cudaSuccess) { status = PE_ERR_CUDA; return; }
+      d->aux_ev.push_back(e);
+    }
+    const char* par = strchr(call, '(');
+    d->aux_names.emplace_back(call, par ? (size_t)(par - call) : strlen(call));
+    cudaEventRecord(d->aux_ev[d->aux_used], st);
+    aux_open = true;
+  }
+  void aux_end() {
+    if (!aux_open) return;
+    cudaEventRecord(d->aux_ev[d->aux_used + 1], st);
+    d->aux_used += 2;
+    aux_open = false;
+  }
+  bool aux_open = false;
+#define PE_NONGEMM(call) do { end_run(); aux_begin(#call); check(call); aux_end(); } while (0)
 
   // raw uint8 frames (resized on the fly) instead of a float32 tensor when frames != nullptr
   const unsigned char* frames = nullptr;
@@ -455,8 +479,10 @@ struct Runner {
       rs.nms_mask = reinterpret_cast<unsigned*>(buf("nms_mask"));
       if (status == PE_OK) {
         end_run();
+        aux_begin("launch_rpn_proposals(");
         check(launch_rpn_proposals(lv, B, c.pre_nms_topk, c.post_nms_topk, c.rpn_nms_thresh, (float)img_h, (float)img_w, rs, kMaxProps,
                                    props, prop_count, st), 4);
+        aux_end();
       }
     }
     if (!(stages & PE_STAGE_ROI_HEADS)) { end_run(); return status; }
@@ -511,6 +537,7 @@ extern "C" PE_API int pe_detector_create(const pe_detector_config* cfg, pe_detec
 
 extern "C" PE_API void pe_detector_destroy(pe_detector* d) {
   if (d) for (cudaEvent_t e : d->ev) cudaEventDestroy(e);
+  if (d) for (cudaEvent_t e : d->aux_ev) cudaEventDestroy(e);
   delete d;
 }
 
@@ -556,6 +583,21 @@ extern "C" PE_API int pe_detector_profile_launches(pe_detector* d, float* ms, do
     if (ms) ms[i] = t;
     if (flops) flops[i] = i < (int)d->prof_flops.size() ? d->prof_flops[i] : 0.0;
     if (bytes) bytes[i] = i < (int)d->prof_bytes.size() ? d->prof_bytes[i] : 0.0;
+  }
+  return n;
+}
+
+// Non-GEMM launch groups of the last mode-1 forward: launcher name (31 chars + NUL per entry) and device time.
+extern "C" PE_API int pe_detector_profile_kernels(pe_detector* d, char* names, float* ms, int capacity) {
+  if (!d) return 0;
+  const int n = d->aux_used / 2;
+  if (!d->profiling || n == 0) return 0;
+  if (cudaEventSynchronize(d->aux_ev[d->aux_used - 1]) != cudaSuccess) return 0;
+  for (int i = 0; i < n && i < capacity; ++i) {
+    float t = 0.f;
+    cudaEventElapsedTime(&t, d->aux_ev[2 * i], d->aux_ev[2 * i + 1]);
+    if (ms) ms[i] = t;
+    if (names) snprintf(names + (size_t)i * 32, 32, "%s", i < (int)d->aux_names.size() ? d->aux_names[i].c_str() : "");
   }
   return n;
 }
@@ -608,6 +650,8 @@ extern "C" PE_API int pe_detector_forward_stages(pe_detector* d, const void* wei
   if (img_h < 1 || img_w < 1 || img_h > d->cfg.canvas_h || img_w > d->cfg.canvas_w) return PE_ERR_INVALID_ARGUMENT;
   if (workspace_bytes < d->ws_bytes) return PE_ERR_WORKSPACE_TOO_SMALL;
   d->ev_used = 0;
+  d->aux_used = 0;
+  d->aux_names.clear();
   d->run_open = false;
   d->prof_flops.clear();
   d->prof_bytes.clear();
@@ -633,6 +677,8 @@ extern "C" PE_API int pe_detector_forward_frames(pe_detector* d, const void* wei
   if (img_h < 1 || img_w < 1 || img_h > d->cfg.canvas_h || img_w > d->cfg.canvas_w) return PE_ERR_INVALID_ARGUMENT;
   if (workspace_bytes < d->ws_bytes) return PE_ERR_WORKSPACE_TOO_SMALL;
   d->ev_used = 0;
+  d->aux_used = 0;
+  d->aux_names.clear();
   d->run_open = false;
   d->prof_flops.clear();
   d->prof_bytes.clear();

@@ -25,6 +25,7 @@ namespace {
 
 constexpr int kMaxBlockDets = 1024;  // cap for the block-per-image path
 constexpr int kBlockThreads = 256;
+constexpr int kMidDets = 256;        // 33..256 detections: thread-per-detection block kernel (fuse_mid_kernel)
 
 struct FuseArgs {
   const float4* boxes;
@@ -41,8 +42,8 @@ struct FuseArgs {
   float* out_scores;
   int* out_classes;
   int* out_counts;
-  int* big_count;  // workspace[0]
-  int* big_list;   // workspace[1..B]
+  int* big_count;  // workspace[0]: images with 33..kMidDets detections, workspace[1]: larger ones
+  int* big_list;   // workspace[4..4+B): medium images from the front, large images from the back
 };
 
 // ---- IoU decisions ---------------------------------------------------------------------------------
@@ -277,7 +278,8 @@ __global__ void __launch_bounds__(kBlockThreads, 4) fuse_packed_kernel(const Fus
       if (lane < nimg) {
         if (ni <= 0) a.out_counts[img0 + lane] = 0;
         else if (ni > kMaxBlockDets) a.out_counts[img0 + lane] = -1;
-        else if (ni > 32) a.big_list[atomicAdd(a.big_count, 1)] = img0 + lane;
+        else if (ni > kMidDets) a.big_list[a.B - 1 - atomicAdd(a.big_count + 1, 1)] = img0 + lane;  // large: from the back
+        else if (ni > 32) a.big_list[atomicAdd(a.big_count, 1)] = img0 + lane;                          // medium: from the front
       }
     }
     int cur = 0;
@@ -534,10 +536,10 @@ __global__ void __launch_bounds__(kBlockThreads) fuse_block_kernel(const FuseArg
 
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   const bool nms_path = a.score_mode == PE_SCORE_MAX && a.box_mode == PE_BOX_ARGMAX;
-  const int nbig = *a.big_count;
+  const int nbig = a.big_count[1];
 
   for (int bi = blockIdx.x; bi < nbig; bi += gridDim.x) {
-    const int img = a.big_list[bi];
+    const int img = a.big_list[a.B - 1 - bi];
     const int base = a.offs[(size_t)img * a.M];
     const int n = a.offs[(size_t)img * a.M + a.M] - base;
     const int W = (n + 31) >> 5;
@@ -698,6 +700,225 @@ __global__ void __launch_bounds__(kBlockThreads) fuse_block_kernel(const FuseArg
   }
 }
 
+// ---- block-per-image kernel for 33..256 detections: thread <-> detection -------------------------------------
+// The regime of the detector pipeline (100 detections per model and image).  Same decisions and the same fold order as
+// fuse_block_kernel, restructured so that nothing runs serially over the detections:
+//   * records are read once, the per-detection terms (logs, weight) are computed by the detection's own thread and everything is
+//     scattered to rank order in shared memory (28 KB static: several blocks per SM);
+//   * pair matrix: thread i evaluates partners (i + d) mod n, d = 1..n/2, so every unordered pair is evaluated once (twice for
+//     the diametrical pairs of an even n) and a match sets both symmetric bits with shared-memory atomics (matches are rare);
+//   * greedy clustering without the serial head scan: "i is a head iff no EARLIER head matches i" is iterated as a bit fixed
+//     point over all detections at once (after t rounds the first t ranks are final; real scenes settle in 2-4 rounds), the owner
+//     of a non-head is the earliest head that matches it, output position = number of earlier heads;
+//   * one thread per head folds its members (rank order, head last) from shared memory.
+template <int K>
+__global__ void __launch_bounds__(kBlockThreads) fuse_mid_kernel(const FuseArgs a) {
+  constexpr int CAP = kMidDets, WMAX = kMidDets / 32;
+  __shared__ float4 s_box[CAP], s_mbox[CAP];
+  __shared__ float s_score[CAP], s_area[CAP], s_pmax[CAP], s_lg[K + 1][CAP];
+  __shared__ double s_wgt[CAP];
+  __shared__ int s_cls[CAP], s_owner[CAP];
+  __shared__ unsigned char s_bad[CAP];
+  __shared__ unsigned s_mask[CAP][WMAX];
+  __shared__ unsigned s_head[2][WMAX];
+  __shared__ float s_red[kBlockThreads / 32];
+
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const bool nms_path = a.score_mode == PE_SCORE_MAX && a.box_mode == PE_BOX_ARGMAX;
+  const int nmid = a.big_count[0];
+
+  for (int bi = blockIdx.x; bi < nmid; bi += gridDim.x) {
+    const int img = a.big_list[bi];
+    const int base = a.offs[(size_t)img * a.M];
+    const int n = a.offs[(size_t)img * a.M + a.M] - base;
+    const int W = (n + 31) >> 5;
+    int live = 0;
+    for (int m = 0; m < a.M; ++m) live += a.offs[(size_t)img * a.M + m + 1] > a.offs[(size_t)img * a.M + m];
+    __syncthreads();  // previous image done with shared memory
+    if (live == 1) {
+      if (tid < n) {
+        a.out_boxes[base + tid] = a.boxes[base + tid];
+        a.out_scores[base + tid] = a.scores[base + tid];
+        a.out_classes[base + tid] = a.classes[base + tid];
+      }
+      if (tid == 0) a.out_counts[img] = n;
+      continue;
+    }
+    // ---- this thread's detection (input order): record, per-detection fusion terms, rank by counting
+    const bool act = tid < n;
+    float4 box = make_float4(0.f, 0.f, 0.f, 0.f);
+    float sc = -INFINITY;
+    int cls = 0;
+    DetAux<K> aux;
+    if (act) {
+      box = a.boxes[base + tid];
+      sc = a.scores[base + tid];
+      cls = a.classes[base + tid];
+      float pr[K];
+#pragma unroll
+      for (int k = 0; k < K; ++k) pr[k] = a.probs[(size_t)(base + tid) * K + k];
+      aux = make_aux<K>(pr, sc, a.vars[base + tid], a.box_mode);
+      s_area[tid] = sc;  // scores in input order (s_area is rewritten below)
+    }
+#pragma unroll
+    for (int w = 0; w < WMAX; ++w) s_mask[tid][w] = 0u;
+    __syncthreads();
+    int rank = 0;
+    if (act) {
+      for (int k = 0; k < n; ++k) {
+        const float sk = s_area[k];
+        rank += (sk > sc) || (sk == sc && (nms_path ? k < tid : k > tid));
+      }
+    }
+    float mc = act ? fmaxf(fmaxf(box.x, box.y), fmaxf(box.z, box.w)) : -INFINITY;
+    if (nms_path) {  // block max of all coordinates (torchvision batched_nms offsets)
+#pragma unroll
+      for (int s = 16; s > 0; s >>= 1) mc = fmaxf(mc, __shfl_xor_sync(kFullMask, mc, s));
+      if (lane == 0) s_red[wid] = mc;
+    }
+    __syncthreads();  // every thread has read the input-order scores
+    if (nms_path) {
+      mc = s_red[0];
+      for (int w = 1; w < kBlockThreads / 32; ++w) mc = fmaxf(mc, s_red[w]);
+    }
+    if (act) {
+      s_box[rank] = box;
+      s_score[rank] = sc;
+      s_cls[rank] = cls;
+#pragma unroll
+      for (int k = 0; k <= K; ++k) s_lg[k][rank] = aux.lg[k];
+      s_wgt[rank] = aux.wgt;
+      s_pmax[rank] = aux.pmax;
+      s_bad[rank] = aux.bad ? 1 : 0;
+      if (nms_path) {
+        const float4 ob = offset_box(box, __fmul_rn((float)cls, __fadd_rn(mc, 1.f)));
+        s_mbox[rank] = ob;
+        s_area[rank] = nms_area(ob);
+      } else {
+        s_mbox[rank] = box;
+        s_area[rank] = (box.z - box.x + 1.f) * (box.w - box.y + 1.f);
+      }
+    }
+    __syncthreads();
+    // ---- from here on thread i <-> rank i.  Pair matrix over the circle.
+    const int i = tid;
+    if (act) {
+      const float4 hb = s_mbox[i];
+      const float ha = s_area[i];
+      const int hc = s_cls[i];
+      const int half_n = n >> 1;
+      int j = i;
+      for (int d = 1; d <= half_n; ++d) {
+        j = j + 1 == n ? 0 : j + 1;
+        const bool m = nms_path ? match_nms(hb, ha, s_mbox[j], s_area[j], a.thr)
+                                : match_bayes(hb, hc, ha, s_mbox[j], s_cls[j], s_area[j], a.img_w, a.img_h, a.thr);
+        if (m) {
+          atomicOr(&s_mask[i][j >> 5], 1u << (j & 31));
+          atomicOr(&s_mask[j][i >> 5], 1u << (i & 31));
+        }
+      }
+    }
+    if (tid < WMAX) s_head[0][tid] = tid < W ? (tid == W - 1 && (n & 31) ? (1u << (n & 31)) - 1u : 0xffffffffu) : 0u;
+    __syncthreads();
+    // ---- heads: bit fixed point.  earlier[w] = bits of my row at ranks below mine
+    unsigned row[WMAX];
+#pragma unroll
+    for (int w = 0; w < WMAX; ++w) {
+      const unsigned m = s_mask[i][w];
+      row[w] = w < (i >> 5) ? m : (w == (i >> 5) ? m & ((1u << (i & 31)) - 1u) : 0u);
+    }
+    int cur = 0;
+    for (int round = 0; round <= n; ++round) {
+      unsigned hit = 0u;
+#pragma unroll
+      for (int w = 0; w < WMAX; ++w) hit |= row[w] & s_head[cur][w];
+      const bool is_head = act && hit == 0u;
+      const unsigned bal = __ballot_sync(kFullMask, is_head);
+      const bool changed = lane == 0 && bal != s_head[cur][wid];
+      if (lane == 0) s_head[cur ^ 1][wid] = bal;
+      cur ^= 1;
+      if (!__syncthreads_or(changed)) break;
+    }
+    // ---- owner of every detection, output position of every head
+    unsigned hw[WMAX];
+#pragma unroll
+    for (int w = 0; w < WMAX; ++w) hw[w] = s_head[cur][w];
+    const bool is_head = act && ((s_head[cur][i >> 5] >> (i & 31)) & 1u);
+    int pos = 0, owner = i, nheads = 0;
+#pragma unroll
+    for (int w = 0; w < WMAX; ++w) {
+      nheads += __popc(hw[w]);
+      pos += w < (i >> 5) ? __popc(hw[w]) : (w == (i >> 5) ? __popc(hw[w] & ((1u << (i & 31)) - 1u)) : 0);
+    }
+    if (act && !is_head) {
+#pragma unroll
+      for (int w = WMAX - 1; w >= 0; --w) {
+        const unsigned h = row[w] & hw[w];
+        if (h) owner = (w << 5) + __ffs(h) - 1;  // descending w: the earliest matching head wins
+      }
+    }
+    if (act) s_owner[i] = owner;
+    if (tid == 0) a.out_counts[img] = nheads;
+    __syncthreads();
+    // ---- fold: one thread per head, members in rank order, head last (the reference's order)
+    if (is_head) {
+      const float4 hbox = s_box[i];
+      const float hscore = s_score[i];
+      float fs = hscore;
+      int fc = s_cls[i];
+      float4 fb = hbox;
+      if (!nms_path) {
+        float S[K + 1];
+#pragma unroll
+        for (int k = 0; k <= K; ++k) S[k] = 0.f;
+        bool bad = false;
+        float pmax = -INFINITY;
+        double ssum = 0.0, wsum = 0.0, bx = 0.0, by = 0.0, bz = 0.0, bw = 0.0;
+        int cnt = 0;
+        bool have_best = false;
+        float4 best_box = hbox;
+        auto fold = [&](int r) {
+          const float4 ob = s_box[r];
+          const double wg = s_wgt[r];
+#pragma unroll
+          for (int k = 0; k <= K; ++k) S[k] += s_lg[k][r];
+          bad |= s_bad[r] != 0;
+          pmax = fmaxf(pmax, s_pmax[r]);
+          ssum += (double)s_score[r];
+          wsum += wg;
+          bx += wg * (double)ob.x; by += wg * (double)ob.y; bz += wg * (double)ob.z; bw += wg * (double)ob.w;
+          ++cnt;
+          if (!have_best && s_score[r] == hscore) { have_best = true; best_box = ob; }
+        };
+        for (int w = i >> 5; w < W; ++w) {
+          unsigned bits = s_mask[i][w] & ~s_head[cur][w];  // later non-heads that match me ...
+          if (w == (i >> 5)) bits &= ~((2u << (i & 31)) - 1u);
+          while (bits) {
+            const int t = __ffs(bits) - 1;
+            bits &= bits - 1u;
+            const int r = (w << 5) + t;
+            if (s_owner[r] == i) fold(r);          // ... and were not claimed by an earlier head
+          }
+        }
+        if (cnt > 0) {
+          fold(i);
+          if (a.score_mode == PE_SCORE_PROBEN) probEn_finish<K>(S, bad, &fs, &fc);
+          else if (a.score_mode == PE_SCORE_AVG) fs = (float)(ssum / (double)cnt);
+          else fs = pmax;
+          if (a.box_mode == PE_BOX_ARGMAX) fb = best_box;
+          else {
+            const double inv = 1.0 / wsum;
+            fb = make_float4((float)(bx * inv), (float)(by * inv), (float)(bz * inv), (float)(bw * inv));
+          }
+        }
+      }
+      a.out_boxes[base + pos] = fb;
+      a.out_scores[base + pos] = fs;
+      a.out_classes[base + pos] = fc;
+    }
+  }
+}
+
 constexpr size_t block_smem_bytes() {
   return (size_t)kMaxBlockDets * (2 * sizeof(float4) + 2 * sizeof(float) + 3 * sizeof(int)) +
          (size_t)kMaxBlockDets * (kMaxBlockDets / 32) * sizeof(unsigned);
@@ -705,7 +926,7 @@ constexpr size_t block_smem_bytes() {
 
 template <int K>
 int launch_fuse(const FuseArgs& a, cudaStream_t st) {
-  PE_CUDA_CHECK(cudaMemsetAsync(a.big_count, 0, sizeof(int), st));
+  PE_CUDA_CHECK(cudaMemsetAsync(a.big_count, 0, 2 * sizeof(int), st));
   const int warps_per_block = kBlockThreads / 32;
   const int sms = sm_count();
   // persistent grid: one wave of resident blocks (4 per SM at 64 registers), warps stride over the windows
@@ -724,6 +945,10 @@ int launch_fuse(const FuseArgs& a, cudaStream_t st) {
                                        (int)block_smem_bytes()));
     attr_once.mark();
   }
+  // 33..256 detections (the detector pipeline's regime): thread-per-detection kernel, several blocks per SM
+  const int grid_m = a.B < sms * 4 ? a.B : sms * 4;
+  fuse_mid_kernel<K><<<grid_m, kBlockThreads, 0, st>>>(a);
+  PE_LAUNCH_CHECK();
   const int grid_b = a.B < sms ? a.B : sms;
   fuse_block_kernel<K><<<grid_b, kBlockThreads, block_smem_bytes(), st>>>(a);
   PE_LAUNCH_CHECK();

@@ -278,6 +278,13 @@ class Detector:
         n = min(capacity, self.lib.pe_detector_profile_launches(self.handle, ms, fl, by, capacity))
         return np.array(ms[:n]), np.array(fl[:n]), np.array(by[:n])
 
+    def profile_kernels(self, capacity=64):
+        """Non-GEMM launch groups of the last forward profiled with mode 1: [(launcher name, device ms), ...]."""
+        names = ctypes.create_string_buffer(32 * capacity)
+        ms = (ctypes.c_float * capacity)()
+        n = min(capacity, self.lib.pe_detector_profile_kernels(self.handle, names, ms, capacity))
+        return [(names.raw[32 * i: 32 * i + 32].split(b"\0", 1)[0].decode(), float(ms[i])) for i in range(n)]
+
     def forward(self, batched_inputs):
         """GeneralizedRCNN.forward-compatible entry (inference only): all images must share one size."""
         imgs = torch.stack([x["image"].to(torch.float32) for x in batched_inputs]).to(self.device)

@@ -36,6 +36,20 @@ def test_cuda_matches_oracle_seeded(M, seed):
             pc.assert_same_detections(got[b], want, TOL, "M%d %s/%s img %d" % (M, sm, bm, b))
 
 
+@pytest.mark.parametrize("M,per_model", [(2, 17), (2, 100), (2, 128), (3, 43), (3, 85), (2, 129)])
+def test_block_kernels_match_oracle(M, per_model):
+    """33..256 detections per image take fuse_mid_kernel (thread per detection, bit fixed-point clustering), 257..1024 the
+    block kernel with the serial head scan: both against the oracle at the pipeline's regime (100 per model) and at the
+    boundaries of the two ranges (34, 256, 129, 255, 258 detections)."""
+    dets = synth.synth_model_detections(3, M, seed=300 + per_model, force_count=per_model)
+    images = [[synth.image_info(d, i) for d in dets] for i in range(3)]
+    for sm, bm in (("probEn", "v-avg"), ("avg", "s-avg"), ("max", "avg"), ("max", "argmax"), ("probEn", "argmax")):
+        got = fusion.late_fusion_batch((sm, bm), images)
+        for b, infos in enumerate(images):
+            want = O.late_fusion_dispatch((sm, bm), infos)
+            pc.assert_same_detections(got[b], want, TOL, "M%d n%d %s/%s img %d" % (M, per_model, sm, bm, b))
+
+
 def test_kaist_binary_form():
     """K = 1: rows [p, 1-p]; checked against the oracle's K-generic restatement."""
     rng = np.random.default_rng(9)

@@ -73,8 +73,11 @@ def test_fused_frame_resize_equals_two_step_path():
     u8 = torch.randint(0, 256, (B, 128, 160, 3), dtype=torch.uint8, generator=g).cuda()
     x = ops.resize_frames(u8, (200, 250), round_u8=True)
     a = det.forward_device(x, (128, 160), out=detector.DetectionBuffers(B, K, det.device))
+    canvas_a = det.buffer("stem_canvas")[0].clone()
     b = det.forward_frames_device(u8, (200, 250), out=detector.DetectionBuffers(B, K, det.device))
     torch.cuda.synchronize()
+    # the stem's fp16 canvas itself (tiled two-pass staging kernel vs the float path's per-pixel kernel): same bits
+    assert torch.equal(canvas_a, det.buffer("stem_canvas")[0])
     assert torch.equal(a.counts, b.counts) and int(a.counts.sum()) > 0
     assert torch.equal(a.boxes, b.boxes) and torch.equal(a.scores, b.scores) and torch.equal(a.classes, b.classes)
 
