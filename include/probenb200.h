@@ -105,6 +105,12 @@ PE_API int pe_conv2d_fwd(const pe_conv_desc* desc, const void* x, const void* w,
 PE_API int pe_conv1x1_chain_fwd(const pe_conv_desc* desc, const void* x, const void* x2, int cin2, int h2, int w2, int stride2,
                                 const void* w, const float* bias, const void* residual, void* y, const void* wc,
                                 const float* bias_c, int n_c, int relu_c, void* y_c, void* stream);
+/* RPN head in one kernel (proposal_generator/rpn.py:74-85): t = relu(conv3x3(x, w) + bias), y_c = t . wc + bias_c with wc = [16][256]
+ * bf16 (3 objectness rows | 1 zero row | 12 delta rows, the engine's kind-3 parameter) and y_c = [N, H, W, 16] float32.  The hidden
+ * tensor t exists only as bf16 sub-tiles in shared memory (the A operand of the second tcgen05 GEMM); it is never written to HBM.
+ * desc: KH = KW = 3, stride 1, Cin % 8 == 0, Cout == 256, relu as given, residual_mode 0, out_fp32 0. */
+PE_API int pe_conv_rpn_head_fwd(const pe_conv_desc* desc, const void* x, const void* w, const float* bias, const void* wc,
+                                const float* bias_c, float* y_c, void* stream);
 PE_API int pe_conv1x1_dual_fwd(const pe_conv_desc* desc, const void* x, const void* x2, int cin2, int h2, int w2, int stride2,
                                const void* w, const float* bias, void* y, void* stream);
 

@@ -33,6 +33,7 @@ class ConvDesc(ctypes.Structure):
 SIGNATURES["pe_conv2d_fwd"] = (c_int, [ctypes.POINTER(ConvDesc)] + [c_void_p] * 6)
 SIGNATURES["pe_conv1x1_chain_fwd"] = (c_int, [ctypes.POINTER(ConvDesc), c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p,
                                                c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p])
+SIGNATURES["pe_conv_rpn_head_fwd"] = (c_int, [ctypes.POINTER(ConvDesc)] + [c_void_p] * 7)
 SIGNATURES["pe_conv1x1_dual_fwd"] = (c_int, [ctypes.POINTER(ConvDesc), c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p,
                                               c_void_p, c_void_p])
 

@@ -57,7 +57,9 @@ struct ConvSecondInput { const void* x; int Cin, H, W, stride; };
 // optional chained 1x1 conv on the layer's own output tile: y2 = act(y . w2 + bias2), w2 = [N][Cout] bf16, y2 = [.., N] bf16
 // (a bottleneck's conv3 followed by the NEXT block's conv1, resnet.py:205-221, in one kernel)
 // bn: main tile width, 256 (one main accumulator stage) | 128 (two stages, deferred chained GEMM / epilogue) | 0 = default
-struct ConvChain { const void* w; const float* bias; void* y; int N; int relu; int bn; };
+// out_fp32: narrow fp32 chain (N = 16, y2 = [.., 16] fp32; the RPN head's objectness | deltas on top of its 3x3 conv): the main
+// output y is NOT stored
+struct ConvChain { const void* w; const float* bias; void* y; int N; int relu; int bn; int out_fp32; };
 int conv2d_launch(const pe_conv_desc& d, const void* x, const void* w, const float* bias, const void* residual, void* y,
                   cudaStream_t st, const ConvSecondInput* x2 = nullptr, int reverse = 0, const ConvChain* chain = nullptr);
 

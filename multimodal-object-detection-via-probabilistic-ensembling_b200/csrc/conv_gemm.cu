@@ -55,6 +55,13 @@ struct ConvArgs {
   int chain_relu;
   int b2_stages;      // ring depth of the chained weight chunks ([chain_n x 64] bf16 each)
   const float* chain_bias;
+  // narrow fp32 chain (RPN head: 3x3 conv + ReLU -> objectness | deltas, rpn.py:74-85): chain_n = 16, the chained output goes
+  // straight to chain_out [pixels][16] fp32, the MAIN output is never stored (nobody else reads the hidden tensor), the chained
+  // weights stay resident, the chained accumulator ALIASES the first columns of the tile's own main TMEM stage (free once the
+  // epilogue has staged sub-tile 0), and the MMA warp issues the chained MMAs of tile i opportunistically between the
+  // k-iterations of tile i + 1 - both main stages stay available and the mainloop never waits for an epilogue.
+  int chain_fp32;
+  float* chain_out;
   int reverse;   // walk the tiles from the last to the first: consecutive layers alternate direction, so a layer starts with
                  // the part of its input that the previous layer wrote last and that is still in the 126 MB L2
   int k_chunks1; // dual-input 1x1 (bottleneck conv3 + projection shortcut as ONE GEMM over K = [t2 | x]): chunks [0, k_chunks1) come
@@ -232,6 +239,12 @@ __device__ __forceinline__ void tmem_ld_32x32b_x16(uint32_t taddr, uint32_t* v) 
       : "r"(taddr)
       : "memory");
 }
+__device__ __forceinline__ void tmem_ld_32x32b_x8(uint32_t taddr, uint32_t* v) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
+               : "r"(taddr)
+               : "memory");
+}
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 template <int kCols>
@@ -315,7 +328,8 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
   // issued AFTER the mainloop of tile i + 1 (so the mainloop overlaps tile i's epilogue as usual) and the chained epilogue of
   // an m-tile group after the first epilogue of the following tile ("deferred" order, same for every role).
   const bool defer = chain && BLOCK_N == 128;
-  const int n_acc = (chain && !defer) ? 1 : 2;
+  const bool rpn = chain && BLOCK_N == 256 && a.chain_fp32 != 0;  // narrow fp32 chain, see ConvArgs::chain_fp32
+  const int n_acc = (chain && !defer && !rpn) ? 1 : 2;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int tiles_m = a.N * a.tiles_h * a.tiles_w;
@@ -326,9 +340,9 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
     tma_prefetch_desc(&map_a);
     tma_prefetch_desc(&map_b);
     if (a.k_chunks1 < a.k_chunks) tma_prefetch_desc(&map_a2);
-    if (a.chain_n) { tma_prefetch_desc(&map_b2); tma_prefetch_desc(&map_out2); }
+    if (a.chain_n) { tma_prefetch_desc(&map_b2); if (!a.chain_fp32) tma_prefetch_desc(&map_out2); }
     if (kStaged) {
-      tma_prefetch_desc(&map_out);
+      if (!a.chain_fp32) tma_prefetch_desc(&map_out);
       if (a.residual_mode) tma_prefetch_desc(&map_res);
     }
   }
@@ -450,6 +464,12 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
         }
         continue;
       }
+      if (rpn && first && leader) {  // the whole chained weight matrix [16][Cout] stays resident: one chunk per 64 main channels
+        for (int s2 = 0; s2 < kSubMain; ++s2) {
+          mbar_expect_tx(&b2_full[s2], (uint32_t)b2_bytes);
+          tma_load_2d(&map_b2, &b2_full[s2], b2_stage + s2 * b2_bytes, s2 * 64, 0);
+        }
+      }
       for (int kh = 0; kh < a.KH; ++kh)
         for (int kw = 0; kw < a.KW; ++kw)
           for (int kc = 0; kc < a.k_chunks; ++kc) {
@@ -476,7 +496,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
           if (++bs == a.b2_stages) { bs = 0; bphase ^= 1; }
         }
       };
-      if (chain && !defer) load_b2(n0);
+      if (chain && !defer && !rpn) load_b2(n0);
       if (defer) {
         if (it >= 1) load_b2(prev_n0);
         prev_n0 = n0;
@@ -498,8 +518,35 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
     const int n_cacc = a.chain_n <= 128 ? 2 : 1;
     int cp = 0, bs = 0, cs = 0, prev_p = 0;
     uint32_t cpar = 0, bphase = 0, cphase = 0, prev_par = 0;
+    // narrow fp32 chain (rpn): running count of chained sub-tile GEMMs issued (sub-tile g belongs to tile g / kSubMain of this
+    // CTA and sits in staging buffer g % io_bufs), issued as soon as the epilogue has staged the sub-tile
+    int rpn_issued = 0, rpn_p = 0, n_done = 0;
+    uint32_t rpn_par = 0;
+    auto rpn_step = [&](bool blocking) -> bool {
+      if (blocking) mbar_wait(&io_written[rpn_p], rpn_par);
+      else if (!__all_sync(0xffffffffu, mbar_try_wait(&io_written[rpn_p], rpn_par))) return false;
+      constexpr int kSubDiv = kSubMain > 0 ? kSubMain : 1;  // (narrow instantiations never take this path)
+      const int t = rpn_issued / kSubDiv, s2 = rpn_issued - t * kSubDiv;
+      mbar_wait(&b2_full[s2], 0);  // resident weights: completes once
+      tc_fence_after();
+      if (leader) {
+        const uint32_t d2 = tmem_base + (uint32_t)((t & 1) * BLOCK_N);  // columns [0, chain_n) of the tile's own main stage
+        const uint64_t da = umma_smem_desc(smem_u32(io_stage + rpn_p * kIoBytes));
+        const uint64_t db = umma_smem_desc(smem_u32(b2_stage + s2 * b2_bytes));
+#pragma unroll
+        for (int k = 0; k < kBlockK / kUmmaK; ++k)
+          umma_bf16(d2, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc2, (s2 | k) != 0);
+        umma_commit(&chain_read[rpn_p]);  // the io warp may hand the buffer to the next sub-tile
+        if (s2 == kSubMain - 1) umma_commit(&chain_full[t & 1]);
+      }
+      ++rpn_issued;
+      if (++rpn_p == a.io_bufs) { rpn_p = 0; rpn_par ^= 1; }
+      return true;
+    };
     for (int it = 0, tile; (tile = tile_at(it)) >= 0; ++it) {
       const bool first = it == 0;
+      // the stage this tile needs was used by tile it - 2 and is released by ITS chained epilogue: all its chained GEMMs must be out
+      if (rpn) while (rpn_issued < kSubMain * (it - 1)) rpn_step(true);
       mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
       tc_fence_after();
       const uint32_t d_tmem = tmem_base + acc * BLOCK_N;
@@ -575,6 +622,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
       }
       const bool sw64 = a.stem_mode == 1;
       for (int ki = 0; ki < k_iters; ++ki) {
+        if (rpn && rpn_issued < kSubMain * it) rpn_step(false);  // a staged sub-tile of the previous tile, if one is ready
         mbar_wait(&full_bar[stage], phase);
         tc_fence_after();
         if (leader) {
@@ -592,6 +640,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
         if (++stage == n_stages) { stage = 0; phase ^= 1; }
       }
       if (++acc == n_acc) { acc = 0; acc_phase ^= 1; }
+      n_done = it + 1;
       // ---- chained GEMM: acc2 += staged out sub-tiles (A, in place) x W2 chunks; t = the tile whose sub-tiles are consumed,
       //      (p0, par0) = staging-buffer cursor at its first sub-tile
       auto chain_part = [&](int t, int p0, uint32_t par0) {
@@ -623,7 +672,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
         }
       };
       auto advance = [&](int n) { for (int i = 0; i < n; ++i) if (++cp == a.io_bufs) { cp = 0; cpar ^= 1; } };
-      if (chain) {
+      if (chain && !rpn) {
         const int p_main = cp;                        // cursor at this tile's first main sub-tile
         const uint32_t par_main = cpar;
         advance(kSubMain);
@@ -637,6 +686,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
         }
       }
     }
+    if (rpn) while (rpn_issued < kSubMain * n_done) rpn_step(true);  // the last tile's (and any left-over) chained GEMMs
   } else if (kStaged && warp == 3) {
     // ================================ io warp (staged epilogue) ================================
     // Owns the 16 KB staging buffers: hands them to the epilogue warps (io_ready: free, or - on residual layers -
@@ -647,6 +697,20 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
     const bool leader = elect_one();
     const int rmode = a.residual_mode;
     const int R = a.io_bufs;
+    if (rpn) {  // nothing is stored: a staging buffer goes back to the epilogue as soon as the chained MMA has read it
+      int n_tiles = 0;
+      while (tile_at(n_tiles) >= 0) ++n_tiles;
+      const int total = n_tiles * kSubMain;
+      for (int i = 0; i < R && i < total; ++i)
+        if (leader) mbar_arrive(&io_ready[i]);
+      int p = 0;
+      uint32_t par = 0;
+      for (int g = 0; g + R < total; ++g) {
+        mbar_wait(&chain_read[p], par);
+        if (leader) mbar_arrive(&io_ready[p]);
+        if (++p == R) { p = 0; par ^= 1; }
+      }
+    } else {
     const uint32_t res_bytes = rmode == 2 ? kCoarseBytes : kIoBytes;
     auto sub_count = [&](int n0) { const int left = (a.Cout - n0) >> 6; return left < kSubMain ? left : kSubMain; };
     // ---- cursor of the next sub-tile to be made ready
@@ -729,6 +793,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
     if (defer && n_its > 0)
       for (int c2 = 0; c2 < nsub2; ++c2) store_one(&map_out2, c2 * 64, pw0, ph0, pimg, true);
     if (leader) tma_store_wait_all();
+    }
   } else if (warp >= kEpilogueWarp0) {
     // ================================ epilogue ================================
     // warps 4-7 and 8-11: warp w may only touch TMEM lanes [32 * (w % 4), +32); the two warps of a lane quarter split
@@ -807,6 +872,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
           *slot = make_uint4(pack_bf16(f[0], f[1]), pack_bf16(f[2], f[3]), pack_bf16(f[4], f[5]), pack_bf16(f[6], f[7]));
         }
         fence_proxy_async();            // make the generic-proxy row writes visible to the TMA store (and the chained MMA)
+        if (rpn) tc_fence_before();     // ... and order this thread's TMEM reads before the chained MMA that overwrites the columns
         mbar_arrive(&io_written[p]);    // 256 arrivals release the buffer to the io warp
         if (++p == R) { p = 0; par ^= 1; }
       };
@@ -819,6 +885,40 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
                    c2 == 0 ? &chain_full[cs] : nullptr, cphase, c2 == nsub2 - 1 ? &chain_empty[cs] : nullptr);
         if (++cs == n_cacc) { cs = 0; cphase ^= 1; }
       };
+      // narrow fp32 chain: this thread's pixel x 8 of the 16 chained outputs (half 0: objectness | pad, half 1... columns 8-15)
+      // from the first columns of the tile's main stage -> + bias -> fp32 row of chain_out; then the stage goes back to the MMA warp
+      auto rpn_epilogue = [&](int tile, int acc_s, uint32_t par_s) {
+        int nt, tw, th, img;
+        decompose(tile, nt, tw, th, img);
+        const int h = th * a.TH + ph, w = tw * a.TW + pw;
+        float4 b0 = make_float4(0.f, 0.f, 0.f, 0.f), b1 = b0;
+        if (a.chain_bias) {
+          b0 = __ldg(reinterpret_cast<const float4*>(a.chain_bias + half * 8));
+          b1 = __ldg(reinterpret_cast<const float4*>(a.chain_bias + half * 8 + 4));
+        }
+        mbar_wait(&chain_full[acc_s], par_s);
+        tc_fence_after();
+        uint32_t v[8];
+        tmem_ld_32x32b_x8(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc_s * BLOCK_N + half * 8), v);
+        tmem_ld_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tmem_empty[acc_s]);
+        if (h < a.Ho && w < a.Wo) {
+          float f[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) f[i] = __uint_as_float(v[i]);
+          f[0] += b0.x; f[1] += b0.y; f[2] += b0.z; f[3] += b0.w;
+          f[4] += b1.x; f[5] += b1.y; f[6] += b1.z; f[7] += b1.w;
+          if (a.chain_relu) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) f[i] = fmaxf(f[i], 0.f);
+          }
+          float4* op = reinterpret_cast<float4*>(a.chain_out + (((size_t)img * a.Ho + h) * a.Wo + w) * 16 + half * 8);
+          op[0] = make_float4(f[0], f[1], f[2], f[3]);
+          op[1] = make_float4(f[4], f[5], f[6], f[7]);
+        }
+      };
       for (int it = 0, tile; (tile = tile_at(it)) >= 0; ++it) {
         const int ptile = a.reverse ? num_tiles - 1 - tile : tile;
         const int n0 = (ptile - (int)fast_div((uint32_t)ptile, a.mul_tiles_n) * a.tiles_n) * BLOCK_N;
@@ -826,9 +926,10 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
         const int nsub = left < kSubMain ? left : kSubMain;
         for (int s2 = 0; s2 < nsub; ++s2)
           sub_tile((uint32_t)(acc * BLOCK_N + s2 * 64), a.bias ? a.bias + n0 + s2 * 64 : nullptr, rmode, a.relu,
-                   s2 == 0 ? &tmem_full[acc] : nullptr, acc_phase, s2 == nsub - 1 ? &tmem_empty[acc] : nullptr);
+                   s2 == 0 ? &tmem_full[acc] : nullptr, acc_phase, (s2 == nsub - 1 && !rpn) ? &tmem_empty[acc] : nullptr);
+        if (rpn) rpn_epilogue(tile, acc, acc_phase);  // waits for the chained GEMMs the MMA warp issues during the next mainloop
         if (++acc == n_acc) { acc = 0; acc_phase ^= 1; }
-        if (chain_after(it)) chained_epilogue();  // an m-tile group is complete (deferred order: the one before this tile)
+        if (!rpn && chain_after(it)) chained_epilogue();  // an m-tile group is complete (deferred order: the one before this tile)
         n_its = it + 1;
       }
       if (defer && n_its > 0) chained_epilogue();
@@ -999,7 +1100,9 @@ int launch_conv(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap&
 int conv2d_launch(const pe_conv_desc& d, const void* x, const void* w, const float* bias, const void* residual, void* y,
                   cudaStream_t st, const ConvSecondInput* x2, int reverse, const ConvChain* ch) {
   if (ch && ch->w) {  // chained 1x1 on this layer's output tile (see ConvArgs::chain_n)
-    if (d.out_fp32 || d.Cout % 256 || d.residual_mode == 2 || d.KH != 1 || (ch->N != 64 && ch->N != 128 && ch->N != 256) || !ch->y)
+    if (ch->out_fp32) {  // narrow fp32 chain: one 256-wide n tile, no residual, 16 chained outputs
+      if (d.out_fp32 || d.Cout != 256 || d.residual_mode || ch->N != 16 || !ch->y || d.stride != 1) return PE_ERR_UNSUPPORTED;
+    } else if (d.out_fp32 || d.Cout % 256 || d.residual_mode == 2 || d.KH != 1 || (ch->N != 64 && ch->N != 128 && ch->N != 256) || !ch->y)
       return PE_ERR_UNSUPPORTED;
     if (ch->bn != 0 && ch->bn != 128 && ch->bn != 256) return PE_ERR_INVALID_ARGUMENT;
   }
@@ -1011,7 +1114,7 @@ int conv2d_launch(const pe_conv_desc& d, const void* x, const void* w, const flo
   if (!((d.KH == 1 && d.KW == 1) || (d.KH == 3 && d.KW == 3))) return PE_ERR_UNSUPPORTED;
   if (d.stride != 1 && !(d.stride == 2 && d.KH == 1)) return PE_ERR_UNSUPPORTED;
   if (d.residual_mode < 0 || d.residual_mode > 2 || (d.residual_mode && !residual)) return PE_ERR_INVALID_ARGUMENT;
-  if (!x || !w || !y) return PE_ERR_INVALID_ARGUMENT;
+  if (!x || !w || (!y && !(ch && ch->w && ch->out_fp32))) return PE_ERR_INVALID_ARGUMENT;  // the narrow fp32 chain stores no main output
   ConvArgs a = {};
   a.N = d.N;
   a.Ho = d.stride == 2 ? (d.H - 1) / 2 + 1 : d.H;
@@ -1038,7 +1141,7 @@ int conv2d_launch(const pe_conv_desc& d, const void* x, const void* w, const flo
   int bn = d.Cout >= 256 ? 256 : (d.Cout >= 128 ? 128 : (d.Cout >= 64 ? 64 : (d.Cout > 16 ? 32 : 16)));
   // chained layers: 128-wide main tiles keep two accumulator stages (deferred order, see the kernel); PE_CONV_CHAIN_BN overrides
   static const int chain_bn_env = [] { const char* e = getenv("PE_CONV_CHAIN_BN"); return e ? atoi(e) : 256; }();
-  if (ch && ch->w && (ch->bn ? ch->bn : chain_bn_env) == 128) bn = 128;
+  if (ch && ch->w && !ch->out_fp32 && (ch->bn ? ch->bn : chain_bn_env) == 128) bn = 128;
   a.tiles_n = ceil_div(d.Cout, bn);
   a.k_chunks = ceil_div(d.Cin, kBlockK);  // a ragged last chunk is zero-filled by TMA (A and W alike)
   a.k_chunks1 = a.k_chunks;
@@ -1047,6 +1150,8 @@ int conv2d_launch(const pe_conv_desc& d, const void* x, const void* w, const flo
   a.chain_n = chained ? ch->N : 0;
   a.chain_relu = chained ? ch->relu : 0;
   a.chain_bias = chained ? ch->bias : nullptr;
+  a.chain_fp32 = chained && ch->out_fp32 ? 1 : 0;
+  a.chain_out = a.chain_fp32 ? reinterpret_cast<float*>(ch->y) : nullptr;
   a.b2_stages = 0;
   const bool dual = x2 && x2->x;
   if (dual) a.k_chunks += ceil_div(x2->Cin, kBlockK);
@@ -1090,7 +1195,7 @@ int conv2d_launch(const pe_conv_desc& d, const void* x, const void* w, const flo
   const bool staged = !d.out_fp32 && bn >= 64 && d.Cout % 64 == 0;
   CUtensorMap mo = ma, mr = ma;
   if (!dual) ma2 = ma;
-  if (staged) {
+  if (staged && !a.chain_fp32) {
     cuuint64_t dims[4] = {(cuuint64_t)d.Cout, (cuuint64_t)a.Wo, (cuuint64_t)a.Ho, (cuuint64_t)d.N};
     cuuint64_t strides[3] = {(cuuint64_t)d.Cout * 2, (cuuint64_t)a.Wo * d.Cout * 2, (cuuint64_t)a.Ho * a.Wo * d.Cout * 2};
     cuuint32_t box[4] = {64, (cuuint32_t)a.TW, (cuuint32_t)a.TH, 1};
@@ -1113,7 +1218,8 @@ int conv2d_launch(const pe_conv_desc& d, const void* x, const void* w, const flo
     cuuint64_t od[4] = {(cuuint64_t)ch->N, (cuuint64_t)a.Wo, (cuuint64_t)a.Ho, (cuuint64_t)d.N};
     cuuint64_t os[3] = {(cuuint64_t)ch->N * 2, (cuuint64_t)a.Wo * ch->N * 2, (cuuint64_t)a.Ho * a.Wo * ch->N * 2};
     cuuint32_t ob[4] = {64, (cuuint32_t)a.TW, (cuuint32_t)a.TH, 1};
-    if (!make_map(&mo2, ch->y, 4, od, os, ob)) return PE_ERR_CUDA;
+    if (ch->out_fp32) mo2 = mb2;  // written with plain stores
+    else if (!make_map(&mo2, ch->y, 4, od, os, ob)) return PE_ERR_CUDA;
   }
   {  // split the smem budget: short K loops need few operand stages and profit from a deep residual/store queue
     const int stage_bytes = kBlockM * kBlockK * 2 + bn * kBlockK * 2;
@@ -1136,15 +1242,23 @@ int conv2d_launch(const pe_conv_desc& d, const void* x, const void* w, const flo
       }
       const int io_bytes = kIoBytes + (d.residual_mode == 2 ? kCoarseBytes : 0);
       int b2_total = 0;
-      if (chained) {  // chained weight ring: [N2 x 64] bf16 chunks; the operand pipeline gives way (these layers are HBM-bound)
+      if (chained && ch->out_fp32) {  // resident chained weights (4 x 2 KB); the long-K mainloop keeps its operand stages and the
+        // staging buffers take what is left (1 with 4 stages: a sub-tile is consumed by the chained MMA before the next is staged)
+        static const int rpn_stages = [] { const char* e = getenv("PE_RPN_CHAIN_STAGES"); return e ? atoi(e) : 4; }();
+        a.b2_stages = 4;
+        b2_total = a.b2_stages * ch->N * 128;
+        st_want = rpn_stages < 2 ? 2 : (rpn_stages > max_stages ? max_stages : rpn_stages);
+        if (k_iters + 1 < st_want) st_want = k_iters + 1 < 2 ? 2 : k_iters + 1;
+      } else if (chained) {  // chained weight ring: [N2 x 64] bf16 chunks; the operand pipeline gives way (these layers are HBM-bound)
         a.b2_stages = ch->N <= 64 ? 4 : (ch->N <= 128 ? (bn == 128 ? 4 : 3) : 2);
         b2_total = a.b2_stages * ch->N * 128;
         if (st_want > 2) st_want = 2;
       }
       int io = (budget - b2_total - st_want * stage_bytes) / io_bytes;
       if (io > kMaxIoBufs) io = kMaxIoBufs;
-      if (io < 2) { io = 2; st_want = (budget - b2_total - 2 * io_bytes) / stage_bytes; }
-      if (chained && (io < 3 || st_want < 2)) return PE_ERR_UNSUPPORTED;
+      if (io < 2 && !(chained && ch->out_fp32)) { io = 2; st_want = (budget - b2_total - 2 * io_bytes) / stage_bytes; }
+      if (chained && !ch->out_fp32 && (io < 3 || st_want < 2)) return PE_ERR_UNSUPPORTED;
+      if (chained && ch->out_fp32 && (io < 1 || st_want < 2)) return PE_ERR_UNSUPPORTED;
       a.stages = st_want;
       a.io_bufs = io;
       if (halo) {
@@ -1258,6 +1372,13 @@ extern "C" PE_API int pe_conv1x1_chain_fwd(const pe_conv_desc* desc, const void*
   pe::ConvSecondInput s2 = {x2, cin2, h2, w2s, stride2};
   pe::ConvChain ch = {wc, bias_c, y_c, n_c, relu_c, 0};
   return pe::conv2d_launch(*desc, x, w, bias, residual, y, reinterpret_cast<cudaStream_t>(stream), x2 ? &s2 : nullptr, 0, &ch);
+}
+
+extern "C" PE_API int pe_conv_rpn_head_fwd(const pe_conv_desc* desc, const void* x, const void* w, const float* bias, const void* wc,
+                                           const float* bias_c, float* y_c, void* stream) {
+  if (!desc || !wc || !y_c) return PE_ERR_INVALID_ARGUMENT;
+  pe::ConvChain ch = {wc, bias_c, y_c, 16, 0, 0, 1};
+  return pe::conv2d_launch(*desc, x, w, bias, nullptr, nullptr, reinterpret_cast<cudaStream_t>(stream), nullptr, 0, &ch);
 }
 
 extern "C" PE_API int pe_conv1x1_dual_fwd(const pe_conv_desc* desc, const void* x, const void* x2, int cin2, int h2, int w2, int stride2,

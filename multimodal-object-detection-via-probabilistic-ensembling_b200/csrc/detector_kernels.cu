@@ -987,7 +987,11 @@ __global__ void __launch_bounds__(224, kMinBlocks) roi_align_kernel(const RoiLev
         for (int p2 = 0; p2 < 7; ++p2) nymax = max(nymax, s_ny[p2]);
         const uint4* col = reinterpret_cast<const uint4*>(feat + ((size_t)y0 * W + xs) * C);
         uint4* dst = dst_roi + (size_t)(ph * 7) * cgroups;
-        if (nymax <= 4) roi_fast_sweep<4>(col, dst, s_col, ncols, cgroups, (size_t)W * cgroups, ny, wy, inv_count, lane);
+        // NR = the block's tallest bin row: rows beyond a warp's own ny are zero-weight re-reads of row 0, so every NR above
+        // the need costs a load + unpack + FMA group per pixel column (3- and 5-row bins are the common case at 14 / 28 px)
+        if (nymax <= 3) roi_fast_sweep<3>(col, dst, s_col, ncols, cgroups, (size_t)W * cgroups, ny, wy, inv_count, lane);
+        else if (nymax <= 4) roi_fast_sweep<4>(col, dst, s_col, ncols, cgroups, (size_t)W * cgroups, ny, wy, inv_count, lane);
+        else if (nymax <= 5) roi_fast_sweep<5>(col, dst, s_col, ncols, cgroups, (size_t)W * cgroups, ny, wy, inv_count, lane);
         else roi_fast_sweep<6>(col, dst, s_col, ncols, cgroups, (size_t)W * cgroups, ny, wy, inv_count, lane);
         return;
       }

@@ -224,7 +224,8 @@ struct Runner {
       double flops = 2.0 * opix * cd.Cout * taps;
       if (chain) {  // + the chained 1x1 (the next block's conv1): its weights and its output; its input never leaves the SM
         flops += 2.0 * opix * cd.Cout * chain->N;
-        bytes += (double)chain->N * cd.Cout * 2 + chain->N * 4.0 + opix * chain->N * 2;
+        bytes += (double)chain->N * cd.Cout * 2 + chain->N * 4.0 + opix * chain->N * (chain->out_fp32 ? 4 : 2);
+        if (chain->out_fp32) bytes -= opix * cd.Cout * 2;  // the RPN head's hidden tensor is not stored at all
       }
       if (e0) {
         d->prof_flops.push_back(flops);
@@ -453,8 +454,23 @@ struct Runner {
       for (int l = 2; l <= 6; ++l) {
         char q[16];
         snprintf(q, sizeof(q), "rpn_out%d", l);
-        conv("proposal_generator.rpn_head.conv", level_feat(l), d->H[l - 1], d->W[l - 1], 1, true, 0, nullptr, buf("rpn_t"));
-        conv("proposal_generator.rpn_head", buf("rpn_t"), d->H[l - 1], d->W[l - 1], 1, false, 0, nullptr, buf(q), true);
+        // 3x3 + ReLU and objectness | deltas as ONE kernel: the 256-channel hidden tensor stays in shared memory as the A operand of
+        // the chained 16-wide GEMM (conv_gemm.cu ConvArgs::chain_fp32); PE_RPN_CHAIN=0 runs the two layers separately (A/B switch)
+        static const int rpn_chain = [] { const char* e = getenv("PE_RPN_CHAIN"); return e ? atoi(e) : 1; }();
+        if (rpn_chain && d->fc == 256) {
+          if (status == PE_OK) {
+            const Param& p3 = d->params[d->find_param("proposal_generator.rpn_head.conv")];
+            const Param& p1 = d->params[d->find_param("proposal_generator.rpn_head")];
+            pe_conv_desc cd;
+            cd.N = B; cd.H = d->H[l - 1]; cd.W = d->W[l - 1]; cd.Cin = p3.Cin; cd.Cout = p3.Cout; cd.KH = 3; cd.KW = 3; cd.stride = 1;
+            cd.relu = 1; cd.residual_mode = 0; cd.out_fp32 = 0; cd.in_fp16 = 0;
+            ConvChain ch = {wts + p1.w_off, reinterpret_cast<const float*>(wts + p1.b_off), buf(q), 16, 0, 0, 1};
+            status = gemm(cd, level_feat(l), wts + p3.w_off, reinterpret_cast<const float*>(wts + p3.b_off), nullptr, nullptr, nullptr, &ch);
+          }
+        } else {
+          conv("proposal_generator.rpn_head.conv", level_feat(l), d->H[l - 1], d->W[l - 1], 1, true, 0, nullptr, buf("rpn_t"));
+          conv("proposal_generator.rpn_head", buf("rpn_t"), d->H[l - 1], d->W[l - 1], 1, false, 0, nullptr, buf(q), true);
+        }
         lv.out[l - 2] = reinterpret_cast<const float*>(buf(q));
         lv.H[l - 2] = d->H[l - 1];
         lv.W[l - 2] = d->W[l - 1];

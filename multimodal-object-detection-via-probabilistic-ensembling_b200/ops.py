@@ -66,6 +66,20 @@ def conv1x1_chain_nhwc(x, w, bias, wc, bias_c, residual=None, x2=None, stride2=1
     return y, yc
 
 
+def conv_rpn_head_nhwc(x, w, bias, wc, bias_c, relu=True):
+    """``pe_conv_rpn_head_fwd``: y_c = relu(conv3x3(x, w) + bias) . wc + bias_c, x [N,H,W,Cin] bf16, w [256,3,3,Cin] bf16,
+    wc [16,256] bf16 -> y_c [N,H,W,16] float32; the hidden 256-channel tensor never leaves the SM (rpn.py:74-85)."""
+    lib = _lib.load()
+    _lib.require_cuda(x, w, bias, wc, bias_c)
+    N, H, W, Cin = x.shape
+    yc = torch.empty((N, H, W, 16), dtype=torch.float32, device=x.device)
+    d = _lib.ConvDesc(N, H, W, Cin, w.shape[0], 3, 3, 1, int(relu), 0, 0, 0)
+    st = lib.pe_conv_rpn_head_fwd(ctypes.byref(d), _lib.ptr(x), _lib.ptr(w), _lib.ptr(bias), _lib.ptr(wc), _lib.ptr(bias_c), _lib.ptr(yc),
+                                  _lib.current_stream_ptr(x.device))
+    _lib.check(st, "pe_conv_rpn_head_fwd")
+    return yc
+
+
 def linear(x, w, bias=None, relu=False, out_fp32=False):
     """x [M,K] bf16, w [N,K] bf16 -> [M,N]; the H=1 case of the conv kernel."""
     M, K = x.shape

@@ -138,3 +138,35 @@ def test_chained_1x1_equals_conv3_then_next_conv1(case):
     want_c = ref_conv(y, wc, bc, None, 1, True, 0)   # the chained conv sees the bf16 output, like a separate launch would
     err_c = (yc.float() - want_c).abs()
     assert bool((err_c <= 2e-3 + want_c.abs() * 2 ** -8).all()), "chained output: max err %g" % float(err_c.max())
+
+
+@pytest.mark.parametrize("case", [
+    # N, H, W, Cin
+    (2, 13, 16, 256),     # p6-like: one ragged tile per CTA (only the final drain of the chained GEMMs)
+    (2, 50, 64, 256),     # one tile per CTA
+    (4, 100, 128, 256),   # 400 tiles on 148 CTAs: chained GEMMs issued between the k-iterations of the next tile, both TMEM stages
+    (16, 50, 64, 256),    # same with batch 16 (tile decomposition over images)
+    (1, 200, 256, 64),    # short K (9 k-iterations per tile)
+])
+def test_rpn_head_single_kernel(case):
+    """3x3 conv + ReLU -> objectness | deltas (16 fp32 outputs) in ONE kernel (the hidden tensor never leaves the SM) against
+    (a) the two separate launches the engine used before - the chained GEMM consumes the same bf16-rounded hidden tile with the
+    same K order, so the results must agree to fp32 accumulation noise - and (b) the fp32 reference of the two ops."""
+    N, H, W, Cin = case
+    g = torch.Generator(device="cuda").manual_seed(sum(case))
+    x = torch.randn(N, H, W, Cin, device="cuda", generator=g).bfloat16()
+    w = (torch.randn(256, 3, 3, Cin, device="cuda", generator=g) / (9 * Cin) ** 0.5).bfloat16()
+    b = torch.randn(256, device="cuda", generator=g)
+    wc = (torch.randn(16, 1, 1, 256, device="cuda", generator=g) / 16.0).bfloat16()
+    bc = torch.randn(16, device="cuda", generator=g)
+    t = ops.conv2d_nhwc(x, w, b, None, 1, True, 0, False)
+    two_step = ops.conv2d_nhwc(t, wc, bc, None, 1, False, 0, True)
+    for _ in range(2):  # twice: the second launch starts from warm TMEM / smem state
+        got = ops.conv_rpn_head_nhwc(x, w, b, wc.view(16, 256).contiguous(), bc)
+        torch.cuda.synchronize()
+        assert got.shape == two_step.shape and got.dtype == torch.float32
+        d = (got - two_step).abs()
+        assert bool((d <= 1e-5 + two_step.abs() * 1e-5).all()), "vs separate launches: max diff %g" % float(d.max())
+    want = ref_conv(t, wc, bc, None, 1, False, 0)
+    err = (got - want).abs()
+    assert bool((err <= 2e-3 + want.abs() * 2 ** -8).all()), "vs fp32 reference: max err %g" % float(err.max())
