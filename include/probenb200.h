@@ -190,6 +190,11 @@ PE_API int pe_detector_forward_frames(pe_detector* d, const void* weights, const
  * enabled = 2: one event pair around every RUN of back-to-back GEMM launches (no event in between, so the launch gaps and the
  * programmatic-dependent-launch overlap of consecutive layers count exactly as in a real forward); 0 = off. */
 PE_API int pe_detector_set_profiling(pe_detector* d, int enabled);
+/* Cross-detector stagger: every following forward records `event` (a cudaEvent_t; NULL switches it off) on its stream once
+ * `after_launches` kernels have been launched (at the latest when the forward ends).  A second detector whose stream waits for
+ * that event starts that much later, so the latency-bound stages of the two (RPN top-k / NMS, a few CTAs each) do not coincide
+ * and each runs under the other one's GEMMs.  Works under stream capture (the record / wait pair becomes a graph edge). */
+PE_API int pe_detector_set_stagger_event(pe_detector* d, void* event, int after_launches);
 PE_API int pe_detector_last_profile(pe_detector* d, float* gemm_ms, float* span_ms, int* launches, int* gemm_launches);
 /* Per GEMM launch of the last profiled forward: device ms, algorithmic FLOPs, algorithmic bytes (every operand once).
  * Fills at most `capacity` entries; returns the number of launches recorded (0 when profiling is off). */

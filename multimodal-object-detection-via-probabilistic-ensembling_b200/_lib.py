@@ -73,6 +73,7 @@ SIGNATURES.update({
                                            ctypes.POINTER(Detections), c_void_p, c_size_t, c_void_p]),
     "pe_pack_detections": (c_int, [ctypes.POINTER(Detections), c_int, c_int, c_int] + [c_void_p] * 7),
     "pe_detector_set_profiling": (c_int, [c_void_p, c_int]),
+    "pe_detector_set_stagger_event": (c_int, [c_void_p, c_void_p, c_int]),
     "pe_detector_last_profile": (c_int, [c_void_p, ctypes.POINTER(c_float), ctypes.POINTER(c_float), ctypes.POINTER(c_int), ctypes.POINTER(c_int)]),
     "pe_detector_profile_launches": (c_int, [c_void_p, ctypes.POINTER(c_float), ctypes.POINTER(ctypes.c_double),
                                              ctypes.POINTER(ctypes.c_double), c_int]),

@@ -886,13 +886,88 @@ __device__ __forceinline__ void roi_fast_sweep(const uint4* col0, uint4* dst0, c
   }
 }
 
+// The same sweep with the pixel columns prefetched through cp.async into a per-warp shared-memory ring instead of registers:
+// kRoiRingSlots / NR columns are in flight per warp (2-4 instead of 1), no registers are held while a load is outstanding (so
+// a fourth block fits on the SM), and the consumer reads its own 16 bytes back (no cross-lane hand-off: cp.async.wait_group is
+// the only synchronisation).  The kernel is latency-bound (633 vs 800 us per 16 000 ROIs at 21 vs 14 resident warps with the
+// same instruction count); the arithmetic and its order are unchanged, so the outputs are bit-identical.
+constexpr int kRoiRingSlots = 12;  // 512-byte warp rows per warp: 6 KB per warp, 42 KB per block
+
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+template <int NR>
+__device__ __forceinline__ void roi_fast_sweep_async(const uint4* col0, uint4* dst0, const float4* s_col, int ncols, int cgroups,
+                                                     size_t row_stride, int ny, float wy, float inv_count, int lane, uint4* ring) {
+  constexpr int D = kRoiRingSlots / NR;  // columns in flight
+  const unsigned long long inv2 = pack2f(inv_count, inv_count);
+  unsigned long long wy2[NR];
+  size_t roff[NR];
+#pragma unroll
+  for (int rr = 0; rr < NR; ++rr) {
+    const float w = __shfl_sync(kFullMask, wy, rr);
+    wy2[rr] = rr < ny ? pack2f(w, w) : 0ull;
+    roff[rr] = (size_t)(rr < ny ? rr : 0) * row_stride;
+  }
+  uint4* my = ring + lane;  // slot (c, rr) of this lane: my[(c * NR + rr) * 32]
+  for (int g = lane; g < cgroups; g += 32) {
+    const uint4* col = col0 + g;  // next column to request
+    uint4* dst = dst0 + g;
+#pragma unroll
+    for (int c = 0; c < D; ++c) {
+      if (c < ncols) {
+#pragma unroll
+        for (int rr = 0; rr < NR; ++rr) cp_async16(my + (c * NR + rr) * 32, col + roff[rr]);
+        col += cgroups;
+      }
+      cp_async_commit();
+    }
+    Acc8 cur, nxt;
+    cur.zero(); nxt.zero();
+    int slot = 0;
+    for (int ci = 0; ci < ncols; ++ci) {
+      cp_async_wait<D - 1>();  // column ci has landed (every iteration commits exactly one group)
+      const float4 e = s_col[ci];
+      uint4 a[NR];
+#pragma unroll
+      for (int rr = 0; rr < NR; ++rr) a[rr] = my[(slot * NR + rr) * 32];
+      if (ci + D < ncols) {  // refill the slot just read with column ci + D
+#pragma unroll
+        for (int rr = 0; rr < NR; ++rr) cp_async16(my + (slot * NR + rr) * 32, col + roff[rr]);
+        col += cgroups;
+      }
+      cp_async_commit();
+      if (++slot == D) slot = 0;
+      Acc8 t;
+      t.zero();
+#pragma unroll
+      for (int rr = 0; rr < NR; ++rr) acc_bf16x8(t, wy2[rr], a[rr]);
+      acc_axpy(cur, pack2f(e.x, e.x), t);
+      acc_axpy(nxt, pack2f(e.y, e.y), t);
+      if (e.z != 0.f) {  // warp-uniform: the column table is shared by the block
+        *dst = acc_store_bf16(cur, inv2);
+        dst += cgroups;
+        cur = nxt;
+        nxt.zero();
+      }
+    }
+    cp_async_wait<0>();
+  }
+}
+
 // The bilinear samples of one bin overlap heavily (sample spacing <= 1 feature pixel), so the bin average is
 // evaluated in its separable form  sum_rows sum_cols Wy[row] * Wx[col] * f(row, col)  with per-pixel weights
 // Wy/Wx accumulated from the reference's per-sample terms: every touched feature pixel is loaded once per bin
 // instead of once per neighbouring sample (up to 4x fewer 128-bit loads).
-template <int kMinBlocks>  // 3 blocks/SM caps the kernel at 96 registers (a few spills), 2 blocks/SM runs spill-free at 127
+// kAsync: the fast sweep prefetches through the cp.async ring (dynamic shared memory: 7 * kRoiRingSlots * 512 B)
+template <int kMinBlocks, bool kAsync>  // 3 blocks/SM caps the kernel at 96 registers (a few spills), 2 blocks/SM runs spill-free at 127
 __global__ void __launch_bounds__(224, kMinBlocks) roi_align_kernel(const RoiLevels fl, const float4* __restrict__ props, const int* __restrict__ prop_count,
                                                         int B, int max_props, int C, __nv_bfloat16* __restrict__ out) {
+  extern __shared__ uint4 s_ring[];
   __shared__ float s_wx[7][kRoiGmax + 2];
   __shared__ int s_x0[7], s_nx[7], s_ny[7];
   __shared__ float4 s_col[kRoiColMax];
@@ -989,6 +1064,14 @@ __global__ void __launch_bounds__(224, kMinBlocks) roi_align_kernel(const RoiLev
         uint4* dst = dst_roi + (size_t)(ph * 7) * cgroups;
         // NR = the block's tallest bin row: rows beyond a warp's own ny are zero-weight re-reads of row 0, so every NR above
         // the need costs a load + unpack + FMA group per pixel column (3- and 5-row bins are the common case at 14 / 28 px)
+        if (kAsync) {
+          uint4* ring = s_ring + ph * (kRoiRingSlots * 32);
+          if (nymax <= 3) roi_fast_sweep_async<3>(col, dst, s_col, ncols, cgroups, (size_t)W * cgroups, ny, wy, inv_count, lane, ring);
+          else if (nymax <= 4) roi_fast_sweep_async<4>(col, dst, s_col, ncols, cgroups, (size_t)W * cgroups, ny, wy, inv_count, lane, ring);
+          else if (nymax <= 5) roi_fast_sweep_async<5>(col, dst, s_col, ncols, cgroups, (size_t)W * cgroups, ny, wy, inv_count, lane, ring);
+          else roi_fast_sweep_async<6>(col, dst, s_col, ncols, cgroups, (size_t)W * cgroups, ny, wy, inv_count, lane, ring);
+          return;
+        }
         if (nymax <= 3) roi_fast_sweep<3>(col, dst, s_col, ncols, cgroups, (size_t)W * cgroups, ny, wy, inv_count, lane);
         else if (nymax <= 4) roi_fast_sweep<4>(col, dst, s_col, ncols, cgroups, (size_t)W * cgroups, ny, wy, inv_count, lane);
         else if (nymax <= 5) roi_fast_sweep<5>(col, dst, s_col, ncols, cgroups, (size_t)W * cgroups, ny, wy, inv_count, lane);
@@ -1558,13 +1641,17 @@ int launch_rpn_proposals(const RpnLevels& lv, int B, int pre_topk, int post_topk
 int launch_roi_align(const RoiLevels& fl, const float4* props, const int* prop_count, int B, int max_props, int C, void* out,
                      cudaStream_t st) {
   if (C % 256) return PE_ERR_UNSUPPORTED;  // lanes cover the channels 8 at a time, whole warps per pass
-  static const int occ = [] { const char* e = getenv("PE_ROI_OCC"); return e ? atoi(e) : 3; }();  // measured: 633 us (3) vs 800 us (2) per 16 000 ROIs
-  if (occ == 3)
-    roi_align_kernel<3><<<dim3((unsigned)max_props, (unsigned)B), 224, 0, st>>>(fl, props, prop_count, B, max_props, C,
-                                                                              reinterpret_cast<__nv_bfloat16*>(out));
-  else
-    roi_align_kernel<2><<<dim3((unsigned)max_props, (unsigned)B), 224, 0, st>>>(fl, props, prop_count, B, max_props, C,
-                                                                              reinterpret_cast<__nv_bfloat16*>(out));
+  // PE_ROI_OCC: resident blocks per SM the kernel is compiled for.  Register prefetch (PE_ROI_ASYNC=0): 633 us (3) vs 800 us (2) per
+  // 16 000 ROIs; cp.async ring (default): 3 | 4 blocks, see profiles/README.md
+  static const int async_env = [] { const char* e = getenv("PE_ROI_ASYNC"); return e ? atoi(e) : 1; }();
+  static const int occ = [] { const char* e = getenv("PE_ROI_OCC"); return e ? atoi(e) : (async_env ? 4 : 3); }();
+  const dim3 grid((unsigned)max_props, (unsigned)B);
+  const size_t ring_bytes = (size_t)7 * kRoiRingSlots * 32 * sizeof(uint4);
+  __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(out);
+  if (async_env && occ >= 4) roi_align_kernel<4, true><<<grid, 224, ring_bytes, st>>>(fl, props, prop_count, B, max_props, C, o);
+  else if (async_env) roi_align_kernel<3, true><<<grid, 224, ring_bytes, st>>>(fl, props, prop_count, B, max_props, C, o);
+  else if (occ == 3) roi_align_kernel<3, false><<<grid, 224, 0, st>>>(fl, props, prop_count, B, max_props, C, o);
+  else roi_align_kernel<2, false><<<grid, 224, 0, st>>>(fl, props, prop_count, B, max_props, C, o);
   PE_LAUNCH_CHECK();
   return PE_OK;
 }

@@ -56,6 +56,12 @@ struct pe_detector {
   int aux_used = 0;
   std::vector<std::string> aux_names;
   int last_launches = 0, last_gemm_launches = 0;
+  // optional cross-detector stagger (pe_detector_set_stagger_event): recorded on the forward's stream once `stagger_after` kernels
+  // have been launched, so that a SECOND detector's stream can start that much later and the two never sit in their latency-bound
+  // stages (RPN selection / NMS: a few CTAs) at the same time
+  cudaEvent_t stagger_ev = nullptr;
+  int stagger_after = 0;
+  bool stagger_sent = false;
   std::vector<pe::Param> params;
   std::vector<pe::Buf> bufs;
   size_t weight_bytes = 0, ws_bytes = 0;
@@ -244,6 +250,7 @@ struct Runner {
     if (d->profiling && e1) cudaEventRecord(e1, st);
     d->last_launches++;
     d->last_gemm_launches++;
+    signal_stagger();
     return s;
   }
 
@@ -279,7 +286,12 @@ struct Runner {
     cd.relu = relu; cd.residual_mode = 0; cd.out_fp32 = out_fp32; cd.in_fp16 = 0;
     status = gemm(cd, x, wts + p.w_off, reinterpret_cast<const float*>(wts + p.b_off), nullptr, y);
   }
-  void check(int s, int launches = 1) { if (status == PE_OK) status = s; d->last_launches += launches; }
+  void check(int s, int launches = 1) { if (status == PE_OK) status = s; d->last_launches += launches; signal_stagger(); }
+  void signal_stagger(bool force = false) {
+    if (!d->stagger_ev || d->stagger_sent || (!force && d->last_launches < d->stagger_after)) return;
+    cudaEventRecord(d->stagger_ev, st);
+    d->stagger_sent = true;
+  }
   // mode 1: event pair around a non-GEMM launch group, labelled with the launcher's name (pe_detector_profile_kernels)
   void aux_begin(const char* call) {
     if (!d->profiling || d->profile_runs || status != PE_OK) return;
@@ -346,6 +358,7 @@ struct Runner {
       if (e1) cudaEventRecord(e1, st);
       d->last_launches++;
       d->last_gemm_launches++;
+      signal_stagger();
     }
     // direction chain (L2 reuse, see ConvArgs::reverse): canvas staging walks forward -> stem conv backwards -> max-pool forward ->
     // res2.0.conv1 backwards -> ...
@@ -501,7 +514,7 @@ struct Runner {
         aux_end();
       }
     }
-    if (!(stages & PE_STAGE_ROI_HEADS)) { end_run(); return status; }
+    if (!(stages & PE_STAGE_ROI_HEADS)) { end_run(); signal_stagger(true); return status; }
     // ROI heads (roi_heads.py:595-631)
     RoiLevels fl;
     for (int l = 2; l <= 5; ++l) {
@@ -525,6 +538,7 @@ struct Runner {
     if (status == PE_OK)
       PE_NONGEMM(launch_head_post(reinterpret_cast<const float*>(buf("head_out")), d->npad, props, prop_count, B, kMaxProps, c.num_classes, hp, out, st));
     end_run();
+    signal_stagger(true);  // a waiter must never be left without its event (short stage masks, errors)
     return status;
   }
 };
@@ -555,6 +569,13 @@ extern "C" PE_API void pe_detector_destroy(pe_detector* d) {
   if (d) for (cudaEvent_t e : d->ev) cudaEventDestroy(e);
   if (d) for (cudaEvent_t e : d->aux_ev) cudaEventDestroy(e);
   delete d;
+}
+
+extern "C" PE_API int pe_detector_set_stagger_event(pe_detector* d, void* event, int after_launches) {
+  if (!d || after_launches < 0) return PE_ERR_INVALID_ARGUMENT;
+  d->stagger_ev = reinterpret_cast<cudaEvent_t>(event);
+  d->stagger_after = after_launches;
+  return PE_OK;
 }
 
 extern "C" PE_API int pe_detector_set_profiling(pe_detector* d, int enabled) {
@@ -672,6 +693,7 @@ extern "C" PE_API int pe_detector_forward_stages(pe_detector* d, const void* wei
   d->prof_flops.clear();
   d->prof_bytes.clear();
   d->last_launches = 0;
+  d->stagger_sent = false;
   d->last_gemm_launches = 0;
   pe::Runner r;
   r.d = d;
@@ -699,6 +721,7 @@ extern "C" PE_API int pe_detector_forward_frames(pe_detector* d, const void* wei
   d->prof_flops.clear();
   d->prof_bytes.clear();
   d->last_launches = 0;
+  d->stagger_sent = false;
   d->last_gemm_launches = 0;
   pe::Runner r;
   r.d = d;

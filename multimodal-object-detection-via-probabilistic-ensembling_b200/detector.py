@@ -261,6 +261,12 @@ class Detector:
     def set_profiling(self, enabled):
         _lib.check(self.lib.pe_detector_set_profiling(self.handle, int(enabled)), "pe_detector_set_profiling")
 
+    def set_stagger_event(self, event, after_launches):
+        """``event``: a ``torch.cuda.Event`` (recorded at least once, so that its handle exists) or None; see
+        ``pe_detector_set_stagger_event``."""
+        handle = None if event is None else ctypes.c_void_p(event.cuda_event)
+        _lib.check(self.lib.pe_detector_set_stagger_event(self.handle, handle, int(after_launches)), "pe_detector_set_stagger_event")
+
     def last_profile(self):
         """(gemm_ms, span_ms, launches, gemm_launches) of the last forward (syncs on its last GEMM event)."""
         g, s = ctypes.c_float(), ctypes.c_float()

@@ -7,6 +7,7 @@ One stream, no host synchronisation: detector m -> fixed-stride detection record
 of a step live in ONE flat device buffer so that the multi-GPU path needs a single NCCL all-gather.
 """
 import ctypes
+import os
 
 import torch
 
@@ -86,6 +87,13 @@ class ProbEnPipeline:
                     d.share_workspace(big)
         self.ev_start = torch.cuda.Event()
         self.ev_done = [torch.cuda.Event() for _ in range(self.M)]
+        # stagger between the model streams: model m + 1 starts once model m has launched ``stagger`` kernels (canvas staging, stem,
+        # max-pool and the first res2 layers: ~0.5 ms), so the detectors never reach their latency-bound stages (RPN top-k / NMS /
+        # merge: ~0.35 ms on a few CTAs) together and each of them runs under the other model's GEMMs.  0 = start together.
+        self.stagger = int(os.environ.get("PE_PIPE_STAGGER", "6")) if self.streams is not None else 0
+        self.ev_stagger = [torch.cuda.Event() for _ in range(self.M - 1)] if self.stagger else []
+        for e in self.ev_stagger:
+            e.record()  # creates the handle the engine records on
         self.dets = [DetectionBuffers(self.B, self.K, self.device) for _ in range(self.M)]
         self.det_structs = (_lib.Detections * self.M)(*[d.struct() for d in self.dets])
         N = self.B * self.M * MAX_DET
@@ -127,9 +135,15 @@ class ProbEnPipeline:
             for m, (det, img, buf) in enumerate(zip(self.detectors, images, self.dets)):
                 with torch.cuda.stream(self.streams[m]):
                     self.streams[m].wait_event(self.ev_start)
+                    if self.stagger and m > 0:
+                        self.streams[m].wait_event(self.ev_stagger[m - 1])  # recorded by model m - 1's forward, see __init__
+                    if self.stagger:
+                        det.set_stagger_event(self.ev_stagger[m] if m + 1 < self.M else None, self.stagger)
                     nvtx.range_push("probenb200.detector[%d]" % m)
                     run(det, img, buf)
                     nvtx.range_pop()
+                    if self.stagger:
+                        det.set_stagger_event(None, 0)
                     self.ev_done[m].record(self.streams[m])
             for m in range(self.M):
                 main.wait_event(self.ev_done[m])
