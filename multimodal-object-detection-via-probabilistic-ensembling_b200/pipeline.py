@@ -90,7 +90,7 @@ class ProbEnPipeline:
         # stagger between the model streams: model m + 1 starts once model m has launched ``stagger`` kernels (canvas staging, stem,
         # max-pool and the first res2 layers: ~0.5 ms), so the detectors never reach their latency-bound stages (RPN top-k / NMS /
         # merge: ~0.35 ms on a few CTAs) together and each of them runs under the other model's GEMMs.  0 = start together.
-        self.stagger = int(os.environ.get("PE_PIPE_STAGGER", "6")) if self.streams is not None else 0
+        self.stagger = int(os.environ.get("PE_PIPE_STAGGER", "0")) if self.streams is not None else 0
         self.ev_stagger = [torch.cuda.Event() for _ in range(self.M - 1)] if self.stagger else []
         for e in self.ev_stagger:
             e.record()  # creates the handle the engine records on
