@@ -59,7 +59,9 @@ struct ConvSecondInput { const void* x; int Cin, H, W, stride; };
 // bn: main tile width, 256 (one main accumulator stage) | 128 (two stages, deferred chained GEMM / epilogue) | 0 = default
 // out_fp32: narrow fp32 chain (N = 16, y2 = [.., 16] fp32; the RPN head's objectness | deltas on top of its 3x3 conv): the main
 // output y is NOT stored
-struct ConvChain { const void* w; const float* bias; void* y; int N; int relu; int bn; int out_fp32; };
+// y2 (narrow fp32 chain only, optional): dense float4 copy of the first three chained outputs per pixel (the RPN objectness
+// logits | 0), the stream rpn_topk_kernel selects from
+struct ConvChain { const void* w; const float* bias; void* y; int N; int relu; int bn; int out_fp32; void* y2; };
 int conv2d_launch(const pe_conv_desc& d, const void* x, const void* w, const float* bias, const void* residual, void* y,
                   cudaStream_t st, const ConvSecondInput* x2 = nullptr, int reverse = 0, const ConvChain* chain = nullptr);
 

@@ -62,6 +62,7 @@ struct ConvArgs {
   // k-iterations of tile i + 1 - both main stages stay available and the mainloop never waits for an epilogue.
   int chain_fp32;
   float* chain_out;
+  float* chain_out2;  // optional dense [pixels][4] copy of chained outputs 0..2 | 0 (the objectness logits)
   int reverse;   // walk the tiles from the last to the first: consecutive layers alternate direction, so a layer starts with
                  // the part of its input that the previous layer wrote last and that is still in the 126 MB L2
   int k_chunks1; // dual-input 1x1 (bottleneck conv3 + projection shortcut as ONE GEMM over K = [t2 | x]): chunks [0, k_chunks1) come
@@ -914,9 +915,11 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
 #pragma unroll
             for (int i = 0; i < 8; ++i) f[i] = fmaxf(f[i], 0.f);
           }
-          float4* op = reinterpret_cast<float4*>(a.chain_out + (((size_t)img * a.Ho + h) * a.Wo + w) * 16 + half * 8);
+          const size_t opix = ((size_t)img * a.Ho + h) * a.Wo + w;
+          float4* op = reinterpret_cast<float4*>(a.chain_out + opix * 16 + half * 8);
           op[0] = make_float4(f[0], f[1], f[2], f[3]);
           op[1] = make_float4(f[4], f[5], f[6], f[7]);
+          if (half == 0 && a.chain_out2) reinterpret_cast<float4*>(a.chain_out2)[opix] = make_float4(f[0], f[1], f[2], 0.f);
         }
       };
       for (int it = 0, tile; (tile = tile_at(it)) >= 0; ++it) {
@@ -1152,6 +1155,7 @@ int conv2d_launch(const pe_conv_desc& d, const void* x, const void* w, const flo
   a.chain_bias = chained ? ch->bias : nullptr;
   a.chain_fp32 = chained && ch->out_fp32 ? 1 : 0;
   a.chain_out = a.chain_fp32 ? reinterpret_cast<float*>(ch->y) : nullptr;
+  a.chain_out2 = a.chain_fp32 ? reinterpret_cast<float*>(ch->y2) : nullptr;
   a.b2_stages = 0;
   const bool dual = x2 && x2->x;
   if (dual) a.k_chunks += ceil_div(x2->Cin, kBlockK);
@@ -1377,7 +1381,7 @@ extern "C" PE_API int pe_conv1x1_chain_fwd(const pe_conv_desc* desc, const void*
 extern "C" PE_API int pe_conv_rpn_head_fwd(const pe_conv_desc* desc, const void* x, const void* w, const float* bias, const void* wc,
                                            const float* bias_c, float* y_c, void* stream) {
   if (!desc || !wc || !y_c) return PE_ERR_INVALID_ARGUMENT;
-  pe::ConvChain ch = {wc, bias_c, y_c, 16, 0, 0, 1};
+  pe::ConvChain ch = {wc, bias_c, y_c, 16, 0, 0, 1, nullptr};
   return pe::conv2d_launch(*desc, x, w, bias, nullptr, nullptr, reinterpret_cast<cudaStream_t>(stream), nullptr, 0, &ch);
 }
 

@@ -528,14 +528,26 @@ __global__ void __launch_bounds__(kTopkThreads) rpn_topk_kernel(const RpnLevels 
   const int n = H * W * A;
   const int k = pre_topk < n ? pre_topk : n;
   const float* base = lv.out[level] + (size_t)b * H * W * kRpnOutC;
-  auto logit = [&](int e) { return __ldg(base + (size_t)(e / A) * kRpnOutC + (e % A)); };
+  // The select passes read one float4 per pixel (3 logits | pad): from the dense logit plane the RPN-head kernel writes next to its
+  // 64-byte records when there is one (4x fewer sectors: a p2 block streams 51 200 pixels twice and is bound by its SM's L2
+  // bandwidth), else from the first 16 bytes of the records.
+  const float* src = lv.logit[level] ? lv.logit[level] + (size_t)b * H * W * 4 : base;
+  const int sstride = lv.logit[level] ? 4 : kRpnOutC;
+  const int npix = H * W;
+  auto logit = [&](int e) { return __ldg(src + (size_t)(e / A) * sstride + (e % A)); };
+  auto logit3 = [&](int p) { return __ldg(reinterpret_cast<const float4*>(src + (size_t)p * sstride)); };
   auto pack = [](uint32_t key, int e) { return ((unsigned long long)key << 32) | (unsigned)(0xffffffffu - (unsigned)e); };
 
   // ---- pass 0 over global memory: histogram of the top 11 key bits -> bin of the k-th largest logit
   for (int i = tid; i < 2048; i += blockDim.x) hist[i] = 0;
   if (tid == 0) { sel_n = 0; eq_run = 0; cand_n = 0; }
   __syncthreads();
-  for (int e = tid; e < n; e += blockDim.x) atomicAdd(&hist[sort_key(logit(e)) >> 21], 1u);
+  for (int p = tid; p < npix; p += blockDim.x) {
+    const float4 v = logit3(p);
+    atomicAdd(&hist[sort_key(v.x) >> 21], 1u);
+    atomicAdd(&hist[sort_key(v.y) >> 21], 1u);
+    atomicAdd(&hist[sort_key(v.z) >> 21], 1u);
+  }
   __syncthreads();
   find_kth_bin(hist, 2048, (unsigned)k, res, warp_tot);
   const unsigned bin0 = res[0], above0 = res[1];
@@ -546,9 +558,12 @@ __global__ void __launch_bounds__(kTopkThreads) rpn_topk_kernel(const RpnLevels 
   const bool small = above0 + in_bin0 <= (unsigned)kTopkCandCap;  // block-uniform
   if (small) {
     // ---- pass 1 over global memory: keep everything from the threshold bin upwards in shared memory
-    for (int e = tid; e < n; e += blockDim.x) {
-      const uint32_t key = sort_key(logit(e));
-      if ((key >> 21) >= bin0) cand[atomicAdd(&cand_n, 1u)] = pack(key, e);
+    for (int p = tid; p < npix; p += blockDim.x) {
+      const float4 v = logit3(p);
+      const uint32_t k0 = sort_key(v.x), k1 = sort_key(v.y), k2 = sort_key(v.z);
+      if ((k0 >> 21) >= bin0) cand[atomicAdd(&cand_n, 1u)] = pack(k0, p * A);
+      if ((k1 >> 21) >= bin0) cand[atomicAdd(&cand_n, 1u)] = pack(k1, p * A + 1);
+      if ((k2 >> 21) >= bin0) cand[atomicAdd(&cand_n, 1u)] = pack(k2, p * A + 2);
     }
     __syncthreads();
     const int nc = (int)cand_n;
@@ -745,35 +760,83 @@ __global__ void __launch_bounds__(kNmsThreads) nms_mask_kernel(const float4* __r
   }
 }
 
-// Greedy scan over the bitmask: the block stages the rows in shared memory, warp 0 walks them in score order.
+// Greedy NMS over the bitmask without a serial walk.  "j is kept iff it is valid and no EARLIER KEPT box suppresses it" is
+// iterated as a fixed point over all boxes at once: keep' = valid & ~OR(rows of the boxes in keep).  Rows only hold bits j > i, so
+// after t rounds the first t boxes are final and the iteration ends in the greedy solution (unique); dense proposal sets settle
+// in a few dozen rounds of ~100 instructions per warp (warp w ORs the kept rows 32w.., lane <-> word, conflict-free) where the
+// serial walk of warp 0 needed <= 1000 dependent shuffle + shared-memory steps (68 us per segment).  A set that has not settled
+// after kNmsMaxRounds rounds falls back to that walk.
+constexpr int kNmsMaxRounds = 96;
+
 __global__ void __launch_bounds__(1024) nms_scan_kernel(const unsigned* __restrict__ mask, const unsigned char* __restrict__ valid,
                                                         const int* __restrict__ counts, int seg_stride, int* __restrict__ keep_idx,
                                                         int* __restrict__ keep_count) {
   extern __shared__ __align__(16) unsigned char nms_smem[];
   unsigned* sm = reinterpret_cast<unsigned*>(nms_smem);  // [n][32]
-  const int seg = blockIdx.x, tid = threadIdx.x, lane = tid & 31;
+  __shared__ unsigned s_keep[2][32], s_valid[32], s_removed[32];
+  __shared__ int s_prefix[33];
+  const int seg = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   const int n = counts[seg];
   const size_t base = (size_t)seg * seg_stride;
   const int Wn = (n + 31) >> 5;
   const uint4* src = reinterpret_cast<const uint4*>(mask + (size_t)seg * 1024 * 32);
   for (int i = tid; i < n * 8; i += blockDim.x) reinterpret_cast<uint4*>(sm)[i] = __ldg(src + i);
+  {  // validity words: warp w <-> boxes 32w..
+    const int j = tid;
+    const unsigned v = __ballot_sync(kFullMask, j < n && valid[base + j] != 0);
+    if (lane == 0) { s_valid[wid] = v; s_keep[0][wid] = v; }
+  }
   __syncthreads();
+  int cur = 0;
+  bool settled = false;
+  for (int round = 0; round < kNmsMaxRounds; ++round) {
+    if (tid < 32) s_removed[tid] = 0u;
+    __syncthreads();
+    unsigned kw = s_keep[cur][wid], acc = 0u;
+    while (kw) {  // warp-uniform
+      const int r = __ffs(kw) - 1;
+      kw &= kw - 1u;
+      if (lane < Wn) acc |= sm[((wid << 5) + r) * 32 + lane];
+    }
+    if (acc) atomicOr(&s_removed[lane], acc);
+    __syncthreads();
+    bool changed = false;
+    if (tid < 32) {
+      const unsigned nk = s_valid[tid] & ~s_removed[tid];
+      changed = nk != s_keep[cur][tid];
+      s_keep[cur ^ 1][tid] = nk;
+    }
+    cur ^= 1;
+    if (!__syncthreads_or(changed)) { settled = true; break; }
+  }
+  if (!settled) {  // block-uniform: the serial greedy walk (lane w owns word w of the removed set)
+    if (tid < 32) {
+      unsigned removed = ~s_valid[lane];
+      for (int i = 0; i < n; ++i) {
+        const unsigned rw = __shfl_sync(kFullMask, removed, i >> 5);
+        if ((rw >> (i & 31)) & 1u) continue;
+        if (lane < Wn) removed |= sm[i * 32 + lane];
+      }
+      s_keep[cur][lane] = ~removed;
+    }
+    __syncthreads();
+  }
+  // survivors in index (= score) order
   if (tid < 32) {
-    unsigned removed = 0;  // lane w owns word w; invalid boxes start out removed
-    for (int w = 0; w < Wn; ++w) {
-      const int j = (w << 5) + lane;
-      const unsigned inv = __ballot_sync(kFullMask, j < n ? valid[base + j] == 0 : true);
-      if (lane == w) removed = inv;
+    const int c = __popc(s_keep[cur][lane]);
+    int incl = c;
+    for (int d = 1; d < 32; d <<= 1) {
+      const int o = __shfl_up_sync(kFullMask, incl, d);
+      if (lane >= d) incl += o;
     }
-    int kept = 0;
-    for (int i = 0; i < n; ++i) {
-      const unsigned rw = __shfl_sync(kFullMask, removed, i >> 5);
-      if ((rw >> (i & 31)) & 1u) continue;
-      if (lane < Wn) removed |= sm[i * 32 + lane];
-      if (lane == 0) keep_idx[base + kept] = i;
-      ++kept;
-    }
-    if (lane == 0) keep_count[seg] = kept;
+    s_prefix[lane + 1] = incl;
+    if (lane == 0) s_prefix[0] = 0;
+    if (lane == 31) keep_count[seg] = incl;
+  }
+  __syncthreads();
+  if (tid < n) {
+    const unsigned kwd = s_keep[cur][wid];
+    if ((kwd >> lane) & 1u) keep_idx[base + s_prefix[wid] + __popc(kwd & ((1u << lane) - 1u))] = tid;
   }
 }
 
@@ -1105,17 +1168,18 @@ __global__ void __launch_bounds__(224, kMinBlocks) roi_align_kernel(const RoiLev
     // zero-padded weights (rows beyond ny re-read row 0), t = sum_r Wy[r] f, cur += wa t, nxt += wb t, and a warp-uniform
     // "bin complete" step.  (The general sweep below spends ~70 instructions per 128-bit load on bookkeeping.)
     {
-      bool fast = true;
-#pragma unroll
-      for (int p2 = 0; p2 < 7; ++p2) fast &= s_ny[p2] <= 6 && s_nx[p2] >= 1;
-#pragma unroll
-      for (int p2 = 0; p2 < 6; ++p2)
-        fast &= s_x0[p2 + 1] >= s_x0[p2] && s_x0[p2 + 1] + s_nx[p2 + 1] > s_x0[p2] + s_nx[p2] && s_x0[p2 + 1] <= s_x0[p2] + s_nx[p2];
-#pragma unroll
-      for (int p2 = 0; p2 < 5; ++p2) fast &= s_x0[p2 + 2] > s_x0[p2] + s_nx[p2] - 1;  // a column lies in at most two bins
-      const int xs = s_x0[0], xe = s_x0[6] + s_nx[6] - 1;
+      // the per-bin conditions are evaluated one bin per lane and combined with a vote (every warp reaches the same verdict):
+      // reading the 21 table entries in every thread cost 6 % of the kernel's stall samples
+      const int bp = lane < 7 ? lane : 6;
+      const int bx = s_x0[bp], bn = s_nx[bp], by = s_ny[bp];
+      const int bx1 = __shfl_down_sync(kFullMask, bx, 1), bn1 = __shfl_down_sync(kFullMask, bn, 1);
+      const int bx2 = __shfl_down_sync(kFullMask, bx, 2);
+      bool ok = by <= 6 && bn >= 1;
+      if (lane < 6) ok &= bx1 >= bx && bx1 + bn1 > bx + bn && bx1 <= bx + bn;
+      if (lane < 5) ok &= bx2 > bx + bn - 1;  // a column lies in at most two bins
+      const int xs = __shfl_sync(kFullMask, bx, 0), xe = __shfl_sync(kFullMask, bx + bn - 1, 6);
       const int ncols = xe - xs + 1;
-      fast &= ncols <= kRoiColMax;
+      const bool fast = __all_sync(kFullMask, ok) && ncols <= kRoiColMax;
       if (fast) {  // block-uniform
         if ((int)threadIdx.x < ncols) {
           const int x = xs + threadIdx.x;
@@ -1128,9 +1192,7 @@ __global__ void __launch_bounds__(224, kMinBlocks) roi_align_kernel(const RoiLev
         }
         __syncthreads();
         const float inv_count = 1.f / count;
-        int nymax = 0;
-#pragma unroll
-        for (int p2 = 0; p2 < 7; ++p2) nymax = max(nymax, s_ny[p2]);
+        const int nymax = __reduce_max_sync(kFullMask, by);
         const uint4* col = reinterpret_cast<const uint4*>(feat + ((size_t)y0 * W + xs) * C);
         uint4* dst = dst_roi + (size_t)(ph * 7) * cgroups;
         // NR = the block's tallest bin row: rows beyond a warp's own ny are zero-weight re-reads of row 0, so every NR above
@@ -1732,7 +1794,7 @@ int launch_roi_align(const RoiLevels& fl, const float4* props, const int* prop_c
   // PE_ROI_OCC: resident blocks per SM the kernel is compiled for.  Register prefetch (PE_ROI_ASYNC=0): 633 us (3) vs 800 us (2) per
   // 16 000 ROIs; cp.async ring (default): 3 | 4 blocks, see profiles/README.md
   static const int async_env = [] { const char* e = getenv("PE_ROI_ASYNC"); return e ? atoi(e) : 1; }();
-  static const int occ = [] { const char* e = getenv("PE_ROI_OCC"); return e ? atoi(e) : (async_env ? 4 : 3); }();
+  static const int occ = [] { const char* e = getenv("PE_ROI_OCC"); return e ? atoi(e) : 3; }();
   const dim3 grid((unsigned)max_props, (unsigned)B);
   const size_t ring_bytes = (size_t)7 * kRoiRingSlots * 32 * sizeof(uint4);
   __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(out);

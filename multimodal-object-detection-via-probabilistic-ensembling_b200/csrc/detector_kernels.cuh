@@ -15,6 +15,7 @@ struct StemNorm { float mean[8]; float std[8]; };
 
 struct RpnLevels {
   const float* out[kRpnLevels];   // [B, H, W, kRpnOutC]
+  const float* logit[kRpnLevels]; // optional dense copy of the objectness logits [B, H, W, 4] (3 logits | pad) or nullptr
   int H[kRpnLevels], W[kRpnLevels], stride[kRpnLevels];
   float anchor[kRpnLevels][3][4]; // cell anchors (anchor_generator.py:151-187), float32 of the double maths
 };

@@ -178,6 +178,8 @@ void build_plan(pe_detector* d) {
     if (c.middle_fusion || l == 6) d->add_buf(q, B, d->H[l - 1], d->W[l - 1], d->fc, 2);
     snprintf(q, sizeof(q), "rpn_out%d", l);
     d->add_buf(q, B, d->H[l - 1], d->W[l - 1], kRpnOutC, 4);
+    snprintf(q, sizeof(q), "rpn_logit%d", l);  // dense copy of the objectness logits (3 | pad) for the top-k passes
+    d->add_buf(q, B, d->H[l - 1], d->W[l - 1], 4, 4);
   }
   d->add_buf("rpn_t", B, d->H[1], d->W[1], d->fc, 2);
   d->add_buf("cand_box", B, kRpnLevels, kTopkSlots, 4, 4);
@@ -232,6 +234,7 @@ struct Runner {
         flops += 2.0 * opix * cd.Cout * chain->N;
         bytes += (double)chain->N * cd.Cout * 2 + chain->N * 4.0 + opix * chain->N * (chain->out_fp32 ? 4 : 2);
         if (chain->out_fp32) bytes -= opix * cd.Cout * 2;  // the RPN head's hidden tensor is not stored at all
+        if (chain->out_fp32 && chain->y2) bytes += opix * 16;  // dense logit plane
       }
       if (e0) {
         d->prof_flops.push_back(flops);
@@ -463,7 +466,7 @@ struct Runner {
     int* prop_count = reinterpret_cast<int*>(buf("prop_count"));
     if (stages & PE_STAGE_RPN) {
       // RPN head on p2..p6 (rpn.py:74-85): 3x3+ReLU, then objectness + deltas as one 16-wide fp32 GEMM
-      RpnLevels lv;
+      RpnLevels lv = {};
       for (int l = 2; l <= 6; ++l) {
         char q[16];
         snprintf(q, sizeof(q), "rpn_out%d", l);
@@ -477,7 +480,10 @@ struct Runner {
             pe_conv_desc cd;
             cd.N = B; cd.H = d->H[l - 1]; cd.W = d->W[l - 1]; cd.Cin = p3.Cin; cd.Cout = p3.Cout; cd.KH = 3; cd.KW = 3; cd.stride = 1;
             cd.relu = 1; cd.residual_mode = 0; cd.out_fp32 = 0; cd.in_fp16 = 0;
-            ConvChain ch = {wts + p1.w_off, reinterpret_cast<const float*>(wts + p1.b_off), buf(q), 16, 0, 0, 1};
+            char ql[20];
+            snprintf(ql, sizeof(ql), "rpn_logit%d", l);
+            ConvChain ch = {wts + p1.w_off, reinterpret_cast<const float*>(wts + p1.b_off), buf(q), 16, 0, 0, 1, buf(ql)};
+            lv.logit[l - 2] = reinterpret_cast<const float*>(buf(ql));
             status = gemm(cd, level_feat(l), wts + p3.w_off, reinterpret_cast<const float*>(wts + p3.b_off), nullptr, nullptr, nullptr, &ch);
           }
         } else {
@@ -485,6 +491,7 @@ struct Runner {
           conv("proposal_generator.rpn_head", buf("rpn_t"), d->H[l - 1], d->W[l - 1], 1, false, 0, nullptr, buf(q), true);
         }
         lv.out[l - 2] = reinterpret_cast<const float*>(buf(q));
+        if (!(rpn_chain && d->fc == 256)) lv.logit[l - 2] = nullptr;
         lv.H[l - 2] = d->H[l - 1];
         lv.W[l - 2] = d->W[l - 1];
         lv.stride[l - 2] = 2 << (l - 1);
@@ -757,7 +764,7 @@ extern "C" PE_API int pe_rpn_proposals(const float* const* rpn_out, const int* H
   if (workspace_bytes < pe_rpn_proposals_workspace_bytes(B)) return PE_ERR_WORKSPACE_TOO_SMALL;
   pe::RpnLevels lv;
   for (int l = 0; l < pe::kRpnLevels; ++l) {
-    lv.out[l] = rpn_out[l]; lv.H[l] = H[l]; lv.W[l] = W[l]; lv.stride[l] = 4 << l;
+    lv.out[l] = rpn_out[l]; lv.logit[l] = nullptr; lv.H[l] = H[l]; lv.W[l] = W[l]; lv.stride[l] = 4 << l;
     const double size = 32.0 * (1 << l);
     const double ratios[3] = {0.5, 1.0, 2.0};
     for (int a = 0; a < 3; ++a) {
