@@ -213,8 +213,13 @@ __global__ void stem_canvas_kernel(const float* __restrict__ img, __half* __rest
 // DefaultPredictor's ResizeShortestEdge) + normalisation fused, so the float32 network input never exists in HBM.
 // Upscales need at most 3 taps per axis: the engine tabulates them once per forward (row table [Hi] then column table
 // [Wi], int4 = first source index, three 22-bit weights) so that the per-pixel work is integer only.
-__global__ void pil_taps_table_kernel(int4* __restrict__ table, int Hs, int Ws, int Hi, int Wi) {
+__global__ void pil_taps_table_kernel(int4* __restrict__ table, int Hs, int Ws, int Hi, int Wi, __half* __restrict__ lut, int C,
+                                      StemNorm nrm) {
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (lut && t < 4 * 256) {  // normalisation table of the tiled staging kernel: lut[c][v] = fp16((v - mean_c) / std_c), 0 for c >= C
+    const int c = t >> 8;
+    lut[t] = __float2half_rn(c < C ? __fdiv_rn((float)(t & 255) - nrm.mean[c], nrm.std[c]) : 0.f);
+  }
   if (t >= Hi + Wi) return;
   const PilTaps<3> tp = t < Hi ? pil_taps<3>(t, Hs, Hi) : pil_taps<3>(t - Hi, Ws, Wi);
   table[t] = make_int4(tp.lo | (tp.n << 24), tp.k[0], tp.k[1], tp.k[2]);
@@ -279,14 +284,14 @@ constexpr int kCanvasSpan = kCanvasRows + 4;
 
 __global__ void __launch_bounds__(256) stem_canvas_u8_tiled_kernel(const unsigned char* __restrict__ frames, __half* __restrict__ canvas,
                                                                     int Ctot, int c0, int C, int Hs, int Ws, int Hi, int Wi, int Hp, int Wp,
-                                                                    StemNorm nrm, const int4* __restrict__ taps) {
-  extern __shared__ uint32_t s_h[];      // [kCanvasSpan][Wi]
+                                                                    const int4* __restrict__ taps, const __half* __restrict__ lut) {
+  extern __shared__ __align__(16) unsigned char s_dyn[];
+  uint32_t* s_h = reinterpret_cast<uint32_t*>(s_dyn);                         // [kCanvasSpan][Wi] filtered rows
+  unsigned char* s_raw = s_dyn + (size_t)kCanvasSpan * Wi * sizeof(uint32_t);  // [kCanvasSpan][Ws * Ctot] source rows
   __shared__ __half s_lut[4][256];
   const int tid = threadIdx.x, b = blockIdx.y, yp0 = blockIdx.x * kCanvasRows;
-  for (int i = tid; i < 4 * 256; i += 256) {
-    const int c = i >> 8;
-    s_lut[c][i & 255] = __float2half_rn(c < C ? __fdiv_rn((float)(i & 255) - nrm.mean[c], nrm.std[c]) : 0.f);
-  }
+  for (int i = tid; i < 4 * 256 / 2; i += 256)  // (v - mean) / std per channel, tabulated once per forward by pil_taps_table_kernel
+    reinterpret_cast<uint32_t*>(&s_lut[0][0])[i] = __ldg(reinterpret_cast<const uint32_t*>(lut) + i);
   const int ya = max(yp0 - 3, 0), yb = min(yp0 + kCanvasRows - 1 - 3, Hi - 1);  // image rows under this block's canvas rows
   int s0 = 0, ns = 0;
   if (ya <= yb) {
@@ -294,12 +299,21 @@ __global__ void __launch_bounds__(256) stem_canvas_u8_tiled_kernel(const unsigne
     s0 = ea.x & 0xffffff;
     ns = min((eb.x & 0xffffff) + (eb.x >> 24) - s0, kCanvasSpan);
   }
-  const unsigned char* im = frames + (size_t)b * Hs * Ws * Ctot;
+  // the source rows of this block are one contiguous byte range: staged with 16-byte loads when aligned, so the 9 byte reads
+  // per filtered pixel hit shared memory (from global memory they were 40 % of the kernel's stall samples)
+  const int row_bytes = Ws * Ctot;
+  const unsigned char* src = frames + ((size_t)b * Hs + s0) * row_bytes;
+  const int nbytes = ns * row_bytes;
+  if (((reinterpret_cast<uintptr_t>(src) | (uintptr_t)nbytes) & 15) == 0) {
+    for (int i = tid; i < nbytes / 16; i += 256) reinterpret_cast<uint4*>(s_raw)[i] = __ldg(reinterpret_cast<const uint4*>(src) + i);
+  } else {
+    for (int i = tid; i < nbytes; i += 256) s_raw[i] = __ldg(src + i);
+  }
+  __syncthreads();
   for (int x = tid; x < Wi; x += 256) {
     const PilTaps<3> tx = pil_taps_from_table(__ldg(taps + Hi + x));
-    const unsigned char* colp = im + ((size_t)s0 * Ws + tx.lo) * Ctot + c0;
-    for (int r = 0; r < ns; ++r) {
-      const unsigned char* rowp = colp + (size_t)r * Ws * Ctot;
+    const unsigned char* rowp = s_raw + tx.lo * Ctot + c0;
+    for (int r = 0; r < ns; ++r, rowp += row_bytes) {
       int h[4];
 #pragma unroll
       for (int c = 0; c < 4; ++c) h[c] = 1 << (kPilPrecisionBits - 1);
@@ -308,7 +322,7 @@ __global__ void __launch_bounds__(256) stem_canvas_u8_tiled_kernel(const unsigne
         if (i < tx.n) {
 #pragma unroll
           for (int c = 0; c < 4; ++c)
-            if (c < C) h[c] += (int)__ldg(rowp + i * Ctot + c) * tx.k[i];
+            if (c < C) h[c] += (int)rowp[i * Ctot + c] * tx.k[i];
         }
       }
       s_h[r * Wi + x] = (uint32_t)pil_clip8(h[0]) | ((uint32_t)pil_clip8(h[1]) << 8) | ((uint32_t)pil_clip8(h[2]) << 16) |
@@ -1545,12 +1559,14 @@ __global__ void __launch_bounds__(kHeadThreads) head_post_kernel(const float* __
   for (int w2 = 1; w2 < kHeadThreads / 32; ++w2) mc = fmaxf(mc, s_red[w2]);
   const float off1 = __fadd_rn(mc, 1.f);
   // 3. greedy per-class NMS in score order, stop after detections_per_image survivors
+  // (the survivor count lives in a register of every thread - all threads take the same decisions - so one barrier per SURVIVOR
+  // is enough: it orders this round's c_dead writes, which only touch later candidates, before the next round's reads)
+  int nkeep = 0;
   for (int a = 0; a < n; ++a) {
     const int i = c_order[a];
     if (c_dead[i]) continue;        // uniform: shared memory, synchronised below
-    if (s_nkeep >= hp.max_det) break;
-    __syncthreads();
-    if (tid == 0) { s_keep[s_nkeep] = i; }
+    if (nkeep >= hp.max_det) break;
+    if (tid == 0) { s_keep[nkeep] = i; }
     const float oi = __fmul_rn((float)c_cls[i], off1);
     const float4 q = c_box[i];
     const float4 bi = make_float4(__fadd_rn(q.x, oi), __fadd_rn(q.y, oi), __fadd_rn(q.z, oi), __fadd_rn(q.w, oi));
@@ -1564,10 +1580,10 @@ __global__ void __launch_bounds__(kHeadThreads) head_post_kernel(const float* __
       const float aj = __fmul_rn(__fsub_rn(bj.z, bj.x), __fsub_rn(bj.w, bj.y));
       if (iou_gt(bi, ai, bj, aj, hp.nms_thresh)) c_dead[j] = 1;
     }
-    __syncthreads();
-    if (tid == 0) s_nkeep = s_nkeep + 1;
+    ++nkeep;
     __syncthreads();
   }
+  if (tid == 0) s_nkeep = nkeep;
   __syncthreads();
   // 4. emit: postprocess scale/clip/non-empty (postprocessing.py:8-52), fork fields
   const int nk = s_nkeep;
@@ -1694,21 +1710,25 @@ int launch_stem_im2col_u8(const unsigned char* frames, void* canvas, void* A, in
   const int grid = grid_for((long long)B * Hp * Wp, 256);
   __half* cv = reinterpret_cast<__half*>(canvas);
   int4* taps = kmax == 3 ? reinterpret_cast<int4*>(taps_ws) : nullptr;
+  __half* lut = nullptr;
   if (taps) {
-    pil_taps_table_kernel<<<ceil_div(Hi + Wi, 256), 256, 0, st>>>(taps, Hs, Ws, Hi, Wi);
+    // the (v - mean) / std table of the tiled kernel (4 x 256 fp16 = 128 int4) sits behind the tap tables: taps_ws holds
+    // canvas_h + canvas_w + 128 int4 (engine.cu "pil_taps")
+    lut = reinterpret_cast<__half*>(taps + Hc + Wc);
+    pil_taps_table_kernel<<<ceil_div(max(Hi + Wi, 1024), 256), 256, 0, st>>>(taps, Hs, Ws, Hi, Wi, lut, C, nrm);
     PE_LAUNCH_CHECK();
   }
   // upscales: the tiled two-pass kernel (PE_STEM_TILED=0 keeps the per-pixel kernel, A/B switch)
   static const int tiled_env = [] { const char* e = getenv("PE_STEM_TILED"); return e ? atoi(e) : 1; }();
-  const size_t tiled_smem = (size_t)kCanvasSpan * Wi * sizeof(uint32_t);
-  if (kmax == 3 && taps && tiled_env && tiled_smem <= 160 * 1024) {
+  const size_t tiled_smem = (size_t)kCanvasSpan * (Wi * sizeof(uint32_t) + (size_t)Ws * Ctot);
+  if (kmax == 3 && taps && lut && tiled_env && tiled_smem <= 160 * 1024) {
     static DeviceOnce attr_once;
     if (attr_once.needed()) {
       PE_CUDA_CHECK(cudaFuncSetAttribute(stem_canvas_u8_tiled_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
       attr_once.mark();
     }
     stem_canvas_u8_tiled_kernel<<<dim3((unsigned)ceil_div(Hp, kCanvasRows), (unsigned)B), 256, tiled_smem, st>>>(frames, cv, Ctot, c0, C, Hs, Ws,
-                                                                                                         Hi, Wi, Hp, Wp, nrm, taps);
+                                                                                                         Hi, Wi, Hp, Wp, taps, lut);
   } else if (kmax == 0) stem_canvas_u8_kernel<0><<<grid, 256, 0, st>>>(frames, cv, B, Ctot, c0, C, Hs, Ws, Hi, Wi, Hp, Wp, nrm, nullptr);
   else if (kmax == 3) stem_canvas_u8_kernel<3><<<grid, 256, 0, st>>>(frames, cv, B, Ctot, c0, C, Hs, Ws, Hi, Wi, Hp, Wp, nrm, taps);
   else stem_canvas_u8_kernel<9><<<grid, 256, 0, st>>>(frames, cv, B, Ctot, c0, C, Hs, Ws, Hi, Wi, Hp, Wp, nrm, nullptr);

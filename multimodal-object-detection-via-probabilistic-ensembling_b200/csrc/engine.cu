@@ -152,7 +152,7 @@ void build_plan(pe_detector* d) {
   const int B = c.max_batch;
   const int passes = c.middle_fusion ? 2 : 1;
   d->add_buf("stem_canvas", B, c.canvas_h + 6, c.canvas_w + 8, 4, 2);
-  d->add_buf("pil_taps", 1, 1, c.canvas_h + c.canvas_w, 4, 4);  // Pillow resize tap tables (rows, then columns)
+  d->add_buf("pil_taps", 1, 1, c.canvas_h + c.canvas_w + 128, 4, 4);  // Pillow resize tap tables (rows, then columns) + 2 KB normalisation table
   d->add_buf("stem_out", B, d->H[0], d->W[0], 64, 2);
   d->add_buf("pool_out", B, d->H[1], d->W[1], 64, 2);
   d->add_buf("x0", B, d->H[1], d->W[1], 256, 2);
