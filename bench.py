@@ -474,7 +474,7 @@ def conv_roofline(rec, args, n_models_flops):
     # DRAM traffic + tensor-pipe activity of the same launches from the committed ncu --set full capture of one detector forward
     # at batch 16 (tools/ncu_conv_all.sh); null when the capture is not in the tree or the shape differs
     traffic, traffic_src, tensor_pipe = None, None, None
-    cap = os.path.join(ROOT, "profiles", "r02_conv_all_layers_b16_final_ncu_summary.csv")
+    cap = os.path.join(ROOT, "profiles", "r02_conv_all_layers_b16_final2_ncu_summary.csv")
     if os.path.isfile(cap) and rec["depth"] == 50 and rec["batch_per_gpu"] == 16 and len(rec["models"]) == 2:
         import csv
         rows = list(csv.DictReader(open(cap)))
@@ -483,7 +483,7 @@ def conv_roofline(rec, args, n_models_flops):
         tp = np.array([float(r["tensor_pipe_active_pct[%]"]) for r in rows])
         traffic = mb * 1e6 * 2
         tensor_pipe = float((us * tp).sum() / us.sum())
-        traffic_src = "profiles/r02_conv_all_layers_b16_final_ncu_summary.csv (%d GEMM launches of one detector at batch 16) x 2 detectors" % len(rows)
+        traffic_src = "profiles/r02_conv_all_layers_b16_final2_ncu_summary.csv (%d GEMM launches of one detector at batch 16) x 2 detectors" % len(rows)
     return {"bound": "tensor", "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf,
             "traffic": traffic, "traffic_unit": "DRAM bytes per batch over the GEMM launches", "traffic_source": traffic_src,
             "tensor_pipe_active_pct_time_weighted": tensor_pipe,

@@ -1147,33 +1147,36 @@ __global__ void __launch_bounds__(224, kMinBlocks) roi_align_kernel(const RoiLev
   const bool separable = gw >= 1 && gh >= 1 && gw <= kRoiGmax && gh <= kRoiGmax;  // block-uniform
 
   if (separable) {
+    // Per-pixel weights of one axis from the bin's samples.  Lane i evaluates sample i ONCE (the reference's float expression
+    // with its IEEE division); the accumulation then walks the samples in the reference's order through shuffles - every lane
+    // used to re-evaluate all g samples plus the first and the last one (10 % of the kernel's instructions).
+    auto axis_weights = [&](float start, float bin, int p, int g, int size, int& first_lo, int& span) -> float {
+      const AxisSample mine = axis_sample(start, bin, p, lane < g ? lane : g - 1, g, size);
+      const unsigned valid = __ballot_sync(kFullMask, mine.valid != 0);
+      first_lo = __shfl_sync(kFullMask, mine.lo, 0);
+      span = __shfl_sync(kFullMask, mine.hi, g - 1) - first_lo + 1;
+      float w = 0.f;
+      for (int i = 0; i < g; ++i) {
+        const int lo = __shfl_sync(kFullMask, mine.lo, i), hi = __shfl_sync(kFullMask, mine.hi, i);
+        const float fr = __shfl_sync(kFullMask, mine.frac, i);
+        if (!((valid >> i) & 1u)) continue;
+        if (lo == first_lo + lane) w += 1.f - fr;
+        if (hi == first_lo + lane) w += fr;
+      }
+      return w;
+    };
     // x weights of bin column pw: warp pw builds them (lane c <-> column x0 + c)
     {
       const int pw = ph;
-      const AxisSample first = axis_sample(rsw, bin_w, pw, 0, gw, W), last = axis_sample(rsw, bin_w, pw, gw - 1, gw, W);
-      const int x0 = first.lo, nx = last.hi - first.lo + 1;
-      float wx = 0.f;
-      for (int ix = 0; ix < gw; ++ix) {
-        const AxisSample ax = axis_sample(rsw, bin_w, pw, ix, gw, W);
-        if (!ax.valid) continue;
-        if (ax.lo == x0 + lane) wx += 1.f - ax.frac;
-        if (ax.hi == x0 + lane) wx += ax.frac;
-      }
+      int x0, nx;
+      const float wx = axis_weights(rsw, bin_w, pw, gw, W, x0, nx);
       if (lane < nx && lane < kRoiGmax + 2) s_wx[pw][lane] = wx;
       if (lane == 0) { s_x0[pw] = x0; s_nx[pw] = nx < kRoiGmax + 2 ? nx : kRoiGmax + 2; }
     }
     // y weights of this warp's bin row (lane r <-> row y0 + r), kept in registers
-    const AxisSample yfirst = axis_sample(rsh, bin_h, ph, 0, gh, H), ylast = axis_sample(rsh, bin_h, ph, gh - 1, gh, H);
-    const int y0 = yfirst.lo;
-    int ny = ylast.hi - yfirst.lo + 1;
+    int y0, ny;
+    const float wy = axis_weights(rsh, bin_h, ph, gh, H, y0, ny);
     if (ny > kRoiGmax + 2) ny = kRoiGmax + 2;
-    float wy = 0.f;
-    for (int iy = 0; iy < gh; ++iy) {
-      const AxisSample ay = axis_sample(rsh, bin_h, ph, iy, gh, H);
-      if (!ay.valid) continue;
-      if (ay.lo == y0 + lane) wy += 1.f - ay.frac;
-      if (ay.hi == y0 + lane) wy += ay.frac;
-    }
     if (lane == 0) s_ny[ph] = ny;
     __syncthreads();
     // ---- fast column sweep (the usual case: <= 6 feature rows per bin row, bin ends strictly increasing) ------------------
@@ -1833,6 +1836,7 @@ int launch_roi_align(const RoiLevels& fl, const float4* props, const int* prop_c
   const size_t ring_bytes = (size_t)7 * kRoiRingSlots * 32 * sizeof(uint4);
   __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(out);
   if (async_env && occ >= 4) roi_align_kernel<4, true><<<grid, 224, ring_bytes, st>>>(fl, props, prop_count, B, max_props, C, o);
+  else if (async_env && occ == 2) roi_align_kernel<2, true><<<grid, 224, ring_bytes, st>>>(fl, props, prop_count, B, max_props, C, o);
   else if (async_env) roi_align_kernel<3, true><<<grid, 224, ring_bytes, st>>>(fl, props, prop_count, B, max_props, C, o);
   else if (occ == 3) roi_align_kernel<3, false><<<grid, 224, 0, st>>>(fl, props, prop_count, B, max_props, C, o);
   else roi_align_kernel<2, false><<<grid, 224, 0, st>>>(fl, props, prop_count, B, max_props, C, o);
