@@ -167,10 +167,12 @@ def fusion_regime(D, images, models, mean_dets, method, steps, warmup, e2e=True,
            "detections_per_pair": N / B, "models": models,
            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": achieved / peaks["hbm_gbs"],
                         "traffic": None, "peak_kind": peak_kind, "algorithmic_bytes_per_launch": alg,
-                        "kernel": "fuse_block_kernel" if N / B / 1 > 32 else "fuse_packed_kernel",
+                        "kernel": "fuse_block_kernel" if N / B > 256 else ("fuse_mid_kernel" if N / B > 32 else "fuse_packed_kernel"),
                         "note": ("%.0f detections per pair: n/4 = %.0f pair-flops per byte, the ALU-bound regime of SURVEY.md §8d (> 40 "
                                  "detections); the HBM fraction is reported for completeness" % (N / B, N / B / 4)) if N / B > 40 else
                                 "HBM-bound regime by arithmetic intensity (SURVEY.md §8d); measured instruction-issue bound"}}
+    if N / B > 40:  # the ALU-bound regime: IoU decisions per second (every unordered pair once)
+        rec["pair_evaluations_per_s"] = rec["value"] * (N / B) * (N / B - 1) / 2
     if e2e:
         host_in = {k: torch.from_numpy(packed[k]).pin_memory() for k in ("boxes", "scores", "classes", "probs", "vars", "offsets")}
         e2e_dev = {k: torch.empty_like(v, device=D.dev) for k, v in host_in.items()}
@@ -564,7 +566,7 @@ def run_pairs(args, D):
                 extra[wl] = r
         method = (args.score_fusion, args.box_fusion)
         fus = {}
-        for tag, md, force in (("5_dets_per_model", 5.0, None), ("7.5_dets_per_model", 7.5, None), ("100_dets_per_model_block_kernel", None, 100)):
+        for tag, md, force in (("5_dets_per_model", 5.0, None), ("7.5_dets_per_model", 7.5, None), ("100_dets_per_model_mid_kernel", None, 100)):
             n_img = (1 << 18) if force is None else (1 << 13)
             r = fusion_regime(D, n_img, 2, md, method, 10, 3, e2e=False, force_count=force)
             r.pop("_window", None)
