@@ -1135,7 +1135,7 @@ int conv2d_launch(const pe_conv_desc& d, const void* x, const void* w, const flo
   // (res2: 64 -> 64 channels, 72 KB of weights; 80 -> 67 us per 8 frames); with streamed weights the fabric traffic is
   // dominated by the weight tiles and the shorter operand queue costs more than the saved A re-reads.
   const bool halo = halo_env && d.KH == 3 && d.stride == 1 && !d.out_fp32 && !d.residual_mode && d.Cin % 64 == 0 && d.Cout % 64 == 0 &&
-                    (halo_env > 1 || (d.Cin <= 64 && d.Cout <= 64));
+                    (halo_env > 1 || (d.Cin <= 64 && d.Cout <= 64)) && !(ch && ch->w);  // chained layers use the generic operand pipeline
   if (halo) { a.TH = kHaloTH; a.TW = kHaloTW; }
   a.tiles_h = ceil_div(a.Ho, a.TH);
   a.tiles_w = ceil_div(a.Wo, a.TW);
