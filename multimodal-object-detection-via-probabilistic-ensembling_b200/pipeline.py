@@ -64,7 +64,8 @@ class FusedOutput:
 class ProbEnPipeline:
     """``detectors``: list of M ``Detector`` objects (same num_classes); model order = fusion order."""
 
-    def __init__(self, detectors, method=("probEn", "v-avg"), iou_thr=0.5, frame_size=(512, 640), concurrent=True, out_storage=None):
+    def __init__(self, detectors, method=("probEn", "v-avg"), iou_thr=0.5, frame_size=(512, 640), concurrent=True, out_storage=None,
+                 stagger=None):
         self.lib = _lib.load()
         self.detectors = list(detectors)
         self.M = len(self.detectors)
@@ -90,7 +91,10 @@ class ProbEnPipeline:
         # stagger between the model streams: model m + 1 starts once model m has launched ``stagger`` kernels (canvas staging, stem,
         # max-pool and the first res2 layers: ~0.5 ms), so the detectors never reach their latency-bound stages (RPN top-k / NMS /
         # merge: ~0.35 ms on a few CTAs) together and each of them runs under the other model's GEMMs.  0 = start together.
-        self.stagger = int(os.environ.get("PE_PIPE_STAGGER", "0")) if self.streams is not None else 0
+        # measured on B200 (profiles/r02_pipeline_stagger_sweep.txt): every offset is slower than starting together, hence 0
+        if stagger is None:
+            stagger = int(os.environ.get("PE_PIPE_STAGGER", "0"))
+        self.stagger = int(stagger) if self.streams is not None else 0
         self.ev_stagger = [torch.cuda.Event() for _ in range(self.M - 1)] if self.stagger else []
         for e in self.ev_stagger:
             e.record()  # creates the handle the engine records on
