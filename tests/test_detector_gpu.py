@@ -73,6 +73,45 @@ def test_roi_align_matches_torchvision(small_case):
         assert tail.numel() == 0 or float(tail.abs().max()) == 0.0
 
 
+def test_roi_align_box_families(small_case):
+    """Every sweep of the fused ROIAlign kernel against torchvision on hand-made boxes: thin / tiny boxes (bins narrower than a
+    pixel: the small-ROI path with its 4 + 3 bin passes, 2..6 rows per bin row), anchor-sized boxes (fast path, 3..6 rows), boxes
+    hanging over the image border (clamped samples), very large boxes (adaptive grids > 8: sample-by-sample path)."""
+    sd, cfg, imgs, res, inter = small_case
+    feats = [inter["features"]["p%d" % l] for l in (2, 3, 4, 5)]
+    feats_bf = [f.permute(0, 2, 3, 1).contiguous().bfloat16().cuda() for f in feats]
+    feats_rounded = [f.float().cpu().permute(0, 3, 1, 2).contiguous() for f in feats_bf]
+    g = torch.Generator().manual_seed(77)
+    H, W = 200.0, 250.0
+
+    def fam(n, wlo, whi, hlo, hhi, over=0.0):
+        w = wlo + (whi - wlo) * torch.rand(n, generator=g)
+        h = hlo + (hhi - hlo) * torch.rand(n, generator=g)
+        cx = torch.rand(n, generator=g) * (W + 2 * over) - over
+        cy = torch.rand(n, generator=g) * (H + 2 * over) - over
+        return torch.stack([cx - w / 2, cy - h / 2, cx + w / 2, cy + h / 2], 1)
+
+    fams = [fam(150, 3, 12, 20, 90), fam(150, 20, 90, 3, 12), fam(100, 2, 9, 2, 9), fam(150, 24, 48, 24, 48),
+            fam(100, 50, 120, 50, 120), fam(80, 30, 80, 30, 80, over=30.0), fam(40, 180, 250, 150, 200)]
+    allb = torch.cat(fams).clamp(min=-40.0, max=290.0)
+    boxes = [allb, allb.flip(0)[:500]]
+    props = torch.zeros((2, 1000, 4))
+    counts = torch.tensor([len(b) for b in boxes], dtype=torch.int32)
+    for n, b in enumerate(boxes):
+        props[n, : len(b)] = b
+    got = ops.roi_align_fpn(feats_bf, props.cuda(), counts.cuda()).float().cpu()
+    want = D.roi_pool(feats_rounded, boxes)
+    start = 0
+    for n, b in enumerate(boxes):
+        w = want[start:start + len(b)].permute(0, 2, 3, 1).reshape(len(b), 49, -1)
+        gt = got[n * 1000: n * 1000 + len(b)]
+        start += len(b)
+        err = (gt - w).abs()
+        bad = (err > 1e-3 + w.abs() * 2 ** -7).reshape(len(b), -1).any(1)
+        assert not bool(bad.any()), ("image %d: %d boxes off, first %s, max err %g" %
+                                     (n, int(bad.sum()), b[bad][0].tolist(), float(err.max())))
+
+
 def test_head_postprocess_matches_oracle(small_case):
     sd, cfg, imgs, res, inter = small_case
     K = 3
