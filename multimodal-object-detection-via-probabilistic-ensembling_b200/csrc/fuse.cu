@@ -9,8 +9,10 @@
 // regime: score>0.5 leaves tens), lane j <-> detection j; each lane loads its record with coalesced
 // loads (float4 box), the sort is rank-by-counting over warp shuffles, the greedy clustering walks
 // cluster heads with redux.sync min + ballot, members are folded into their head with shuffles.
-// Images with 33..1024 detections are appended to a work list and handled by a block-per-image kernel
-// that stages the records in shared memory and materialises the suppression bitmask there.
+// Images with 33..256 detections (the detector pipeline: 100 per model) go to a work list handled by
+// fuse_mid_kernel (thread per detection, symmetric pair circle, bit fixed-point clustering, several
+// blocks per SM); 257..1024 detections take the block-per-image kernel that materialises the full
+// suppression bitmask in shared memory and walks the heads serially.
 //
 // Numerics: the reference works in float64 on float32-exact inputs.  Membership (iou > thr) is decided
 // in float32 and re-evaluated with the reference's exact float64 expression whenever the float32 margin
@@ -18,6 +20,7 @@
 // float64; probEn log/exp run in float32 with the background mass 1-sum(p) formed in float64 (its sign
 // drives the reference's NaN behaviour).
 #include <math.h>
+#include <stdlib.h>
 #include "common.cuh"
 
 namespace pe {
@@ -42,6 +45,7 @@ struct FuseArgs {
   float* out_scores;
   int* out_classes;
   int* out_counts;
+  int bucket;      // fuse_mid_kernel: walk same-class partners only (PE_FUSE_BUCKET, default 1)
   int* big_count;  // workspace[0]: images with 33..kMidDets detections, workspace[1]: larger ones
   int* big_list;   // workspace[4..4+B): medium images from the front, large images from the back
 };
@@ -722,6 +726,8 @@ __global__ void __launch_bounds__(kBlockThreads) fuse_mid_kernel(const FuseArgs 
   __shared__ unsigned s_mask[CAP][WMAX];
   __shared__ unsigned s_head[2][WMAX];
   __shared__ float s_red[kBlockThreads / 32];
+  __shared__ int s_wc[K + 1][kBlockThreads / 32], s_cq[CAP], s_flag[CAP], s_nflag;
+  __shared__ float s_ext[4][kBlockThreads / 32];
 
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   const bool nms_path = a.score_mode == PE_SCORE_MAX && a.box_mode == PE_BOX_ARGMAX;
@@ -800,9 +806,93 @@ __global__ void __launch_bounds__(kBlockThreads) fuse_mid_kernel(const FuseArgs 
       }
     }
     __syncthreads();
-    // ---- from here on thread i <-> rank i.  Pair matrix over the circle.
+    // ---- from here on thread i <-> rank i.
     const int i = tid;
-    if (act) {
+    // Class buckets: a match needs equal classes - different classes live in different offset tiles (demo_probEn.py:100-105) and
+    // can only meet through the +1 border, which takes a box reaching the far corner of its tile and one starting at the near
+    // corner of the next (the reference's legacy areas give such degenerate pairs a non-zero overlap).  So every thread walks the
+    // circle of ITS CLASS only (K = 3: a third of the pair evaluations), and the rare corner-reaching / corner-starting boxes are
+    // collected in a list and tested against each other with the reference's cross-class expression: the set of pairs that can
+    // pass `w > -0.01 && h > -0.01` is a subset of (flagged x flagged), every other cross-class pair has an empty intersection.
+    bool bucketed = false;
+    if (a.bucket) {  // block-uniform
+      const int mycls = act ? s_cls[i] : -1;
+      const int cb = (mycls >= 0 && mycls < K) ? mycls : K;  // bucket K: class ids outside [0, K) -> no bucketing for this image
+      int mypos = 0;
+#pragma unroll
+      for (int c = 0; c <= K; ++c) {
+        const unsigned bal = __ballot_sync(kFullMask, act && cb == c);
+        if (cb == c) mypos = __popc(bal & ((1u << lane) - 1u));
+        if (lane == 0) s_wc[c][wid] = __popc(bal);
+      }
+      const float4 mb = act ? s_mbox[i] : make_float4(INFINITY, INFINITY, -INFINITY, -INFINITY);
+      float mnx = mb.x, mny = mb.y, mxz = mb.z, mxw = mb.w;
+#pragma unroll
+      for (int sft = 16; sft > 0; sft >>= 1) {
+        mnx = fminf(mnx, __shfl_xor_sync(kFullMask, mnx, sft)); mny = fminf(mny, __shfl_xor_sync(kFullMask, mny, sft));
+        mxz = fmaxf(mxz, __shfl_xor_sync(kFullMask, mxz, sft)); mxw = fmaxf(mxw, __shfl_xor_sync(kFullMask, mxw, sft));
+      }
+      if (lane == 0) { s_ext[0][wid] = mnx; s_ext[1][wid] = mny; s_ext[2][wid] = mxz; s_ext[3][wid] = mxw; }
+      if (tid == 0) s_nflag = 0;
+      __syncthreads();
+      int cstart = 0, ccount = 0, other = 0;
+#pragma unroll
+      for (int c = 0; c <= K; ++c) {
+        int tot = 0;
+        for (int w = 0; w < kBlockThreads / 32; ++w) { const int v = s_wc[c][w]; if (c == cb && w < wid) mypos += v; tot += v; }
+        if (c < cb) cstart += tot;
+        if (c == cb) ccount = tot;
+        if (c == K) other = tot;
+      }
+      bucketed = other == 0;  // block-uniform
+      if (bucketed) {
+        bool flagged = false;
+        if (act) {
+          s_cq[cstart + mypos] = i;
+          if (!nms_path) {
+            for (int w = 0; w < kBlockThreads / 32; ++w) {
+              mnx = fminf(mnx, s_ext[0][w]); mny = fminf(mny, s_ext[1][w]); mxz = fmaxf(mxz, s_ext[2][w]); mxw = fmaxf(mxw, s_ext[3][w]);
+            }
+            const float tw = a.img_w - 1.02f, th = a.img_h - 1.02f;  // the predicate's -0.01 plus float32 round-off slack
+            const bool fa = (mb.z - mnx > tw) && (mb.w - mny > th);   // can be the lower-class side of a border contact
+            const bool fb = (mxz - mb.x > tw) && (mxw - mb.y > th);   // ... the higher-class side
+            flagged = fa || fb;
+            if (flagged) s_flag[atomicAdd(&s_nflag, 1)] = i;
+          }
+        }
+        __syncthreads();
+        if (act) {
+          const float4 hb = s_mbox[i];
+          const float ha = s_area[i];
+          const int hc = s_cls[i];
+          const int half_c = ccount >> 1, cend = cstart + ccount;
+          int pos = cstart + mypos;
+          for (int d = 1; d <= half_c; ++d) {
+            pos = pos + 1 == cend ? cstart : pos + 1;
+            const int j = s_cq[pos];
+            const bool m = nms_path ? match_nms(hb, ha, s_mbox[j], s_area[j], a.thr)
+                                    : match_bayes(hb, hc, ha, s_mbox[j], hc, s_area[j], a.img_w, a.img_h, a.thr);
+            if (m) {
+              atomicOr(&s_mask[i][j >> 5], 1u << (j & 31));
+              atomicOr(&s_mask[j][i >> 5], 1u << (i & 31));
+            }
+          }
+          if (flagged) {
+            const int nf = s_nflag;
+            for (int t = 0; t < nf; ++t) {
+              const int j = s_flag[t];
+              const int cc = s_cls[j];
+              if (cc != hc && match_bayes(hb, hc, ha, s_mbox[j], cc, s_area[j], a.img_w, a.img_h, a.thr)) {
+                atomicOr(&s_mask[i][j >> 5], 1u << (j & 31));
+                atomicOr(&s_mask[j][i >> 5], 1u << (i & 31));
+              }
+            }
+          }
+        }
+      }
+    }
+    // Pair matrix over the circle of all detections (no bucketing: class ids outside [0, K), or PE_FUSE_BUCKET=0).
+    if (!bucketed && act) {
       const float4 hb = s_mbox[i];
       const float ha = s_area[i];
       const int hc = s_cls[i];
@@ -995,6 +1085,8 @@ extern "C" PE_API int pe_fuse_batch(const float* boxes, const float* scores, con
   a.out_scores = out_scores;
   a.out_classes = out_classes;
   a.out_counts = out_counts;
+  static const int bucket_env = [] { const char* e = getenv("PE_FUSE_BUCKET"); return e ? atoi(e) : 1; }();
+  a.bucket = bucket_env;
   a.big_count = reinterpret_cast<int*>(workspace);
   a.big_list = a.big_count + 4;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);

@@ -50,6 +50,35 @@ def test_block_kernels_match_oracle(M, per_model):
             pc.assert_same_detections(got[b], want, TOL, "M%d n%d %s/%s img %d" % (M, per_model, sm, bm, b))
 
 
+def test_mid_kernel_cross_class_border_contact():
+    """fuse_mid_kernel walks same-class partners only; boxes of DIFFERENT classes that touch through the +1 border of the
+    reference's class-offset tiles (a box ending at the far corner of its 640 x 512 tile, a box starting at the near corner of
+    the next: demo_probEn.py:100-123) must still be clustered as the reference does.  40+ detections per image so that the
+    block path runs; degenerate corner boxes of classes 0/1 and 1/2 plus near misses injected into both models."""
+    dets = synth.synth_model_detections(3, 2, seed=77, force_count=20)
+    images = [[synth.image_info(d, i) for d in dets] for i in range(3)]
+    extra = [  # (model, box, class, score)
+        (0, [640.0, 512.0, 640.0, 512.0], 0, 0.93), (1, [0.0, 0.0, 0.0, 0.0], 1, 0.81),          # IoU 1 through the border
+        (0, [639.5, 511.5, 640.0, 512.0], 1, 0.77), (1, [0.0, 0.0, 0.25, 0.25], 2, 0.66),        # overlap 1 px^2, IoU < 0.5
+        (1, [638.0, 510.0, 640.0, 512.0], 0, 0.71), (0, [0.0, 0.0, 1.0, 1.0], 2, 0.62),          # class gap 2: tiles not adjacent
+        (0, [0.0, 0.0, 640.0, 512.0], 1, 0.58), (1, [0.0, 0.0, 640.0, 512.0], 2, 0.57),          # full-frame boxes: both flags
+    ]
+    for infos in images:
+        for m, box, cls, score in extra:
+            p = [(1.0 - score) / 3.0] * 3
+            p[cls] = score
+            infos[m]["bbox"].append(box); infos[m]["score"].append(score); infos[m]["class"].append(cls)
+            infos[m]["prob"].append(p); infos[m]["vars"].append([1.5])
+            if "class_logits" in infos[m]:
+                infos[m]["class_logits"].append([0.0] * 4)
+    for sm, bm in (("probEn", "v-avg"), ("avg", "s-avg"), ("max", "argmax")):
+        got = fusion.late_fusion_batch((sm, bm), images)
+        for b, infos in enumerate(images):
+            want = O.late_fusion_dispatch((sm, bm), infos)
+            assert len(infos[0]["bbox"]) + len(infos[1]["bbox"]) > 32
+            pc.assert_same_detections(got[b], want, TOL, "border contact %s/%s img %d" % (sm, bm, b))
+
+
 def test_kaist_binary_form():
     """K = 1: rows [p, 1-p]; checked against the oracle's K-generic restatement."""
     rng = np.random.default_rng(9)
