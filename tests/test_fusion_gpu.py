@@ -79,6 +79,18 @@ def test_mid_kernel_cross_class_border_contact():
             pc.assert_same_detections(got[b], want, TOL, "border contact %s/%s img %d" % (sm, bm, b))
 
 
+@pytest.mark.parametrize("per_model", [30, 100])
+def test_block_kernel_binary_form(per_model):
+    """K = 1 (KAIST: one class, rows [p, 1 - p]) through fuse_mid_kernel<1> at 60 / 200 detections per image - the kaist32
+    workload of bench.py (100 detections per model)."""
+    dets = synth.synth_model_detections(2, 2, seed=500 + per_model, K=1, force_count=per_model)
+    images = [[synth.image_info(d, i) for d in dets] for i in range(2)]
+    for sm, bm in (("probEn", "v-avg"), ("avg", "avg"), ("max", "argmax")):
+        got = fusion.late_fusion_batch((sm, bm), images, K=1)
+        for b, infos in enumerate(images):
+            pc.assert_same_detections(got[b], O.late_fusion_dispatch((sm, bm), infos), TOL, "K1 n%d %s/%s img %d" % (per_model, sm, bm, b))
+
+
 def test_kaist_binary_form():
     """K = 1: rows [p, 1-p]; checked against the oracle's K-generic restatement."""
     rng = np.random.default_rng(9)
