@@ -968,7 +968,7 @@ __device__ __forceinline__ void roi_fast_sweep(const uint4* col0, uint4* dst0, c
 // a fourth block fits on the SM), and the consumer reads its own 16 bytes back (no cross-lane hand-off: cp.async.wait_group is
 // the only synchronisation).  The kernel is latency-bound (633 vs 800 us per 16 000 ROIs at 21 vs 14 resident warps with the
 // same instruction count); the arithmetic and its order are unchanged, so the outputs are bit-identical.
-constexpr int kRoiRingSlots = 12;  // 512-byte warp rows per warp: 6 KB per warp, 42 KB per block
+constexpr int kRoiRingSlots = 12;  // 512-byte warp rows per warp: 6 KB per warp, 42 KB per block (below the 48 KB a launch gets without opting in)
 
 __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
   asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gsrc) : "memory");

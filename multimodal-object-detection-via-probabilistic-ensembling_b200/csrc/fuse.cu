@@ -716,7 +716,7 @@ __global__ void __launch_bounds__(kBlockThreads) fuse_block_kernel(const FuseArg
 //     of a non-head is the earliest head that matches it, output position = number of earlier heads;
 //   * one thread per head folds its members (rank order, head last) from shared memory.
 template <int K>
-__global__ void __launch_bounds__(kBlockThreads) fuse_mid_kernel(const FuseArgs a) {
+__global__ void __launch_bounds__(kBlockThreads, 4) fuse_mid_kernel(const FuseArgs a) {
   constexpr int CAP = kMidDets, WMAX = kMidDets / 32;
   __shared__ float4 s_box[CAP], s_mbox[CAP];
   __shared__ float s_score[CAP], s_area[CAP], s_pmax[CAP], s_lg[K + 1][CAP];
